@@ -1,0 +1,319 @@
+// bayesn_capi.cu - extern "C" boundary of libbayesn_b200.so (see include/bayesn_b200.h).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bayesn_kernels.cuh"
+
+using namespace bayesn;
+
+struct bayesn_ctx {
+    int device = 0;
+    std::string err;
+    bool have_model = false, have_data = false;
+    int LP = 0, TP = 0, VPL = 0;
+    ModelDev M{};
+    DataDev D{};
+    std::vector<void*> owned;   // device allocations made by set_model
+    long long launches = 0;
+};
+
+namespace {
+
+int fail(bayesn_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define CU_CHECK(ctx, expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(ctx, -2, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+    } while (0)
+
+template <typename T>
+int upload(bayesn_ctx* ctx, const std::vector<T>& h, const T** out) {
+    void* d = nullptr;
+    CU_CHECK(ctx, cudaMalloc(&d, h.size() * sizeof(T)));
+    ctx->owned.push_back(d);
+    CU_CHECK(ctx, cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<const T*>(d);
+    return 0;
+}
+
+void free_owned(bayesn_ctx* ctx) {
+    for (void* p : ctx->owned) cudaFree(p);
+    ctx->owned.clear();
+}
+
+struct Combo { int LP, TP, VPL; };
+const Combo kCombos[] = {{6, 6, 1}, {9, 6, 2}, {11, 6, 2}, {10, 9, 3}, {12, 10, 4}};
+
+int ntile_for(int C) { return (C % WPB == 0) ? 1 : (C == 1 ? WPB : 2); }
+
+template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
+int launch_logp(bayesn_ctx* ctx, int C, const float* q, float* logp, float* grad, cudaStream_t st) {
+    const int ntile = ntile_for(C);
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ntile, RVFREE, STAGE);
+    const size_t bytes = (size_t)P.totalFloats * 4;
+    auto kern = logp_grad_kernel<LP, TP, VPL, RVFREE, STAGE>;
+    if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
+    CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    const long long units = (long long)ctx->D.N * C;
+    const unsigned grid = (unsigned)((units + WPB - 1) / WPB);
+    kern<<<grid, WPB * 32, bytes, st>>>(ctx->M, ctx->D, C, ntile, q, logp, grad);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
+int launch_nuts(bayesn_ctx* ctx, const NutsDev& cfg, const float* q0, float* samples, float* stats, float* info,
+                float* work, cudaStream_t st) {
+    const int C = cfg.num_chains;
+    const int ntile = ntile_for(C);
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ntile, RVFREE, STAGE);
+    const size_t bytes = (size_t)P.totalFloats * 4;
+    auto kern = nuts_kernel<LP, TP, VPL, RVFREE, STAGE>;
+    if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
+    CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    const long long units = (long long)ctx->D.N * C;
+    const unsigned grid = (unsigned)((units + WPB - 1) / WPB);
+    kern<<<grid, WPB * 32, bytes, st>>>(ctx->M, ctx->D, cfg, ntile, q0, samples, stats, info, work);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// compile-time dispatch over the supported (knots, parameter-vector) shapes
+template <typename F>
+int dispatch(bayesn_ctx* ctx, bool stage, F&& f) {
+    const bool rvfree = ctx->M.rv_mode != BAYESN_RV_FIXED;
+#define BAYESN_CASE(LPv, TPv, VPLv)                                                                   \
+    if (ctx->LP == LPv && ctx->TP == TPv && ctx->VPL == VPLv) {                                       \
+        if (rvfree) return stage ? f.template operator()<LPv, TPv, VPLv, true, true>()               \
+                                 : f.template operator()<LPv, TPv, VPLv, true, false>();             \
+        return stage ? f.template operator()<LPv, TPv, VPLv, false, true>()                           \
+                     : f.template operator()<LPv, TPv, VPLv, false, false>();                         \
+    }
+    BAYESN_CASE(6, 6, 1)
+    BAYESN_CASE(9, 6, 2)
+    BAYESN_CASE(11, 6, 2)
+    BAYESN_CASE(10, 9, 3)
+    BAYESN_CASE(12, 10, 4)
+#undef BAYESN_CASE
+    return fail(ctx, -4, "no kernel instantiation for this model shape");
+}
+
+struct LogpCall {
+    bayesn_ctx* ctx; int C; const float* q; float* logp; float* grad; cudaStream_t st;
+    template <int LP, int TP, int VPL, bool RV, bool ST>
+    int operator()() { return launch_logp<LP, TP, VPL, RV, ST>(ctx, C, q, logp, grad, st); }
+};
+struct NutsCall {
+    bayesn_ctx* ctx; NutsDev cfg; const float* q0; float* samples; float* stats; float* info; float* work;
+    cudaStream_t st;
+    template <int LP, int TP, int VPL, bool RV, bool ST>
+    int operator()() { return launch_nuts<LP, TP, VPL, RV, ST>(ctx, cfg, q0, samples, stats, info, work, st); }
+};
+
+// numpyro.infer.hmc_util.build_adaptation_schedule (Stan windows)
+std::vector<int> adaptation_window_ends(int num_steps) {
+    std::vector<int> ends;
+    if (num_steps <= 0) return ends;
+    if (num_steps < 20) { ends.push_back(num_steps - 1); return ends; }
+    int start_buffer = 75, end_buffer = 50, init_window = 25;
+    if (start_buffer + end_buffer + init_window > num_steps) {
+        start_buffer = (int)(0.15 * num_steps);
+        end_buffer = (int)(0.1 * num_steps);
+        init_window = num_steps - start_buffer - end_buffer;
+    }
+    ends.push_back(start_buffer - 1);
+    const int end_window_start = num_steps - end_buffer;
+    int next_size = init_window, next_start = start_buffer;
+    while (next_start < end_window_start) {
+        int cur_start = next_start, cur_size = next_size;
+        if (3 * cur_size <= end_window_start - cur_start) next_size = 2 * cur_size;
+        else cur_size = end_window_start - cur_start;
+        next_start = cur_start + cur_size;
+        ends.push_back(next_start - 1);
+    }
+    ends.push_back(num_steps - 1);
+    return ends;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bayesn_abi_version(void) { return 1; }
+
+int bayesn_ctx_create(int device, bayesn_ctx** out) {
+    if (!out) return -1;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || device < 0 || device >= n) return -2;
+    if (cudaSetDevice(device) != cudaSuccess) return -2;
+    bayesn_ctx* c = new bayesn_ctx();
+    c->device = device;
+    *out = c;
+    return 0;
+}
+
+void bayesn_ctx_destroy(bayesn_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    free_owned(ctx);
+    delete ctx;
+}
+
+const char* bayesn_last_error(bayesn_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+long long bayesn_launch_count(bayesn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int bayesn_param_dim(bayesn_ctx* ctx) { return (ctx && ctx->have_model) ? ctx->M.D : -1; }
+
+int bayesn_set_model(bayesn_ctx* ctx, const bayesn_model_desc* m) {
+    if (!ctx || !m) return -1;
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    const int L = m->L, T = m->T;
+    if (L < 3 || L > BAYESN_MAX_L || T < 2 || T > BAYESN_MAX_T) return fail(ctx, -1, "unsupported knot counts");
+    const int ne = (L - 2) * T;
+    const int n_sc = (m->rv_mode == BAYESN_RV_FIXED) ? 4 : 5;
+    const int D = ne + n_sc;
+    ctx->LP = 0;
+    for (const Combo& c : kCombos)
+        if (c.LP >= L && c.TP >= T && 32 * c.VPL >= D) { ctx->LP = c.LP; ctx->TP = c.TP; ctx->VPL = c.VPL; break; }
+    if (!ctx->LP) return fail(ctx, -4, "model shape not supported");
+    free_owned(ctx);
+    ctx->have_model = false;
+    const int LP = ctx->LP, TP = ctx->TP;
+    std::vector<float> Jl((size_t)LP * BP, 0.f), hs((size_t)NPH * BP, 0.f), Mf((size_t)9 * BP, 0.f), ad(BP, 0.f);
+    std::vector<float> W0((size_t)LP * TP, 0.f), W1((size_t)LP * TP, 0.f), KD((size_t)TP * TP, 0.f), tau(TP, 0.f);
+    std::vector<float> Ls((size_t)ne * ne), LsT((size_t)ne * ne);
+    for (int b = 0; b < NB; ++b) {
+        for (int l = 0; l < L; ++l) Jl[(size_t)l * BP + b] = m->J_l[(size_t)b * L + l];
+        for (int i = 0; i < NPH; ++i) hs[(size_t)i * BP + b] = m->hsiao[(size_t)b * NPH + i];
+        for (int j = 0; j < 9; ++j) Mf[(size_t)j * BP + b] = m->M_fitz[(size_t)b * 9 + j];
+        if (m->a_dust) ad[b] = m->a_dust[b];
+    }
+    for (int l = 0; l < L; ++l)
+        for (int t = 0; t < T; ++t) {
+            W0[(size_t)l * TP + t] = m->W0[(size_t)l * T + t];
+            W1[(size_t)l * TP + t] = m->W1[(size_t)l * T + t];
+        }
+    for (int a = 0; a < T; ++a) {
+        tau[a] = m->tau_knots[a];
+        for (int b = 0; b < T; ++b) KD[(size_t)a * TP + b] = m->KD_t[(size_t)a * T + b];
+    }
+    for (int i = 0; i < ne; ++i)
+        for (int j = 0; j < ne; ++j) {
+            Ls[(size_t)i * ne + j] = m->L_Sigma[(size_t)i * ne + j];
+            LsT[(size_t)j * ne + i] = m->L_Sigma[(size_t)i * ne + j];
+        }
+    ModelDev& M = ctx->M;
+    M = ModelDev{};
+    M.L = L; M.T = T; M.n_eps = ne; M.D = D; M.n_sc = n_sc; M.rv_mode = m->rv_mode;
+    M.fix_tmax = m->fix_tmax; M.fix_theta = m->fix_theta; M.fix_AV = m->fix_AV;
+    M.theta_val = m->theta_val; M.AV_val = m->AV_val;
+    M.inv_tauA = 1.f / m->tauA;
+    M.inv_sd2 = 1.f / (m->Ds_prior_sd * m->Ds_prior_sd);
+    M.RV = m->RV; M.mu_R = m->mu_R; M.sigma_R = m->sigma_R;
+    M.phi_alpha = (m->rv_mode == BAYESN_RV_POP)
+                      ? (float)(0.5 * erfc(-((double)m->trunc_R - m->mu_R) / m->sigma_R / sqrt(2.0))) : 0.f;
+    int rc = 0;
+    rc |= upload(ctx, Jl, &M.Jl);   rc |= upload(ctx, hs, &M.hs);   rc |= upload(ctx, Mf, &M.Mf);
+    rc |= upload(ctx, ad, &M.ad);   rc |= upload(ctx, W0, &M.W0);   rc |= upload(ctx, W1, &M.W1);
+    rc |= upload(ctx, KD, &M.KD);   rc |= upload(ctx, tau, &M.tau); rc |= upload(ctx, Ls, &M.Ls);
+    rc |= upload(ctx, LsT, &M.LsT);
+    if (rc) return rc;
+    ctx->have_model = true;
+    return 0;
+}
+
+int bayesn_bind_dataset(bayesn_ctx* ctx, const bayesn_dataset_desc* d) {
+    if (!ctx || !d) return -1;
+    if (d->N <= 0 || d->N_obs <= 0 || d->n_b <= 0) return fail(ctx, -1, "empty dataset");
+    if ((d->n_b * BP * 4) % 16 || ((uintptr_t)d->obs4 & 15) || ((uintptr_t)d->weights & 15))
+        return fail(ctx, -1, "dataset arrays must be 16-byte aligned");
+    DataDev& D = ctx->D;
+    D.N = d->N; D.N_obs = d->N_obs; D.n_b = d->n_b;
+    D.obs4 = reinterpret_cast<const float4*>(d->obs4);
+    D.n_valid = d->n_valid;
+    D.wt = d->weights;
+    D.sup = reinterpret_cast<const int2*>(d->support);
+    D.muhat = d->muhat;
+    D.lconst = d->lconst;
+    ctx->have_data = true;
+    return 0;
+}
+
+int bayesn_logp_grad_fit(bayesn_ctx* ctx, int n_chains, const float* q, float* logp, float* grad, void* stream) {
+    if (!ctx) return -1;
+    if (!ctx->have_model || !ctx->have_data) return fail(ctx, -1, "set_model and bind_dataset first");
+    if (n_chains < 1) return fail(ctx, -1, "n_chains must be >= 1");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    LogpCall call{ctx, n_chains, q, logp, grad, (cudaStream_t)stream};
+    return dispatch(ctx, /*stage=*/n_chains >= 2, call);
+}
+
+size_t bayesn_nuts_workspace_bytes(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg) {
+    if (!ctx || !cfg || !ctx->have_model || !ctx->have_data) return 0;
+    return (size_t)ctx->D.N * cfg->num_chains * nuts_num_vectors(cfg->max_tree_depth) * 32 * ctx->VPL * sizeof(float);
+}
+
+int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_init, float* samples, float* stats,
+                    float* chain_info, void* work, size_t work_bytes, void* stream) {
+    if (!ctx || !cfg) return -1;
+    if (!ctx->have_model || !ctx->have_data) return fail(ctx, -1, "set_model and bind_dataset first");
+    if (cfg->num_chains < 1 || cfg->num_samples < 1 || cfg->num_warmup < 0 || cfg->max_tree_depth < 1 ||
+        cfg->max_tree_depth > 12)
+        return fail(ctx, -1, "bad NUTS configuration");
+    if (work_bytes < bayesn_nuts_workspace_bytes(ctx, cfg)) return fail(ctx, -1, "workspace too small");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    NutsDev nd{};
+    nd.num_warmup = cfg->num_warmup; nd.num_samples = cfg->num_samples; nd.num_chains = cfg->num_chains;
+    nd.max_depth = cfg->max_tree_depth; nd.target_accept = cfg->target_accept; nd.init_step = cfg->init_step_size;
+    nd.adapt_step = cfg->adapt_step_size; nd.adapt_mass = cfg->adapt_mass_matrix;
+    nd.regularize = cfg->regularize_mass_matrix;
+    nd.seed_lo = (unsigned)(cfg->seed & 0xffffffffu); nd.seed_hi = (unsigned)(cfg->seed >> 32);
+    std::vector<int> ends = adaptation_window_ends(cfg->num_warmup);
+    if (ends.size() > 24) return fail(ctx, -1, "too many adaptation windows");
+    nd.n_windows = (int)ends.size();
+    for (size_t i = 0; i < 24; ++i) nd.win_end[i] = i < ends.size() ? ends[i] : 0x7fffffff;
+    NutsCall call{ctx, nd, q_init, samples, stats, chain_info, (float*)work, (cudaStream_t)stream};
+    return dispatch(ctx, /*stage=*/cfg->num_chains >= 2, call);
+}
+
+int bayesn_flux_batch(bayesn_ctx* ctx, int N, int N_obs, int n_b, int mag, float M0, const float* theta,
+                      const float* AV, const float* W0, const float* W1, const float* eps, const float* Ds,
+                      const float* RV, const int32_t* band_indices, const uint8_t* mask, const float* J_t,
+                      const float* hsiao_interp, const float* weights, const double* band_log10_scale, float* out,
+                      void* stream) {
+    if (!ctx) return -1;
+    if (!ctx->have_model) return fail(ctx, -1, "set_model first");
+    if (N <= 0 || N_obs <= 0) return 0;
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<double> bs(n_b);
+    for (int k = 0; k < n_b; ++k) bs[k] = band_log10_scale[k] * 3.321928094887362;   // -> log2
+    double* dbs = nullptr;
+    CU_CHECK(ctx, cudaMallocAsync((void**)&dbs, n_b * sizeof(double), st));
+    CU_CHECK(ctx, cudaMemcpyAsync(dbs, bs.data(), n_b * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_CHECK(ctx, cudaStreamSynchronize(st));   // bs is a host temporary
+    FluxArgs A{};
+    A.N = N; A.N_obs = N_obs; A.n_b = n_b; A.L = ctx->M.L; A.T = ctx->M.T; A.mag = mag; A.M0 = M0;
+    A.theta = theta; A.AV = AV; A.W0 = W0; A.W1 = W1; A.eps = eps; A.Ds = Ds; A.RV = RV;
+    A.band = band_indices; A.mask = mask; A.J_t = J_t; A.hsi = hsiao_interp; A.weights = weights;
+    A.bscale = dbs; A.Jl = ctx->M.Jl; A.hs = ctx->M.hs; A.Mf = ctx->M.Mf; A.LPs = ctx->LP; A.out = out;
+    const long long items = (long long)N * N_obs;
+    flux_kernel<<<(unsigned)((items + 3) / 4), 128, 0, st>>>(A);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    CU_CHECK(ctx, cudaFreeAsync(dbs, st));
+    return 0;
+}
+
+}  // extern "C"

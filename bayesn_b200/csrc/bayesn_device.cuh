@@ -1,0 +1,643 @@
+// bayesn_device.cuh - device code of the BayeSN hot path for sm_100a.
+//
+// One warp owns one (supernova, chain) pair.  The 32 lanes split the wavelength bins of the
+// band-pass integral; the per-observation sums (flux and the adjoint moments) are combined with
+// a transposed warp-shuffle reduction.  A CTA is 4 warps; the warps of a CTA that work on the
+// same supernova share its band-weight tile, which is staged in shared memory with a 1-D TMA
+// bulk copy (cp.async.bulk + mbarrier) together with the wavelength-spline matrix J_l.
+//
+// Math (reference bayesn/bayesn_model.py:556-709, :761-816, :909-945):
+//   W      = W0 + theta W1 + eps,   eps = reshape_F(L_Sigma eps_tform) with zero end rows
+//   u_o[l] = -c2 sum_m W[l][m] Jt_o[m]                     c2 = 0.4 log2(10)
+//   P_o[b] = w[k_o][b] H(t_o, b) 2^( sum_l J_l[b][l] u_o[l] - c2 A_V a[b] )
+//   flux_o = 2^(-c2 (Ds - muhat)) sum_b P_o[b]             (band scale folded into w)
+//   log L  = sum_o -((y_o - flux_o)/sigma_o)^2 / 2  + data constant
+// and the analytic reverse mode of it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "bayesn_b200.h"
+
+namespace bayesn {
+
+constexpr int NB = BAYESN_NBINS;
+constexpr int BP = BAYESN_BPAD;
+constexpr int NPH = BAYESN_NPHASE;
+constexpr int WPB = 4;                          // warps (= (SN, chain) units) per CTA
+constexpr float C2 = 1.3287712379549449f;       // 0.4 * log2(10)
+constexpr float KAPPA = 0.9210340371976184f;    // 0.4 * ln(10)
+constexpr float LN2 = 0.6931471805599453f;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct ModelDev {
+    int L, T, n_eps, D, n_sc, rv_mode;
+    int fix_tmax, fix_theta, fix_AV;
+    float theta_val, AV_val;
+    float inv_tauA, inv_sd2, RV, mu_R, sigma_R, phi_alpha;
+    const float* Jl;    // [LP][BP]  wavelength spline matrix, knot-major
+    const float* hs;    // [NPH][BP] Hsiao template, phase-major
+    const float* Mf;    // [9][BP]   F99 spline basis
+    const float* ad;    // [BP]      dust basis for the fixed global RV
+    const float* W0;    // [LP*TP]
+    const float* W1;    // [LP*TP]
+    const float* KD;    // [TP*TP]
+    const float* tau;   // [TP]
+    const float* Ls;    // [n_eps][n_eps] row-major L_Sigma
+    const float* LsT;   // [n_eps][n_eps] its transpose
+};
+
+struct DataDev {
+    int N, N_obs, n_b;
+    const float4* obs4;     // [N][N_obs]
+    const int* n_valid;     // [N]
+    const float* wt;        // [N][n_b][BP]
+    const int2* sup;        // [N][n_b]
+    const float* muhat;     // [N]
+    const float* lconst;    // [N]
+};
+
+struct NutsDev {
+    int num_warmup, num_samples, num_chains, max_depth;
+    float target_accept, init_step;
+    int adapt_step, adapt_mass, regularize;
+    unsigned seed_lo, seed_hi;
+    int n_windows;
+    int win_end[24];
+};
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// Transposed reduction of 16 per-lane partials: 16 shuffles instead of 80.  On return every
+// lane holds the warp total of value index (lane >> 1).
+__device__ __forceinline__ float treduce16(float (&v)[16], int lane) {
+    bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float send = up ? v[i] : v[i + 8];
+        float keep = up ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(FULL, send, 16);
+    }
+    up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float send = up ? v[i] : v[i + 4];
+        float keep = up ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+    up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float send = up ? v[i] : v[i + 2];
+        float keep = up ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+    up = lane & 2;
+    {
+        float send = up ? v[0] : v[1];
+        float keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+    v[0] += __shfl_xor_sync(FULL, v[0], 1);
+    return v[0];
+}
+
+// mbarrier + 1-D TMA bulk copy (global -> shared)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// Philox4x32-10 counter RNG (Salmon et al. 2011): the same stream is reproduced on the CPU by
+// oracle/ref_nuts.py so that GPU and oracle trajectories can be compared draw for draw.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }  // [0,1)
+
+// ------------------------------------------------------------------------------------------
+// shared-memory plan
+// ------------------------------------------------------------------------------------------
+template <int LP, int TP>
+struct Dims {
+    static constexpr int LP4 = (LP + 3) & ~3;
+    static constexpr int UST = 2 * LP4;                 // floats per observation in the u / du buffer
+    static constexpr int NPAIR = (LP * TP + 31) / 32;   // (l, m) pairs per lane
+};
+
+struct SmemPlan {
+    // CTA-shared (float offsets)
+    int oJl, oAd, oMf, oW0, oW1, oKD, oTau, oWt, oSup, oObs, oBar;
+    int oWarp, warpStride;     // per-warp region
+    // inside the per-warp region
+    int wWs, wEv, wEps, wUs, wJts, wOf, wOi, wAd, wDad;
+    int totalFloats;
+};
+
+__host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b, int N_obs, int ntile, bool rvfree,
+                                              bool stage) {
+    SmemPlan p;
+    int LP4 = (LP + 3) & ~3, UST = 2 * LP4;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+    p.oJl = take(LP * BP);
+    p.oAd = take(rvfree ? 0 : BP);
+    p.oMf = take(rvfree ? 9 * BP : 0);
+    p.oW0 = take(LP * TP);
+    p.oW1 = take(LP * TP);
+    p.oKD = take(TP * TP);
+    p.oTau = take(TP);
+    p.oWt = take(stage ? ntile * n_b * BP : 0);
+    p.oSup = take(ntile * n_b * 2);
+    p.oObs = take(ntile * N_obs * 4);
+    p.oBar = take(4);
+    p.oWarp = o;
+    int w = 0;
+    auto wtake = [&](int n) { int r = w; w += (n + 3) & ~3; return r; };
+    p.wWs = wtake(LP * TP);
+    p.wEv = wtake(n_eps);
+    p.wEps = wtake(n_eps);
+    p.wUs = wtake(N_obs * UST);
+    p.wJts = wtake(N_obs * TP);
+    p.wOf = wtake(N_obs);
+    p.wOi = wtake(N_obs);
+    p.wAd = wtake(rvfree ? BP : 0);
+    p.wDad = wtake(rvfree ? BP : 0);
+    p.warpStride = w;
+    p.totalFloats = o + WPB * w;
+    return p;
+}
+
+// Everything one warp needs to evaluate log p and its gradient.
+struct WarpCtx {
+    const float *sJl, *sAd, *sMf, *sW0, *sW1, *sKD, *sTau;
+    const float* wt;      // this SN's weight tile (shared or global)
+    const int2* sup;      // this SN's band supports (shared)
+    const float4* obs;    // this SN's observations (shared)
+    float *Ws, *ev, *eps, *us, *Jts, *of, *wad, *wdad;
+    int* oi;
+    int nobs;
+    float muhat, lconst;
+};
+
+// ------------------------------------------------------------------------------------------
+// time-spline row and its derivative (reference spline_coeffs_irr_step, :761-816)
+// ------------------------------------------------------------------------------------------
+template <int TP>
+__device__ __forceinline__ void spline_row(float t, int T, const float* tau, const float* KD, float (&J)[TP],
+                                           float (&dJ)[TP]) {
+    const float tl = tau[T - 1], tf = tau[0];
+    int q;
+    float a, b, c, d, da, dc, dd;   // row = a e_q + b e_{q+1} + c KD[q] + d KD[q+1]
+    if (t > tl) {
+        q = T - 2;
+        float h = tl - tau[T - 2];
+        a = (tl - t) / h;
+        b = 1.f - a;
+        c = (t - tl) * h * (1.f / 6.f);
+        d = 0.f;
+        da = -1.f / h;
+        dc = h * (1.f / 6.f);
+        dd = 0.f;
+    } else if (t < tf) {
+        q = 0;
+        float h = tau[1] - tf;
+        b = (t - tf) / h;
+        a = 1.f - b;
+        c = 0.f;
+        d = -(t - tf) * h * (1.f / 6.f);
+        da = -1.f / h;
+        dc = 0.f;
+        dd = -h * (1.f / 6.f);
+    } else {
+        q = 0;
+#pragma unroll
+        for (int m = 1; m < TP - 1; ++m)
+            if (m < T - 1 && tau[m] <= t) q = m;
+        float h = tau[q + 1] - tau[q];
+        a = (tau[q + 1] - t) / h;
+        b = 1.f - a;
+        float h2 = h * h * (1.f / 6.f);
+        c = (a * a * a - a) * h2;
+        d = (b * b * b - b) * h2;
+        da = -1.f / h;
+        dc = -(3.f * a * a - 1.f) * h * (1.f / 6.f);
+        dd = (3.f * b * b - 1.f) * h * (1.f / 6.f);
+    }
+    const float* k0 = KD + q * TP;
+    const float* k1 = KD + (q + 1) * TP;
+#pragma unroll
+    for (int m = 0; m < TP; ++m) {
+        float v = fmaf(c, k0[m], d * k1[m]);
+        float dv = fmaf(dc, k0[m], dd * k1[m]);
+        if (m == q) { v += a; dv += da; }
+        if (m == q + 1) { v += b; dv -= da; }
+        J[m] = v;
+        dJ[m] = dv;
+    }
+}
+
+// element i of a lane-strided vector (element i lives in lane i%32, slot i/32), broadcast
+template <int VPL>
+__device__ __forceinline__ float vget(const float (&v)[VPL], int i) {
+    float x = v[0];
+#pragma unroll
+    for (int s = 1; s < VPL; ++s)
+        if ((i >> 5) == s) x = v[s];
+    return __shfl_sync(FULL, x, i & 31);
+}
+
+// ------------------------------------------------------------------------------------------
+// log p and gradient for one (SN, chain): the unit of work of one leapfrog step
+// ------------------------------------------------------------------------------------------
+template <int LP, int TP, int VPL, bool RVFREE>
+__device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx& c, const float* __restrict__ hs,
+                                               const float (&q)[VPL], float& logp_out, float (&grad)[VPL], int lane) {
+    using DM = Dims<LP, TP>;
+    constexpr int LP4 = DM::LP4, UST = DM::UST, NPAIR = DM::NPAIR;
+    const int L = M.L, T = M.T, ne = M.n_eps;
+
+    // ---- scalars ------------------------------------------------------------------------
+    const float theta_s = vget<VPL>(q, ne + 0);
+    const float uAV = vget<VPL>(q, ne + 1);
+    const float ut = vget<VPL>(q, ne + 2);
+    const float Ds = vget<VPL>(q, ne + 3);
+    const float AV_s = expf(uAV);
+    const float sg = 1.f / (1.f + expf(-ut));
+    const float tmax_s = -10.f + 20.f * sg;
+    const float theta = M.fix_theta ? M.theta_val : theta_s;
+    const float AV = M.fix_AV ? M.AV_val : AV_s;
+    const float tmax = M.fix_tmax ? 0.f : tmax_s;
+    float RVv = M.RV, dRV_du = 0.f, sgR = 0.f;
+    if (RVFREE) {
+        const float uR = vget<VPL>(q, ne + 4);
+        sgR = 1.f / (1.f + expf(-uR));
+        if (M.rv_mode == BAYESN_RV_UNIFORM) {
+            RVv = 1.f + 5.f * sgR;
+            dRV_du = 5.f * sgR * (1.f - sgR);
+        } else {
+            float pp = M.phi_alpha + sgR * (1.f - M.phi_alpha);
+            float z = normcdfinvf(pp);
+            RVv = M.mu_R + M.sigma_R * z;
+            float pdf = 0.3989422804014327f * expf(-0.5f * z * z);
+            dRV_du = M.sigma_R * (1.f - M.phi_alpha) * sgR * (1.f - sgR) / pdf;
+        }
+    }
+    const float AVc = -C2 * AV;
+    const float S = exp2f(-C2 * (Ds - c.muhat));
+
+    // ---- eps = L_Sigma eps_tform, W = W0 + theta W1 + eps ---------------------------------
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+        int i = lane + 32 * s;
+        if (i < ne) c.ev[i] = q[s];
+    }
+    __syncwarp();
+    for (int i = lane; i < ne; i += 32) {
+        float acc = 0.f;
+        const float* col = M.LsT + i;
+        for (int j = 0; j < ne; ++j) acc = fmaf(__ldg(col + j * ne), c.ev[j], acc);
+        c.eps[i] = acc;
+    }
+    __syncwarp();
+    for (int p = lane; p < LP * TP; p += 32) {
+        int l = p / TP, m = p - l * TP;
+        float w = 0.f;
+        if (l < L && m < T) {
+            w = fmaf(theta, c.sW1[p], c.sW0[p]);
+            if (l >= 1 && l <= L - 2) w += c.eps[(l - 1) + (L - 2) * m];
+        }
+        c.Ws[p] = w;
+    }
+    const float* adv = c.sAd;
+    if (RVFREE) {
+        // per-chain dust basis a[b] = 1 + (M_fitz yk(RV))/RV and its RV derivative (reference :604-625)
+        float yk[9], dyk[9];
+        {
+            const float R = RVv, R2 = R * R, R3 = R2 * R;
+            const float c2f = -0.824f + 4.717f / R, c1f = 2.030f - 3.007f * c2f;
+            const float dc2 = -4.717f / R2, dc1 = -3.007f * dc2;
+            const float x7 = 1e4f / 2700.f, x8 = 1e4f / 2600.f, x0 = 4.596f, gm = 0.99f;
+            const float d1 = x7 * x7 / ((x7 * x7 - x0 * x0) * (x7 * x7 - x0 * x0) + gm * gm * x7 * x7);
+            const float d2 = x8 * x8 / ((x8 * x8 - x0 * x0) * (x8 * x8 - x0 * x0) + gm * gm * x8 * x8);
+            yk[0] = -R;                                   dyk[0] = -1.f;
+            yk[1] = 0.26469f * R / 3.1f - R;              dyk[1] = 0.26469f / 3.1f - 1.f;
+            yk[2] = 0.82925f * R / 3.1f - R;              dyk[2] = 0.82925f / 3.1f - 1.f;
+            yk[3] = -0.422809f + 0.00270f * R + 2.13572e-4f * R2;     dyk[3] = 0.00270f + 2.f * 2.13572e-4f * R;
+            yk[4] = -5.13540e-2f + 0.00216f * R - 7.35778e-5f * R2;   dyk[4] = 0.00216f - 2.f * 7.35778e-5f * R;
+            yk[5] = 0.700127f + 0.00184f * R - 3.32598e-5f * R2;      dyk[5] = 0.00184f - 2.f * 3.32598e-5f * R;
+            yk[6] = 1.19456f + 0.01707f * R - 5.46959e-3f * R2 + 7.97809e-4f * R3 - 4.45636e-5f * R2 * R2;
+            dyk[6] = 0.01707f - 2.f * 5.46959e-3f * R + 3.f * 7.97809e-4f * R2 - 4.f * 4.45636e-5f * R3;
+            yk[7] = c1f + c2f * x7 + 3.23f * d1;          dyk[7] = dc1 + dc2 * x7;
+            yk[8] = c1f + c2f * x8 + 3.23f * d2;          dyk[8] = dc1 + dc2 * x8;
+        }
+        const float iR = 1.f / RVv;
+        for (int b = lane; b < BP; b += 32) {
+            float my = 0.f, dmy = 0.f;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                float mf = c.sMf[j * BP + b];
+                my = fmaf(mf, yk[j], my);
+                dmy = fmaf(mf, dyk[j], dmy);
+            }
+            c.wad[b] = 1.f + my * iR;
+            c.wdad[b] = (dmy - my * iR) * iR;
+        }
+        adv = c.wad;
+    }
+    __syncwarp();
+
+    // ---- per-observation setup, lanes over observations -------------------------------------
+    for (int o = lane; o < c.nobs; o += 32) {
+        float t = c.obs[o].x - tmax;
+        float J[TP], dJ[TP];
+        spline_row<TP>(t, T, c.sTau, c.sKD, J, dJ);
+#pragma unroll
+        for (int m = 0; m < TP; ++m) c.Jts[o * TP + m] = J[m];
+#pragma unroll
+        for (int l = 0; l < LP4; ++l) {
+            float u = 0.f, du = 0.f;
+            if (l < LP) {
+#pragma unroll
+                for (int m = 0; m < TP; ++m) {
+                    float w = c.Ws[l * TP + m];
+                    u = fmaf(w, J[m], u);
+                    du = fmaf(w, dJ[m], du);
+                }
+            }
+            c.us[o * UST + l] = -C2 * u;
+            c.us[o * UST + LP4 + l] = -C2 * du;
+        }
+        float fl = floorf(t);
+        int i0 = 19 + (int)fl, i1 = 19 + (int)ceilf(t);
+        i0 = min(max(i0, 0), NPH - 1);
+        i1 = min(max(i1, 0), NPH - 1);
+        c.of[o] = t - fl;
+        c.oi[o] = i0 | (i1 << 8);
+    }
+    __syncwarp();
+
+    // ---- band-pass integrals, lanes over wavelength bins --------------------------------------
+    float logL = 0.f, gDs = 0.f, gAV = 0.f, gT = 0.f, gRV = 0.f;
+    for (int o = 0; o < c.nobs; ++o) {
+        const float4 ob = c.obs[o];
+        const int k = __float_as_int(ob.w);
+        const int2 sp = c.sup[k];
+        const float* wrow = c.wt + k * BP;
+        float u[LP4], du[LP4];
+        {
+            const float4* up = reinterpret_cast<const float4*>(c.us + o * UST);
+#pragma unroll
+            for (int j = 0; j < LP4 / 4; ++j) {
+                float4 a = up[j], b = up[LP4 / 4 + j];
+                u[4 * j] = a.x; u[4 * j + 1] = a.y; u[4 * j + 2] = a.z; u[4 * j + 3] = a.w;
+                du[4 * j] = b.x; du[4 * j + 1] = b.y; du[4 * j + 2] = b.z; du[4 * j + 3] = b.w;
+            }
+        }
+        const int pk = c.oi[o];
+        const float f = c.of[o];
+        const float* h0p = hs + (pk & 0xff) * BP;
+        const float* h1p = hs + (pk >> 8) * BP;
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+        for (int b0 = sp.x; b0 < sp.y; b0 += 32) {
+            const int b = b0 + lane;
+            const int bb = min(b, NB - 1);
+            const float w = (b < sp.y) ? wrow[bb] : 0.f;
+            float jl[LP];
+            float g = 0.f, gd = 0.f;
+#pragma unroll
+            for (int l = 0; l < LP; ++l) {
+                jl[l] = c.sJl[l * BP + bb];
+                g = fmaf(jl[l], u[l], g);
+                gd = fmaf(jl[l], du[l], gd);
+            }
+            const float a = adv[bb];
+            const float h0 = __ldg(h0p + bb), h1 = __ldg(h1p + bb);
+            const float dh = h1 - h0;
+            const float H = fmaf(f, dh, h0);
+            const float e = ex2_approx(fmaf(AVc, a, g));
+            const float we = w * e;
+            const float P = we * H;
+            acc[0] += P;
+            acc[1] = fmaf(P, a, acc[1]);
+            acc[2] += fmaf(P, gd * LN2, we * dh);
+            if (RVFREE) acc[3] = fmaf(P, c.wdad[bb], acc[3]);
+#pragma unroll
+            for (int l = 0; l < LP; ++l) acc[4 + l] = fmaf(jl[l], P, acc[4 + l]);
+        }
+        const float val = treduce16(acc, lane);
+        const float F = __shfl_sync(FULL, val, 0);
+        const float FA = __shfl_sync(FULL, val, 2);
+        const float FT = __shfl_sync(FULL, val, 4);
+        const float flux = S * F;
+        const float resid = ob.y - flux;
+        const float chi = resid * ob.z;
+        logL = fmaf(-0.5f * chi, chi, logL);
+        const float r = chi * ob.z;
+        const float coef = r * S;
+        gDs = fmaf(-KAPPA * r, flux, gDs);
+        gAV = fmaf(-KAPPA * coef, FA, gAV);
+        gT = fmaf(coef, FT, gT);
+        if (RVFREE) gRV = fmaf(-KAPPA * AV * coef, __shfl_sync(FULL, val, 6), gRV);
+        // d logL / d(sum_m W[l][m] Jt[m]) for this observation, overwriting u (no longer needed)
+        __syncwarp();
+        {
+            const int vi = lane >> 1;
+            if (!(lane & 1) && vi >= 4 && vi < 4 + LP) c.us[o * UST + (vi - 4)] = -KAPPA * coef * val;
+        }
+    }
+    __syncwarp();
+
+    // ---- reverse: dW, theta, eps_tform -------------------------------------------------------
+    float dW[NPAIR];
+    float gth = 0.f;
+#pragma unroll
+    for (int s = 0; s < NPAIR; ++s) {
+        int p = lane + 32 * s;
+        float acc = 0.f;
+        if (p < LP * TP) {
+            int l = p / TP, m = p - l * TP;
+            for (int o = 0; o < c.nobs; ++o) acc = fmaf(c.us[o * UST + l], c.Jts[o * TP + m], acc);
+            gth = fmaf(acc, c.sW1[p], gth);
+        }
+        dW[s] = acc;
+    }
+    gth = wsum(gth);
+#pragma unroll
+    for (int s = 0; s < NPAIR; ++s) {
+        int p = lane + 32 * s;
+        if (p < LP * TP) {
+            int l = p / TP, m = p - l * TP;
+            if (l >= 1 && l <= L - 2 && m < T) c.ev[(l - 1) + (L - 2) * m] = dW[s];
+        }
+    }
+    __syncwarp();
+
+    // ---- priors, Jacobians, assemble gradient in the unconstrained space ---------------------
+    float lp = logL + c.lconst;
+    float ss = 0.f;
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+        int i = lane + 32 * s;
+        float gi = 0.f;
+        if (i < ne) {
+            float acc = 0.f;
+            const float* col = M.Ls + i;
+            for (int j = 0; j < ne; ++j) acc = fmaf(__ldg(col + j * ne), c.ev[j], acc);
+            gi = acc - q[s];
+            ss = fmaf(q[s], q[s], ss);
+        }
+        grad[s] = gi;
+    }
+    ss = wsum(ss);
+    lp += -0.5f * ss;
+    // theta ~ N(0,1)
+    lp += -0.5f * theta_s * theta_s;
+    float g_theta = (M.fix_theta ? 0.f : gth) - theta_s;
+    // A_V = exp(u): Exponential(1/tauA) prior + log|J| = u
+    lp += -AV_s * M.inv_tauA + uAV;
+    float g_uAV = ((M.fix_AV ? 0.f : gAV) - M.inv_tauA) * AV_s + 1.f;
+    // tmax = -10 + 20 sigmoid(u): uniform prior cancels the affine Jacobian
+    lp += logf(sg) + logf(1.f - sg);
+    float g_ut = (M.fix_tmax ? 0.f : -gT) * 20.f * sg * (1.f - sg) + (1.f - 2.f * sg);
+    // Ds ~ N(muhat, sd)
+    float dD = Ds - c.muhat;
+    lp += -0.5f * dD * dD * M.inv_sd2;
+    float g_Ds = gDs - dD * M.inv_sd2;
+    float g_uR = 0.f;
+    if (RVFREE) {
+        lp += logf(sgR) + logf(1.f - sgR);
+        g_uR = gRV * dRV_du + (1.f - 2.f * sgR);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+        int i = lane + 32 * s;
+        if (i == ne + 0) grad[s] = g_theta;
+        if (i == ne + 1) grad[s] = g_uAV;
+        if (i == ne + 2) grad[s] = g_ut;
+        if (i == ne + 3) grad[s] = g_Ds;
+        if (RVFREE && i == ne + 4) grad[s] = g_uR;
+    }
+    logp_out = lp;
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA prologue shared by the log p kernel and the NUTS kernel: stage tables with TMA, carve smem
+// ------------------------------------------------------------------------------------------
+template <int LP, int TP, bool RVFREE, bool STAGE>
+__device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, int n_chains, int ntile, float* smem,
+                                          WarpCtx& c, int& sn, int& chain) {
+    const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, ntile, RVFREE, STAGE);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long unit0 = (long long)blockIdx.x * WPB;
+    const long long total = (long long)Dd.N * n_chains;
+    const int s_first = (int)(unit0 / n_chains);
+    long long last_unit = unit0 + WPB - 1;
+    if (last_unit >= total) last_unit = total - 1;
+    const int s_last = (int)(last_unit / n_chains);
+    const int nt = s_last - s_first + 1;
+
+    float* sJl = smem + P.oJl;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P.oBar);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t bytes = LP * BP * 4 + (RVFREE ? 9 * BP * 4 : BP * 4);
+        bytes += nt * Dd.N_obs * 16;
+        if (STAGE) bytes += nt * Dd.n_b * BP * 4;
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(sJl, M.Jl, LP * BP * 4, bar);
+        if (RVFREE) tma_load_1d(smem + P.oMf, M.Mf, 9 * BP * 4, bar);
+        else tma_load_1d(smem + P.oAd, M.ad, BP * 4, bar);
+        tma_load_1d(smem + P.oObs, Dd.obs4 + (size_t)s_first * Dd.N_obs, nt * Dd.N_obs * 16, bar);
+        if (STAGE) tma_load_1d(smem + P.oWt, Dd.wt + (size_t)s_first * Dd.n_b * BP, nt * Dd.n_b * BP * 4, bar);
+    }
+    // small tables with plain loads while the bulk copies are in flight
+    for (int i = tid; i < LP * TP; i += blockDim.x) {
+        smem[P.oW0 + i] = M.W0[i];
+        smem[P.oW1 + i] = M.W1[i];
+    }
+    for (int i = tid; i < TP * TP; i += blockDim.x) smem[P.oKD + i] = M.KD[i];
+    for (int i = tid; i < TP; i += blockDim.x) smem[P.oTau + i] = M.tau[i];
+    int2* sSup = reinterpret_cast<int2*>(smem + P.oSup);
+    for (int i = tid; i < nt * Dd.n_b; i += blockDim.x) sSup[i] = Dd.sup[(size_t)s_first * Dd.n_b + i];
+    mbar_wait(bar, 0);
+    __syncthreads();
+
+    const long long unit = unit0 + warp;
+    const bool active = unit < total;
+    sn = active ? (int)(unit / n_chains) : s_first;
+    chain = active ? (int)(unit - (long long)sn * n_chains) : 0;
+    const int slot = sn - s_first;
+    float* wb = smem + P.oWarp + warp * P.warpStride;
+    c.sJl = sJl;
+    c.sAd = smem + P.oAd;
+    c.sMf = smem + P.oMf;
+    c.sW0 = smem + P.oW0;
+    c.sW1 = smem + P.oW1;
+    c.sKD = smem + P.oKD;
+    c.sTau = smem + P.oTau;
+    c.wt = STAGE ? (smem + P.oWt + (size_t)slot * Dd.n_b * BP) : (Dd.wt + (size_t)sn * Dd.n_b * BP);
+    c.sup = sSup + slot * Dd.n_b;
+    c.obs = reinterpret_cast<const float4*>(smem + P.oObs) + slot * Dd.N_obs;
+    c.Ws = wb + P.wWs;
+    c.ev = wb + P.wEv;
+    c.eps = wb + P.wEps;
+    c.us = wb + P.wUs;
+    c.Jts = wb + P.wJts;
+    c.of = wb + P.wOf;
+    c.oi = reinterpret_cast<int*>(wb + P.wOi);
+    c.wad = wb + P.wAd;
+    c.wdad = wb + P.wDad;
+    c.nobs = Dd.n_valid[sn];
+    c.muhat = Dd.muhat[sn];
+    c.lconst = Dd.lconst[sn];
+    return active;
+}
+
+}  // namespace bayesn

@@ -1,0 +1,420 @@
+// bayesn_kernels.cuh - __global__ kernels: fused log p + gradient, forward flux, device NUTS.
+#pragma once
+#include "bayesn_device.cuh"
+
+namespace bayesn {
+
+// ------------------------------------------------------------------------------------------
+// (1) fused log-density + gradient for every (SN, chain)
+// ------------------------------------------------------------------------------------------
+template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
+__global__ void __launch_bounds__(WPB * 32) logp_grad_kernel(ModelDev M, DataDev Dd, int n_chains, int ntile,
+                                                             const float* __restrict__ q_in,
+                                                             float* __restrict__ logp_out,
+                                                             float* __restrict__ grad_out) {
+    extern __shared__ __align__(16) float smem[];
+    WarpCtx c;
+    int sn, chain;
+    const bool active = cta_setup<LP, TP, RVFREE, STAGE>(M, Dd, n_chains, ntile, smem, c, sn, chain);
+    if (!active) return;
+    const int lane = threadIdx.x & 31;
+    const size_t unit = (size_t)sn * n_chains + chain;
+    float q[VPL], g[VPL];
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+        int i = lane + 32 * s;
+        q[s] = (i < M.D) ? q_in[unit * M.D + i] : 0.f;
+    }
+    float lp;
+    eval_logp_grad<LP, TP, VPL, RVFREE>(M, c, M.hs, q, lp, g, lane);
+    if (lane == 0) logp_out[unit] = lp;
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+        int i = lane + 32 * s;
+        if (i < M.D) grad_out[unit * M.D + i] = g[s];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// (2) forward only: get_flux_batch / get_mag_batch with the reference's argument layouts
+//     (bayesn/bayesn_model.py:645-759).  One warp per (observation, SN); lanes over bins.
+// ------------------------------------------------------------------------------------------
+struct FluxArgs {
+    int N, N_obs, n_b, L, T, mag;
+    float M0;
+    const float *theta, *AV, *W0, *W1, *eps, *Ds, *RV;
+    const int* band;
+    const uint8_t* mask;
+    const float *J_t, *hsi, *weights;
+    const double* bscale;   // [n_b] log2 of the band scale (double: the exponent is ~+60)
+    const float *Jl, *hs, *Mf;   // model tables: [LP][BP], [NPH][BP], [9][BP]
+    int LPs;                // row count of Jl
+    float* out;
+};
+
+__global__ void __launch_bounds__(128) flux_kernel(FluxArgs A) {
+    __shared__ float su[4][BAYESN_MAX_L];
+    __shared__ float syk[4][12];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long item = (long long)blockIdx.x * 4 + warp;
+    const long long total = (long long)A.N * A.N_obs;
+    if (item >= total) return;
+    const int s = (int)(item / A.N_obs), o = (int)(item - (long long)s * A.N_obs);
+    const size_t on = (size_t)o * A.N + s;
+    const bool msk = A.mask[on] != 0;
+    const int L = A.L, T = A.T;
+    // u[l] = -c2 * sum_m (W0 + theta W1 + eps)[l][m] J_t[s][m][o]
+    if (lane < L) {
+        float th = A.theta[s], acc = 0.f;
+        for (int m = 0; m < T; ++m) {
+            float w = A.W0[lane * T + m] + th * A.W1[lane * T + m] + A.eps[((size_t)s * L + lane) * T + m];
+            acc = fmaf(w, A.J_t[((size_t)s * T + m) * A.N_obs + o], acc);
+        }
+        su[warp][lane] = -C2 * acc;
+    }
+    const float RV = A.RV[s];
+    if (lane == 0) {
+        const float R = RV, R2 = R * R, R3 = R2 * R;
+        const float c2f = -0.824f + 4.717f / R, c1f = 2.030f - 3.007f * c2f;
+        const float x7 = 1e4f / 2700.f, x8 = 1e4f / 2600.f, x0 = 4.596f, gm = 0.99f;
+        const float d1 = x7 * x7 / ((x7 * x7 - x0 * x0) * (x7 * x7 - x0 * x0) + gm * gm * x7 * x7);
+        const float d2 = x8 * x8 / ((x8 * x8 - x0 * x0) * (x8 * x8 - x0 * x0) + gm * gm * x8 * x8);
+        float* yk = syk[warp];
+        yk[0] = -R;
+        yk[1] = 0.26469f * R / 3.1f - R;
+        yk[2] = 0.82925f * R / 3.1f - R;
+        yk[3] = -0.422809f + 0.00270f * R + 2.13572e-4f * R2;
+        yk[4] = -5.13540e-2f + 0.00216f * R - 7.35778e-5f * R2;
+        yk[5] = 0.700127f + 0.00184f * R - 3.32598e-5f * R2;
+        yk[6] = 1.19456f + 0.01707f * R - 5.46959e-3f * R2 + 7.97809e-4f * R3 - 4.45636e-5f * R2 * R2;
+        yk[7] = c1f + c2f * x7 + 3.23f * d1;
+        yk[8] = c1f + c2f * x8 + 3.23f * d2;
+    }
+    __syncwarp();
+    const int k = A.band[on];
+    const float AVc = -C2 * A.AV[s];
+    const float iR = 1.f / RV;
+    int i0 = (int)A.hsi[on], i1 = (int)A.hsi[(size_t)A.N_obs * A.N + on];
+    const float f = A.hsi[2 * (size_t)A.N_obs * A.N + on];
+    i0 = min(max(i0, 0), NPH - 1);
+    i1 = min(max(i1, 0), NPH - 1);
+    const float* wcol = A.weights + (size_t)s * NB * A.n_b + k;
+    float F = 0.f;
+    for (int b = lane; b < NB; b += 32) {
+        float g = 0.f;
+        for (int l = 0; l < L; ++l) g = fmaf(A.Jl[l * BP + b], su[warp][l], g);
+        float my = 0.f;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) my = fmaf(A.Mf[j * BP + b], syk[warp][j], my);
+        const float a = 1.f + my * iR;
+        const float h0 = A.hs[i0 * BP + b], h1 = A.hs[i1 * BP + b];
+        const float H = fmaf(f, h1 - h0, h0);
+        F = fmaf(wcol[(size_t)b * A.n_b] * H, ex2_approx(fmaf(AVc, a, g)), F);
+    }
+    F = wsum(F);
+    if (lane == 0) {
+        // scale = 10^(-0.4 (M0 + Ds)) * band scale, assembled in the log2 domain
+        float flux = F * (float)exp2(A.bscale[k] - 1.3287712379549449 * ((double)A.M0 + (double)A.Ds[s]));
+        flux = msk ? flux : 0.f;
+        float outv = flux;
+        if (A.mag) {
+            float fm = flux + (msk ? 0.f : 0.01f);
+            outv = msk ? (-2.5f * log10f(fm) + 27.5f) : 0.f;
+        }
+        A.out[on] = outv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// (3) device-resident NUTS: one warp per chain, iterative tree doubling, on-device adaptation.
+//     Semantics follow numpyro.infer.NUTS (third-party, not in the reference tree; restated from
+//     SURVEY.md Appendix C): multinomial sampling, checkpointed U-turn test, dual averaging,
+//     Stan-style windowed diagonal mass matrix.
+// ------------------------------------------------------------------------------------------
+enum { V_ZL = 0, V_RL, V_GL, V_ZR, V_RR, V_GR, V_ZP, V_GP, V_RSUM, V_SZP, V_SGP, V_WMEAN, V_WM2, V_CKPT };
+__host__ __device__ inline int nuts_num_vectors(int max_depth) { return V_CKPT + 2 * max_depth; }
+
+template <int VPL>
+struct VecIO {
+    float* base;   // this chain's workspace: [nvec][32*VPL]
+    int lane;
+    __device__ __forceinline__ void st(int v, const float (&x)[VPL]) const {
+#pragma unroll
+        for (int s = 0; s < VPL; ++s) base[(v * VPL + s) * 32 + lane] = x[s];
+    }
+    __device__ __forceinline__ void ld(int v, float (&x)[VPL]) const {
+#pragma unroll
+        for (int s = 0; s < VPL; ++s) x[s] = base[(v * VPL + s) * 32 + lane];
+    }
+};
+
+template <int VPL>
+__device__ __forceinline__ float vdot_im(const float (&im)[VPL], const float (&a)[VPL], const float (&b)[VPL]) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) s = fmaf(im[i] * a[i], b[i], s);
+    return wsum(s);
+}
+
+// generalised U-turn test (numpyro _is_turning): r_sum - (r_left + r_right)/2 against both ends
+template <int VPL>
+__device__ __forceinline__ bool is_turning(const float (&im)[VPL], const float (&rl)[VPL], const float (&rr)[VPL],
+                                           const float (&rsum)[VPL]) {
+    float sl = 0.f, sr = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        float rs = rsum[i] - 0.5f * (rl[i] + rr[i]);
+        sl = fmaf(im[i] * rl[i], rs, sl);
+        sr = fmaf(im[i] * rr[i], rs, sr);
+    }
+    sl = wsum(sl);
+    sr = wsum(sr);
+    return (sl <= 0.f) || (sr <= 0.f);
+}
+
+__device__ __forceinline__ float logaddexpf(float a, float b) {
+    float m = fmaxf(a, b);
+    if (m == -INFINITY) return -INFINITY;
+    return m + log1pf(expf(-fabsf(a - b)));
+}
+
+template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
+__global__ void __launch_bounds__(WPB * 32) nuts_kernel(ModelDev M, DataDev Dd, NutsDev cfg, int ntile,
+                                                        const float* __restrict__ q_init, float* __restrict__ samples,
+                                                        float* __restrict__ stats, float* __restrict__ chain_info,
+                                                        float* __restrict__ work) {
+    extern __shared__ __align__(16) float smem[];
+    WarpCtx c;
+    int sn, chain;
+    const int C = cfg.num_chains;
+    const bool active = cta_setup<LP, TP, RVFREE, STAGE>(M, Dd, C, ntile, smem, c, sn, chain);
+    if (!active) return;
+    const int lane = threadIdx.x & 31;
+    const size_t unit = (size_t)sn * C + chain;
+    const int D = M.D;
+    const int nvec = nuts_num_vectors(cfg.max_depth);
+    VecIO<VPL> io{work + unit * (size_t)nvec * 32 * VPL, lane};
+    const uint2 key = make_uint2(cfg.seed_lo, cfg.seed_hi);
+    bool own[VPL];
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) own[s] = (lane + 32 * s) < D;
+
+    float z[VPL], r[VPL], g[VPL], im[VPL], rsum[VPL], tmp[VPL], tmp2[VPL];
+#pragma unroll
+    for (int s = 0; s < VPL; ++s) {
+        z[s] = own[s] ? q_init[unit * D + lane + 32 * s] : 0.f;
+        im[s] = own[s] ? 1.f : 0.f;
+        tmp[s] = 0.f;
+    }
+    io.st(V_WMEAN, tmp);
+    io.st(V_WM2, tmp);
+    float pe;   // potential energy = -log p
+    {
+        float lp;
+        eval_logp_grad<LP, TP, VPL, RVFREE>(M, c, M.hs, z, lp, g, lane);
+        pe = -lp;
+#pragma unroll
+        for (int s = 0; s < VPL; ++s) g[s] = -g[s];
+    }
+    // adaptation state (numpyro warmup_adapter / dual_averaging / welford_covariance)
+    float step = cfg.init_step;
+    float da_x = 0.f, da_xavg = 0.f, da_gavg = 0.f, da_prox = logf(10.f * step);
+    int da_t = 0, wf_n = 0, window = 0;
+    float mean_acc = 0.f;
+    long long total_steps = 0;
+    int n_div = 0;
+    const int n_iter = cfg.num_warmup + cfg.num_samples;
+
+    for (int it = 0; it < n_iter; ++it) {
+        uint32_t rk = 0;   // draw counter within this transition
+        // ---- momentum refresh r ~ N(0, M) -------------------------------------------------
+        {
+            uint4 ra = philox4x32(make_uint4((uint32_t)it, 0x40000000u, (uint32_t)lane, (uint32_t)unit), key);
+            float n0 = sqrtf(-2.f * logf(u01(ra.x) + 5.9604644775390625e-8f));
+            float n1 = sqrtf(-2.f * logf(u01(ra.z) + 5.9604644775390625e-8f));
+            float sn0, cs0, sn1, cs1;
+            sincospif(2.f * u01(ra.y), &sn0, &cs0);
+            sincospif(2.f * u01(ra.w), &sn1, &cs1);
+            float nrm[4] = {n0 * cs0, n0 * sn0, n1 * cs1, n1 * sn1};
+#pragma unroll
+            for (int s = 0; s < VPL; ++s) r[s] = own[s] ? nrm[s & 3] * rsqrtf(im[s]) : 0.f;
+        }
+        const float E0 = pe + 0.5f * vdot_im<VPL>(im, r, r);
+        io.st(V_ZL, z); io.st(V_RL, r); io.st(V_GL, g);
+        io.st(V_ZR, z); io.st(V_RR, r); io.st(V_GR, g);
+        io.st(V_ZP, z); io.st(V_GP, g); io.st(V_RSUM, r);
+        float prop_pe = pe;
+        float w_main = 0.f, sum_acc = 0.f;
+        int depth = 0, n_prop = 0;
+        bool turning = false, diverging = false;
+
+        while (depth < cfg.max_depth && !turning && !diverging) {
+            uint4 rd = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, (uint32_t)unit), key);
+            const bool going_right = (rd.x >> 31) != 0;
+            const float u_main = u01(rd.y);
+            if (going_right) { io.ld(V_ZR, z); io.ld(V_RR, r); io.ld(V_GR, g); }
+            else { io.ld(V_ZL, z); io.ld(V_RL, r); io.ld(V_GL, g); }
+            const float eps_dir = going_right ? step : -step;
+            const int n_max = 1 << depth;
+            int n_sub = 0;
+            bool s_turn = false, s_div = false;
+            float w_sub = -INFINITY, s_acc = 0.f, sprop_pe = 0.f;
+            while (n_sub < n_max && !s_turn && !s_div) {
+                // leapfrog (velocity Verlet)
+#pragma unroll
+                for (int s = 0; s < VPL; ++s) {
+                    r[s] = fmaf(-0.5f * eps_dir, g[s], r[s]);
+                    z[s] = fmaf(eps_dir * im[s], r[s], z[s]);
+                }
+                float lp;
+                eval_logp_grad<LP, TP, VPL, RVFREE>(M, c, M.hs, z, lp, g, lane);
+                const float pe_new = -lp;
+#pragma unroll
+                for (int s = 0; s < VPL; ++s) {
+                    g[s] = -g[s];
+                    r[s] = fmaf(-0.5f * eps_dir, g[s], r[s]);
+                }
+                const float E_new = pe_new + 0.5f * vdot_im<VPL>(im, r, r);
+                float dE = E_new - E0;
+                if (!(dE == dE)) dE = INFINITY;
+                const float leaf_w = -dE;
+                s_div = dE > 1000.f;
+                s_acc += fminf(1.f, expf(-dE));
+                if (n_sub == 0) {
+#pragma unroll
+                    for (int s = 0; s < VPL; ++s) rsum[s] = r[s];
+                    w_sub = leaf_w;
+                    io.st(V_SZP, z); io.st(V_SGP, g);
+                    sprop_pe = pe_new;
+                } else {
+#pragma unroll
+                    for (int s = 0; s < VPL; ++s) rsum[s] += r[s];
+                    uint4 rl = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, (uint32_t)unit), key);
+                    const float tp = 1.f / (1.f + expf(-(leaf_w - w_sub)));   // uniform transition kernel
+                    if (u01(rl.x) < tp) {
+                        io.st(V_SZP, z); io.st(V_SGP, g);
+                        sprop_pe = pe_new;
+                    }
+                    w_sub = logaddexpf(w_sub, leaf_w);
+                }
+                const int leaf = n_sub;
+                ++n_sub;
+                // checkpoint indices (numpyro _leaf_idx_to_ckpt_idxs)
+                const int idx_max = __popc(leaf >> 1);
+                const int n_sub_trees = __ffs(~leaf) - 1;   // trailing ones
+                const int idx_min = idx_max - n_sub_trees + 1;
+                if ((leaf & 1) == 0) {
+                    io.st(V_CKPT + 2 * idx_max, r);
+                    io.st(V_CKPT + 2 * idx_max + 1, rsum);
+                }
+                for (int i = idx_max; i >= idx_min && !s_turn; --i) {
+                    io.ld(V_CKPT + 2 * i, tmp);          // r_ckpt
+                    io.ld(V_CKPT + 2 * i + 1, tmp2);     // r_sum_ckpt
+#pragma unroll
+                    for (int s = 0; s < VPL; ++s) tmp2[s] = rsum[s] - tmp2[s] + tmp[s];
+                    s_turn = is_turning<VPL>(im, tmp, r, tmp2);
+                }
+            }
+            total_steps += n_sub;
+            // ---- merge the new subtree into the trajectory (biased progressive sampling) ------
+            if (going_right) { io.st(V_ZR, z); io.st(V_RR, r); io.st(V_GR, g); }
+            else { io.st(V_ZL, z); io.st(V_RL, r); io.st(V_GL, g); }
+            io.ld(V_RSUM, tmp);
+#pragma unroll
+            for (int s = 0; s < VPL; ++s) tmp[s] += rsum[s];
+            io.st(V_RSUM, tmp);
+            float tp = (s_turn || s_div) ? 0.f : fminf(1.f, expf(w_sub - w_main));
+            if (u_main < tp) {
+                io.ld(V_SZP, tmp2); io.st(V_ZP, tmp2);
+                io.ld(V_SGP, tmp2); io.st(V_GP, tmp2);
+                prop_pe = sprop_pe;
+            }
+            if (s_turn) turning = true;
+            else {
+                float rl_[VPL], rr_[VPL];
+                io.ld(V_RL, rl_); io.ld(V_RR, rr_);
+                turning = is_turning<VPL>(im, rl_, rr_, tmp);
+            }
+            w_main = logaddexpf(w_main, w_sub);
+            diverging = s_div;
+            sum_acc += s_acc;
+            n_prop += n_sub;
+            ++depth;
+        }
+        const float accept = sum_acc / (float)max(n_prop, 1);
+        io.ld(V_ZP, z); io.ld(V_GP, g);
+        pe = prop_pe;
+
+        if (it < cfg.num_warmup) {
+            // ---- warm-up adaptation (numpyro warmup_adapter.update_fn) --------------------------
+            if (cfg.adapt_step) {
+                ++da_t;
+                const float gg = cfg.target_accept - accept;
+                da_gavg = (1.f - 1.f / (da_t + 10.f)) * da_gavg + gg / (da_t + 10.f);
+                da_x = da_prox - sqrtf((float)da_t) / 0.05f * da_gavg;
+                const float wt = powf((float)da_t, -0.75f);
+                da_xavg = (1.f - wt) * da_xavg + wt * da_x;
+                step = (it == cfg.num_warmup - 1) ? expf(da_xavg) : expf(da_x);
+                step = fmaxf(step, 1.17549435e-38f);
+            }
+            const bool middle = (window > 0) && (window < cfg.n_windows - 1);
+            if (cfg.adapt_mass && middle) {
+                ++wf_n;
+                io.ld(V_WMEAN, tmp); io.ld(V_WM2, tmp2);
+#pragma unroll
+                for (int s = 0; s < VPL; ++s) {
+                    float dpre = z[s] - tmp[s];
+                    tmp[s] += dpre / (float)wf_n;
+                    tmp2[s] = fmaf(dpre, z[s] - tmp[s], tmp2[s]);
+                }
+                io.st(V_WMEAN, tmp); io.st(V_WM2, tmp2);
+            }
+            const bool at_end = (it == cfg.win_end[window]);
+            if (at_end) ++window;
+            if (at_end && middle) {
+                if (cfg.adapt_mass) {
+                    io.ld(V_WM2, tmp2);
+#pragma unroll
+                    for (int s = 0; s < VPL; ++s) {
+                        float cov = tmp2[s] / (float)(wf_n - 1);
+                        if (cfg.regularize) cov = (wf_n / (wf_n + 5.f)) * cov + 1e-3f * (5.f / (wf_n + 5.f));
+                        im[s] = own[s] ? cov : 0.f;
+                        tmp[s] = 0.f;
+                    }
+                    io.st(V_WMEAN, tmp); io.st(V_WM2, tmp);
+                    wf_n = 0;
+                }
+                if (cfg.adapt_step) {
+                    da_prox = logf(10.f * step);
+                    da_x = 0.f; da_xavg = 0.f; da_gavg = 0.f; da_t = 0;
+                }
+            }
+        } else {
+            const int k = it - cfg.num_warmup;
+            const size_t row = unit * cfg.num_samples + k;
+#pragma unroll
+            for (int s = 0; s < VPL; ++s)
+                if (own[s]) samples[row * D + lane + 32 * s] = z[s];
+            if (lane == 0) {
+                stats[row * 4 + 0] = accept;
+                stats[row * 4 + 1] = (float)n_prop;
+                stats[row * 4 + 2] = diverging ? 1.f : 0.f;
+                stats[row * 4 + 3] = pe;
+            }
+            mean_acc += (accept - mean_acc) / (float)(k + 1);
+            n_div += diverging ? 1 : 0;
+        }
+    }
+    float* ci = chain_info + unit * (4 + D);
+    if (lane == 0) {
+        ci[0] = step;
+        ci[1] = mean_acc;
+        ci[2] = (float)total_steps;
+        ci[3] = (float)n_div;
+    }
+#pragma unroll
+    for (int s = 0; s < VPL; ++s)
+        if (own[s]) ci[4 + lane + 32 * s] = im[s];
+}
+
+}  // namespace bayesn

@@ -1,0 +1,547 @@
+"""``SEDmodel``: host-side mirror of the reference's public class (``bayesn/bayesn_model.py:59``)
+for the hot path.  Same constructor, attributes, method names, argument meaning and array
+layouts; the arithmetic runs in the sm_100a kernels behind ``libbayesn_b200.so``.
+
+What is kept from the reference API (file:line = ``bayesn/bayesn_model.py``):
+``SEDmodel(num_devices, load_model, filter_yaml, fiducial_cosmology)`` :199, ``get_spectra`` is
+not exposed (the kernels never materialise spectra), ``get_flux_batch`` :645, ``get_mag_batch``
+:711, ``fit`` :1994, ``fit_from_file`` :1926, ``simulate_light_curve`` :3103, ``sample_*``
+:3347-3424, ``get_flux_from_chains`` :3426, plus ``fit_batch`` (the vmapped per-object fit of
+``run`` :1809-1849 as a plain method).  numpyro models are replaced by ``logp_grad`` (the
+unconstrained log-density + gradient of ``fit_model_globalRV`` / ``popRV`` / ``uniformRV``).
+"""
+import math
+import os
+import pickle
+import time
+
+import numpy as np
+
+from . import datafiles, native, packing
+from .static import FilterSet, FlatLambdaCDM, ModelGrid, spline_row, HSIAO_PHASE0_INDEX, f99_yk
+from . import snana, summary
+
+
+class SEDmodel(object):
+    def __init__(self, num_devices=4, load_model='T21_model', filter_yaml=None,
+                 fiducial_cosmology={"H0": 73.24, "Om0": 0.28}, device=None, verbose=False):
+        self.start_time = time.time()
+        self.end_time = None
+        self.num_devices = num_devices          # kept for signature compatibility; sharding is per process
+        self.__root_dir__ = datafiles.DATA_ROOT
+        self.cosmo = FlatLambdaCDM(**fiducial_cosmology)
+        self.data = None
+        self.hsiao_interp = None
+        self.RV_MW = 3.1
+        self.sigma_pec = 150 / 3e5
+        self.sn_list = None
+        self.filter_yaml = filter_yaml
+        self.verbose = verbose
+        if verbose:
+            print(f'Loading model {load_model}')
+        params = datafiles.load_model_yaml(load_model)
+        self.example_lc = datafiles.EXAMPLE_LC
+        self.l_knots = np.array(params['L_KNOTS'], dtype=np.float64)
+        self.tau_knots = np.array(params['TAU_KNOTS'], dtype=np.float64)
+        self.W0 = np.array(params['W0'], dtype=np.float64)
+        self.W1 = np.array(params['W1'], dtype=np.float64)
+        self.L_Sigma = np.array(params['L_SIGMA_EPSILON'], dtype=np.float64)
+        self.M0 = float(params['M0'])
+        self.sigma0 = float(params['SIGMA0'])
+        self.tauA = float(params['TAUA'])
+        if 'RV' in params:
+            self.model_type = 'fixed_RV'
+            self.RV = float(params['RV'])
+        elif 'MUR' in params:
+            self.model_type = 'pop_RV'
+            self.mu_R = float(params['MUR'])
+            self.sigma_R = float(params['SIGMAR'])
+        self.trunc_val = 1.2
+        self.used_band_inds = None
+        self.band_weights = None
+        self._device = device
+        self._ctxs = {}
+        self._setup_band_weights()
+
+    # ------------------------------------------------------------------ static tables
+    def _setup_band_weights(self):
+        """Reference :287-497."""
+        self.spectrum_bins = 300
+        self.band_oversampling = 51
+        self.max_redshift = 4
+        self.grid = ModelGrid(self.l_knots, self.tau_knots)
+        self.filters = FilterSet(self.grid, self.filter_yaml)
+        f = self.filters
+        self.band_dict, self.zp_dict, self.band_lim_dict = f.band_dict, f.zp_dict, f.band_lim_dict
+        self.inv_band_dict = f.inv_band_dict
+        self.zps, self.offsets = f.zps, f.offsets
+        self.used_band_inds = np.array(list(self.band_dict.values()))
+        self.used_band_dict = {v: v for v in self.band_dict.values()}
+        self.band_interpolate_weights = f.master
+        self.band_interpolate_spacing = self.grid.band_spacing
+        self.model_wave = self.grid.model_wave
+        self.J_l_T = self.grid.J_l
+        self.KD_t = self.grid.KD_t
+        self.hsiao_flux = self.grid.hsiao_flux
+        self.hsiao_t = self.grid.hsiao_phase
+        self.xk = np.array([0.0, 1e4 / 26500., 1e4 / 12200., 1e4 / 6000., 1e4 / 5470., 1e4 / 4670., 1e4 / 4110.,
+                            1e4 / 2700., 1e4 / 2600.])
+        self.M_fitz_block = self.grid.M_fitz
+        self.ZPT = 27.5
+        self.sim = False
+        self._ctxs = {}
+
+    def _calculate_band_weights(self, redshifts, ebv, band_inds=None):
+        """Reference :499-554.  Unlike the reference this does not mutate
+        ``band_interpolate_weights``; ``band_inds`` defaults to
+        ``self.used_band_inds``."""
+        if band_inds is None:
+            band_inds = self.used_band_inds
+        return self.filters.band_weights(redshifts, ebv, band_inds, RV_MW=self.RV_MW)
+
+    def J_t_map(self, t, tau_knots=None, KD_t=None):
+        """Rows of the time-spline matrix (vmapped ``spline_coeffs_irr_step``, reference :258)."""
+        return spline_row(t, self.tau_knots if tau_knots is None else tau_knots,
+                          self.KD_t if KD_t is None else KD_t)
+
+    # ------------------------------------------------------------------ native context
+    def _device_index(self):
+        import torch
+        if self._device is not None:
+            return torch.device(self._device).index or 0
+        return int(os.environ.get('LOCAL_RANK', torch.cuda.current_device() if torch.cuda.is_available() else 0))
+
+    def _rv_mode(self, RV=None):
+        if RV == 'uniform':
+            return native.RV_UNIFORM
+        return native.RV_FIXED if self.model_type == 'fixed_RV' else native.RV_POP
+
+    def _context(self, rv_mode, fix_tmax=False, fix_theta=False, theta_val=0.0, fix_AV=False, AV_val=0.0):
+        """A native context whose model tables match the current attributes and fit flags."""
+        import torch
+        dev = self._device_index()
+        torch.cuda.set_device(dev)
+        ctx = native.Context(dev)
+        RV = float(getattr(self, 'RV', 3.0))
+        a_dust, _ = self.grid.dust_basis(np.array(RV))
+        ctx.set_model(tau_knots=self.tau_knots, KD_t=self.KD_t, J_l=self.J_l_T, hsiao=self.hsiao_flux,
+                      M_fitz=self.M_fitz_block, a_dust=a_dust, W0=self.W0, W1=self.W1, L_Sigma=self.L_Sigma,
+                      tauA=self.tauA, Ds_prior_sd=math.sqrt(25.0 + self.sigma0 ** 2), rv_mode=rv_mode, RV=RV,
+                      mu_R=float(getattr(self, 'mu_R', 0.0)), sigma_R=float(getattr(self, 'sigma_R', 1.0)),
+                      trunc_R=self.trunc_val, fix_tmax=fix_tmax, fix_theta=fix_theta, fix_AV=fix_AV,
+                      theta_val=theta_val, AV_val=AV_val)
+        return ctx
+
+    @property
+    def n_eps(self):
+        return (len(self.l_knots) - 2) * len(self.tau_knots)
+
+    # ------------------------------------------------------------------ parameter packing
+    def param_dim(self, rv_mode=native.RV_FIXED):
+        return self.n_eps + (4 if rv_mode == native.RV_FIXED else 5)
+
+    def prepare(self, obs, weights, band_inds=None, rv_mode=None, **fix):
+        """Upload model + data set; returns the native context ready for ``logp_grad`` / ``nuts``.
+        ``obs`` (10, N_obs, N) and ``weights`` (N, 300, n_b) use the reference layouts; the band
+        indices in ``obs[-6]`` address the columns of ``weights`` (``band_inds`` gives the global
+        filter index of each column, default: all filters)."""
+        if rv_mode is None:
+            rv_mode = self._rv_mode()
+        if band_inds is None:
+            band_inds = np.arange(weights.shape[2])
+        ctx = self._context(rv_mode, **fix)
+        packed = packing.pack_dataset(obs, weights, self.zps[band_inds], self.offsets[band_inds], self.M0,
+                                      math.sqrt(25.0 + self.sigma0 ** 2), self.tauA, self.n_eps,
+                                      device=f'cuda:{ctx.device}')
+        ctx.bind_dataset(packed)
+        return ctx
+
+    def init_to_median(self, muhat, n_chains, rv_mode=native.RV_FIXED, seed=0, num_samples=15, device='cuda'):
+        """numpyro ``init_to_median(num_samples=15)`` (reference :1757, :2110): per chain, the
+        median of 15 prior draws of every site, mapped to the unconstrained space."""
+        import torch
+        N = len(muhat)
+        g = torch.Generator(device=device)
+        g.manual_seed(int(seed) + 7919)
+        ne = self.n_eps
+        D = self.param_dim(rv_mode)
+        sh = (N, n_chains, num_samples)
+        med = lambda x: x.median(dim=2).values
+        q = torch.empty((N, n_chains, D), dtype=torch.float32, device=device)
+        q[..., :ne] = torch.randn(sh + (ne,), generator=g, device=device).median(dim=2).values
+        q[..., ne + 0] = med(torch.randn(sh, generator=g, device=device))
+        u = torch.rand(sh, generator=g, device=device).clamp_(1e-7, 1 - 1e-7)
+        q[..., ne + 1] = torch.log(med(-self.tauA * torch.log(u)))
+        u = med(torch.rand(sh, generator=g, device=device)).clamp_(1e-6, 1 - 1e-6)
+        q[..., ne + 2] = torch.log(u) - torch.log1p(-u)
+        mu = torch.as_tensor(np.asarray(muhat, dtype=np.float32), device=device)[:, None]
+        q[..., ne + 3] = mu + math.sqrt(25.0 + self.sigma0 ** 2) * med(torch.randn(sh, generator=g, device=device))
+        if rv_mode != native.RV_FIXED:
+            u = med(torch.rand(sh, generator=g, device=device)).clamp_(1e-6, 1 - 1e-6)
+            q[..., ne + 4] = torch.log(u) - torch.log1p(-u)
+        return q.contiguous()
+
+    def constrain(self, q, rv_mode=native.RV_FIXED):
+        """Unconstrained draws (..., D) -> dict of constrained arrays (torch), reference site names."""
+        import torch
+        ne = self.n_eps
+        out = {'eps_tform': q[..., :ne], 'theta': q[..., ne], 'AV': torch.exp(q[..., ne + 1]),
+               'tmax': -10 + 20 * torch.sigmoid(q[..., ne + 2]), 'Ds': q[..., ne + 3]}
+        Ls = torch.as_tensor(self.L_Sigma, dtype=q.dtype, device=q.device)
+        out['eps'] = out['eps_tform'] @ Ls.T
+        if rv_mode == native.RV_UNIFORM:
+            out['RV'] = 1 + 5 * torch.sigmoid(q[..., ne + 4])
+        elif rv_mode == native.RV_POP:
+            rt = torch.sigmoid(q[..., ne + 4])
+            out['RV_tform'] = rt
+            nd = torch.distributions.Normal(0.0, 1.0)
+            pa = float(nd.cdf(torch.tensor((self.trunc_val - self.mu_R) / self.sigma_R)))
+            out['RV'] = self.mu_R + self.sigma_R * nd.icdf((pa + rt.double() * (1 - pa))).to(q.dtype)
+        return out
+
+    # ------------------------------------------------------------------ forward model
+    def _forward(self, mag, M0, theta, AV, W0, W1, eps, Ds, RV, band_indices, mask, J_t, hsiao_interp, weights,
+                 band_inds=None):
+        import torch
+        dev = f'cuda:{self._device_index()}'
+        key = ('fwd',)
+        ctx = self._ctxs.get(key)
+        if ctx is None:
+            ctx = self._ctxs[key] = self._context(native.RV_FIXED)
+        to = lambda a, dt=torch.float32: torch.as_tensor(np.asarray(a), device=dev).to(dt)
+        theta = to(theta)
+        N = theta.shape[0]
+        RV = np.broadcast_to(np.asarray(RV, dtype=np.float64), (N,))
+        if band_inds is None:
+            band_inds = np.arange(np.asarray(weights).shape[2]) if np.asarray(weights).shape[2] == len(self.zps) \
+                else self.used_band_inds
+        bls = packing.band_log10_scale(self.zps[band_inds], self.offsets[band_inds])
+        out = ctx.flux_batch(M0, theta, to(AV), to(W0), to(W1), to(eps), to(Ds), to(RV),
+                             to(band_indices, torch.int32), to(np.asarray(mask) != 0, torch.uint8), to(J_t),
+                             to(hsiao_interp), to(weights), bls, mag=mag)
+        return out.cpu().numpy().astype(np.float64)
+
+    def get_flux_batch(self, M0, theta, AV, W0, W1, eps, Ds, RV, band_indices, mask, J_t, hsiao_interp, weights):
+        """Reference :645-709: FLUXCAL (N_obs, N)."""
+        return self._forward(False, M0, theta, AV, W0, W1, eps, Ds, RV, band_indices, mask, J_t, hsiao_interp, weights)
+
+    def get_mag_batch(self, M0, theta, AV, W0, W1, eps, Ds, RV, band_indices, mask, J_t, hsiao_interp, weights):
+        """Reference :711-759: magnitudes (N_obs, N)."""
+        return self._forward(True, M0, theta, AV, W0, W1, eps, Ds, RV, band_indices, mask, J_t, hsiao_interp, weights)
+
+    # ------------------------------------------------------------------ fitting
+    def build_fit_data(self, t, flux, flux_err, filters, z, ebv_mw=0, peak_mjd=None, filt_map={}, drop_bands=[],
+                       mag=False):
+        """Data preparation of ``fit`` (reference :2061-2106): returns ``obs`` (10, n, 1) with band
+        indices into the compact used-band list, ``weights`` (1, 300, n_used) and ``band_inds``."""
+        if type(drop_bands) == str:
+            drop_bands = [drop_bands]
+        drop_bands = list(drop_bands)
+        t, flux, flux_err, filters = np.array(t, dtype=float), np.array(flux, dtype=float), \
+            np.array(flux_err, dtype=float), np.array(filters)
+        if mag:
+            flux = np.power(10, (27.5 - flux) / 2.5)
+            flux_err = (np.log(10) / 2.5) * flux * flux_err
+        if peak_mjd is not None:
+            t = (t - peak_mjd) / (1 + z)
+        keep = (t > self.tau_knots.min()) & (t < self.tau_knots.max())
+        flux, flux_err, filters, t = flux[keep], flux_err[keep], filters[keep], t[keep]
+        filters = np.array([filt_map.get(f, f) for f in filters])
+        for f in np.unique(filters):
+            if f not in self.band_dict.keys():
+                raise ValueError(f'Filter "{f}" not defined in BayeSN, either add a mapping to filt_map to ensure '
+                                 f'that your filter names match up with ones built-in or add some custom filters if '
+                                 f'you want to use your own')
+            if z > (self.band_lim_dict[f][0] / self.l_knots[0] - 1) or z < (
+                    self.band_lim_dict[f][1] / self.l_knots[-1] - 1):
+                drop_bands.append(f)
+        for f in drop_bands:
+            inds = filters != f
+            flux, flux_err, filters, t = flux[inds], flux_err[inds], filters[inds], t[inds]
+        n_data = len(t)
+        if n_data == 0:
+            raise ValueError('No data in rest-frame phase range covered by model, maybe you gave the wrong peak MJD?')
+        glob = np.array([self.band_dict[f] for f in filters])
+        band_inds = np.r_[0, np.unique(glob)]                 # NULL band + the bands in play
+        local = np.searchsorted(band_inds, glob)
+        data = np.zeros((10, n_data, 1))
+        data[0, :, 0] = t
+        data[1, :, 0] = flux
+        data[2, :, 0] = flux_err
+        data[4, :, 0] = local
+        data[5, :, 0] = z
+        data[7, :, 0] = self.cosmo.distmod(np.array([z]))[0]
+        data[8, :, 0] = ebv_mw
+        data[9, :, 0] = 1
+        weights = self._calculate_band_weights(data[-5, 0, :], data[-2, 0, :], band_inds)
+        return data, weights, band_inds
+
+    def fit_batch(self, obs, weights, band_inds=None, num_chains=4, num_warmup=250, num_samples=250,
+                  max_tree_depth=10, seed=0, RV=None, fix_tmax=False, fix_theta=False, theta_val=0.0, fix_AV=False,
+                  AV_val=0.0, init='median', return_device=False, q_init=None):
+        """Independent NUTS fits of N supernovae (the vmapped ``fit_vmap_mcmc`` of reference
+        :1809-1849).  Returns (samples dict with arrays shaped (chains, draws, [dim,] N) like
+        the reference after :1839-1848, extras dict)."""
+        import torch
+        rv_mode = self._rv_mode(RV)
+        ctx = self.prepare(obs, weights, band_inds, rv_mode, fix_tmax=bool(fix_tmax), fix_theta=bool(fix_theta),
+                           theta_val=float(theta_val), fix_AV=bool(fix_AV), AV_val=float(AV_val))
+        dev = f'cuda:{ctx.device}'
+        muhat = np.asarray(obs)[-3, 0, :]
+        if q_init is None:
+            q_init = self.init_to_median(muhat, num_chains, rv_mode, seed=seed, device=dev)
+        out = ctx.nuts(q_init, num_warmup=num_warmup, num_samples=num_samples, max_tree_depth=max_tree_depth,
+                       seed=seed)
+        torch.cuda.synchronize()
+        cons = self.constrain(out['samples'], rv_mode)     # (N, C, S, ...)
+        if return_device:
+            return cons, out
+        samples = {}
+        for k, v in cons.items():
+            v = v.cpu().numpy().astype(np.float64)
+            if v.ndim == 4:
+                samples[k] = v.transpose(1, 2, 3, 0) if k == 'eps' else v.transpose(1, 2, 0, 3)
+            else:
+                samples[k] = v.transpose(1, 2, 0)
+        stats = out['stats'].cpu().numpy()
+        samples['diverging'] = stats[..., 2].transpose(1, 2, 0) > 0
+        extras = {'accept_prob': stats[..., 0].transpose(1, 2, 0), 'num_steps': stats[..., 1].transpose(1, 2, 0),
+                  'potential_energy': stats[..., 3].transpose(1, 2, 0),
+                  'chain_info': out['chain_info'].cpu().numpy(), 'launches': ctx.launches()}
+        return samples, extras
+
+    def fit(self, t, flux, flux_err, filters, z, ebv_mw=0, peak_mjd=None, filt_map={}, print_summary=True,
+            file_prefix=None, drop_bands=[], fix_tmax=False, fix_theta=False, fix_AV=False, RV=False, mu_R=False,
+            sigma_R=False, mag=False, seed=0):
+        """Reference :1994-2168 (4 chains x (250 + 250), max_tree_depth 10)."""
+        data, band_weights, band_inds = self.build_fit_data(t, flux, flux_err, filters, z, ebv_mw, peak_mjd,
+                                                            filt_map, drop_bands, mag)
+        rv_arg = None
+        if RV == 'uniform':
+            rv_arg = 'uniform'
+        else:
+            if RV:
+                self.RV = float(RV)
+                self.model_type = 'fixed_RV'
+            elif mu_R:
+                if not sigma_R:
+                    raise ValueError('You have set a custom mu_R, please also set a custom sigma_R')
+                self.mu_R, self.sigma_R = float(mu_R), float(sigma_R)
+                self.model_type = 'pop_RV'
+        theta_val = 0
+        if fix_theta:
+            theta_val, fix_theta = fix_theta, True
+        AV_val = 0
+        if fix_AV:
+            AV_val, fix_AV = fix_AV, True
+        samples, extras = self.fit_batch(data, band_weights, band_inds, num_chains=4, num_warmup=250,
+                                         num_samples=250, max_tree_depth=10, seed=seed, RV=rv_arg,
+                                         fix_tmax=fix_tmax, fix_theta=fix_theta, theta_val=theta_val, fix_AV=fix_AV,
+                                         AV_val=AV_val)
+        samples.pop('diverging')
+        samples['potential_energy'] = extras['potential_energy'][..., 0]
+        if print_summary:
+            summary.print_summary({k: v for k, v in samples.items() if k not in ('potential_energy', 'eps')},
+                                  n_div=int((extras['chain_info'][..., 3]).sum()))
+        if peak_mjd is not None:
+            samples['peak_MJD'] = peak_mjd + samples['tmax'] * (1 + z)
+        muhat = self.cosmo.distmod(np.array([z]))[0]
+        muhat_err = 5
+        Ds_err = np.sqrt(muhat_err * muhat_err + self.sigma0 * self.sigma0)
+        samples['mu'] = np.random.normal(
+            (samples['Ds'] * np.power(muhat_err, 2) + muhat * np.power(self.sigma0, 2)) / np.power(Ds_err, 2),
+            np.sqrt((np.power(self.sigma0, 2) * np.power(muhat_err, 2)) / np.power(Ds_err, 2)))
+        samples['delM'] = samples['Ds'] - samples['mu']
+        if fix_tmax:
+            samples['tmax'] = np.zeros_like(samples['tmax'])
+        if fix_theta:
+            samples['theta'] = np.full_like(samples['theta'], theta_val)
+        if fix_AV:
+            samples['AV'] = np.full_like(samples['AV'], AV_val)
+        if file_prefix is not None:
+            summary.summary_table(samples).to_csv(f'{file_prefix}_fit_summary.csv')
+            with open(f'{file_prefix}_chains.pkl', 'wb') as file:
+                pickle.dump(samples, file)
+        return samples, (z, ebv_mw)
+
+    def fit_from_file(self, path, filt_map={}, peak_mjd_key='SEARCH_PEAKMJD', print_summary=True, file_prefix=None,
+                      drop_bands=[], fix_tmax=False, fix_theta=False, fix_AV=False, RV=False, mu_R=False,
+                      sigma_R=False, mag=False, seed=0):
+        """Reference :1926-1992 (SNANA text file)."""
+        meta, lc = snana.read_snana_ascii(path)
+        return self.fit(lc['MJD'], lc['FLUXCAL'], lc['FLUXCALERR'], lc['FLT'], meta['REDSHIFT_HELIO'],
+                        ebv_mw=meta['MWEBV'], peak_mjd=meta[peak_mjd_key], filt_map=filt_map,
+                        print_summary=print_summary, file_prefix=file_prefix, drop_bands=drop_bands,
+                        fix_tmax=fix_tmax, fix_theta=fix_theta, fix_AV=fix_AV, RV=RV, mu_R=mu_R, sigma_R=sigma_R,
+                        mag=mag, seed=seed)
+
+    # ------------------------------------------------------------------ simulation (reference :3103-3424)
+    def sample_del_M(self, N):
+        return np.random.normal(0, self.sigma0, N)
+
+    def sample_AV(self, N):
+        return np.random.exponential(self.tauA, N)
+
+    def sample_theta(self, N):
+        return np.random.normal(0, 1, N)
+
+    def sample_epsilon(self, N):
+        L, T = len(self.l_knots), len(self.tau_knots)
+        n_sig = (L - 2) * T
+        eps_tform = np.random.multivariate_normal(np.zeros(n_sig), np.eye(n_sig), N).T
+        eps = np.matmul(self.L_Sigma, eps_tform).T
+        eps = np.reshape(eps, (N, L - 2, T), order='F')
+        eps_full = np.zeros((N, L, T))
+        eps_full[:, 1:-1, :] = eps
+        return eps_full
+
+    def simulate_light_curve(self, t, N, bands, yerr=0, err_type='mag', z=0, zerr=1e-4, mu=0, ebv_mw=0, RV=None,
+                             logM=None, tmax=0, del_M=None, AV=None, theta=None, eps=None, mag=True,
+                             write_to_files=False, output_dir=None):
+        """Reference :3103-3345: same validation, same draw order from the global numpy RNG."""
+        def per_object(val, name):
+            val = np.array(val)
+            if len(val.shape) == 0:
+                return val.repeat(N)
+            if val.shape[0] != N:
+                raise ValueError(f'If not providing a scalar {name} value, array must be of same length as the '
+                                 f'number of objects to simulate, N')
+            return val
+        del_M = self.sample_del_M(N) if del_M is None else per_object(del_M, 'del_M')
+        AV = self.sample_AV(N) if AV is None else per_object(AV, 'AV')
+        theta = self.sample_theta(N) if theta is None else per_object(theta, 'theta')
+        L, T = self.l_knots.shape[0], self.tau_knots.shape[0]
+        if eps is None:
+            eps = self.sample_epsilon(N)
+        elif len(np.array(eps).shape) == 0:
+            if np.array(eps) == 0:
+                eps = np.zeros((N, L, T))
+            else:
+                raise ValueError('For epsilon, please pass an array-like object of shape (N, l_knots, tau_knots). '
+                                 'The only scalar value accepted is 0, which will effectively remove the effect of '
+                                 'epsilon')
+        else:
+            eps = np.array(eps)
+            if len(eps.shape) == 2 and eps.shape == (L, T):
+                eps = np.repeat(eps[None], N, axis=0)
+            if len(eps.shape) != 3 or eps.shape[0] != N or eps.shape[1] != L or eps.shape[2] != T:
+                raise ValueError('For epsilon, please pass an array-like object of shape (N, l_knots, tau_knots)')
+        ebv_mw = per_object(ebv_mw, 'ebv_mw').astype(float)
+        tmax = per_object(tmax, 'tmax').astype(float)
+        RV = per_object(self.RV if RV is None else RV, 'RV').astype(float)
+        z = per_object(z, 'z').astype(float)
+        if type(mu) == str and mu == 'z':
+            mu = self.cosmo.distmod(z)
+        else:
+            mu = per_object(mu, 'mu').astype(float)
+        param_dict = {'del_M': del_M, 'AV': AV, 'theta': theta, 'eps': eps, 'z': z, 'mu': mu, 'ebv_mw': ebv_mw,
+                      'RV': RV}
+        t = np.asarray(t, dtype=float)
+        for band in bands:
+            if band not in self.band_dict.keys():
+                raise ValueError(f'{band} is not present in filters yaml file')
+        if t.shape[0] == np.array(bands).shape[0]:
+            glob = np.array([self.band_dict[band] for band in bands])
+        else:
+            num_per_band = t.shape[0]
+            glob = np.repeat(np.array([self.band_dict[band] for band in bands]), num_per_band)
+            t = np.repeat(t[:, None], len(bands), axis=1).flatten(order='F')
+        band_inds = np.r_[0, np.unique(glob)]
+        band_indices = np.searchsorted(band_inds, glob)[:, None].repeat(N, axis=1).astype(int)
+        mask = np.ones_like(band_indices)
+        band_weights = self._calculate_band_weights(z, ebv_mw, band_inds)
+        tt = np.repeat(t[..., None], N, axis=1) - tmax[None, :]
+        hsiao_interp = np.array([HSIAO_PHASE0_INDEX + np.floor(tt), HSIAO_PHASE0_INDEX + np.ceil(tt),
+                                 np.remainder(tt, 1)])
+        J_t = self.J_t_map(tt).transpose(1, 2, 0)                      # (N, T, N_obs)
+        data = self._forward(bool(mag), self.M0, theta, AV, self.W0, self.W1, eps, mu + del_M, RV, band_indices,
+                             mask, J_t, hsiao_interp, band_weights, band_inds=band_inds)
+        yerr = np.array(yerr, dtype=float)
+        if err_type == 'mag' and not mag:
+            yerr = yerr * (np.log(10) / 2.5) * data
+        if len(yerr.shape) == 0:
+            yerr = np.ones_like(data) * yerr
+        elif len(yerr.shape) == 1:
+            assert data.shape[0] == yerr.shape[0], f'If passing a 1d array, shape of yerr must match number of ' \
+                                                   f'simulated data points per objects, {data.shape[0]}'
+            yerr = np.repeat(yerr[..., None], N, axis=1)
+        else:
+            assert data.shape == yerr.shape, f'If passing a 2d array, shape of yerr must match generated data ' \
+                                             f'shape of {data.shape}'
+        data = np.random.normal(data, yerr)
+        if write_to_files and mag:
+            if output_dir is None:
+                raise ValueError('If writing to SNANA files, please provide an output directory')
+            os.makedirs(output_dir, exist_ok=True)
+            for i in range(N):
+                flt = [self.inv_band_dict[band_inds[b]] for b in band_indices[:, i]]
+                snana.write_snana_lcfile(output_dir, f'{i}', tt[:, i] * (1 + z[i]), flt, data[:, i], yerr[:, i], 0,
+                                         z[i], z[i], zerr, ebv_mw[i])
+        elif write_to_files:
+            raise ValueError('If writing to SNANA files, please generate mags')
+        self._last_sim = dict(t=np.repeat(t[:, None], N, axis=1), band_indices=band_indices, band_inds=band_inds,
+                              band_weights=band_weights)
+        return data, yerr, param_dict
+
+    def simulated_obs_array(self, data, yerr, param_dict):
+        """Pack the output of the last ``simulate_light_curve(mag=False)`` call into the
+        reference's (10, N_obs, N) ``obs`` layout."""
+        sim = self._last_sim
+        N_obs, N = data.shape
+        obs = np.zeros((10, N_obs, N))
+        obs[0] = sim['t']
+        obs[1] = data
+        obs[2] = yerr
+        obs[4] = sim['band_indices']
+        obs[5] = param_dict['z'][None, :]
+        obs[6] = 1e-4
+        obs[7] = self.cosmo.distmod(param_dict['z'])[None, :]
+        obs[8] = param_dict['ebv_mw'][None, :]
+        obs[9] = 1
+        return obs, sim['band_weights'], sim['band_inds']
+
+    def get_flux_from_chains(self, t, bands, chains, zs, ebv_mws, mag=True, num_samples=None, mean=False):
+        """Reference :3426-3524: model photometry for posterior samples,
+        (N_sne, num_samples, n_bands, len(t))."""
+        if type(chains) == str:
+            with open(chains, 'rb') as file:
+                chains = pickle.load(file)
+        N_sne = chains['theta'].shape[2]
+        if num_samples is None:
+            num_samples = chains['theta'].shape[0] * chains['theta'].shape[1]
+        zs = np.atleast_1d(np.asarray(zs, dtype=float))
+        ebv_mws = np.atleast_1d(np.asarray(ebv_mws, dtype=float))
+        if mean:
+            num_samples = 1
+        band_list = isinstance(bands[0], list)
+        max_bands = max(len(b) for b in bands) if band_list else len(bands)
+        t = np.asarray(t, dtype=float)
+        flux_grid = np.zeros((N_sne, num_samples, max_bands, len(t)))
+        L, T = len(self.l_knots), len(self.tau_knots)
+        state = np.random.get_state()
+        for i in range(N_sne):
+            fit_bands = bands[i] if band_list else bands
+            fl = lambda k: chains[k][..., i].flatten(order='F')
+            theta, AV, tmax, mu, del_M = fl('theta'), fl('AV'), fl('tmax'), fl('mu'), fl('delM')
+            RV = fl('RV') if 'RV' in chains.keys() else None
+            eps = chains['eps'][..., i]
+            eps = eps.reshape((eps.shape[0] * eps.shape[1], eps.shape[2]), order='F')
+            eps = eps.reshape((eps.shape[0], L - 2, T), order='F')
+            eps_full = np.zeros((eps.shape[0], L, T))
+            eps_full[:, 1:-1, :] = eps
+            eps = eps_full
+            sl = slice(0, num_samples)
+            theta, AV, mu, eps, del_M, tmax = theta[sl], AV[sl], mu[sl], eps[sl], del_M[sl], tmax[sl]
+            if RV is not None:
+                RV = RV[sl]
+            if mean:
+                theta, AV, mu, eps, del_M, tmax = theta.mean()[None], AV.mean()[None], mu.mean()[None], \
+                    eps.mean(axis=0)[None], del_M.mean()[None], tmax.mean()[None]
+                if RV is not None:
+                    RV = RV.mean()[None]
+            lc, _, _ = self.simulate_light_curve(t, theta.shape[0], fit_bands, theta=theta, AV=AV, mu=mu, tmax=tmax,
+                                                 del_M=del_M, eps=eps, RV=RV, z=zs[i], write_to_files=False,
+                                                 ebv_mw=ebv_mws[i], yerr=0, mag=mag)
+            flux_grid[i, :, :len(fit_bands), :] = lc.T.reshape(num_samples, len(fit_bands), len(t))
+        np.random.set_state(state)
+        return flux_grid

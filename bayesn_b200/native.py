@@ -1,0 +1,218 @@
+"""ctypes binding of ``libbayesn_b200.so`` (C ABI in ``include/bayesn_b200.h``).
+
+There is no CPU fallback: if the library is missing or no CUDA device is present the product
+path raises.  Tensors are torch CUDA tensors used purely as device buffers (``data_ptr()``).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libbayesn_b200.so')
+
+NBINS, BPAD, NPHASE = 300, 304, 105
+RV_FIXED, RV_POP, RV_UNIFORM = 0, 1, 2
+
+_fp = C.POINTER(C.c_float)
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [('L', C.c_int32), ('T', C.c_int32), ('rv_mode', C.c_int32),
+                ('tau_knots', _fp), ('KD_t', _fp), ('J_l', _fp), ('hsiao', _fp), ('M_fitz', _fp), ('a_dust', _fp),
+                ('W0', _fp), ('W1', _fp), ('L_Sigma', _fp),
+                ('tauA', C.c_float), ('Ds_prior_sd', C.c_float),
+                ('RV', C.c_float), ('mu_R', C.c_float), ('sigma_R', C.c_float), ('trunc_R', C.c_float),
+                ('fix_tmax', C.c_int32), ('fix_theta', C.c_int32), ('fix_AV', C.c_int32),
+                ('theta_val', C.c_float), ('AV_val', C.c_float)]
+
+
+class DatasetDesc(C.Structure):
+    _fields_ = [('N', C.c_int32), ('N_obs', C.c_int32), ('n_b', C.c_int32),
+                ('obs4', C.c_void_p), ('n_valid', C.c_void_p), ('weights', C.c_void_p), ('support', C.c_void_p),
+                ('muhat', C.c_void_p), ('lconst', C.c_void_p)]
+
+
+class NutsCfg(C.Structure):
+    _fields_ = [('num_warmup', C.c_int32), ('num_samples', C.c_int32), ('num_chains', C.c_int32),
+                ('max_tree_depth', C.c_int32), ('target_accept', C.c_float), ('init_step_size', C.c_float),
+                ('adapt_step_size', C.c_int32), ('adapt_mass_matrix', C.c_int32),
+                ('regularize_mass_matrix', C.c_int32), ('seed', C.c_uint64)]
+
+
+EXPORTS = ['bayesn_abi_version', 'bayesn_ctx_create', 'bayesn_ctx_destroy', 'bayesn_last_error',
+           'bayesn_set_model', 'bayesn_bind_dataset', 'bayesn_param_dim', 'bayesn_logp_grad_fit',
+           'bayesn_flux_batch', 'bayesn_nuts_workspace_bytes', 'bayesn_nuts_fit', 'bayesn_launch_count']
+
+_lib = None
+
+
+def load_library():
+    """Load the shared library (fails loudly if it has not been built: run
+    ``python -c 'import __graft_entry__ as g; g.build()'`` or ``make -C bayesn_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f'{LIB_PATH} not found: the CUDA library has not been built. There is no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    lib.bayesn_abi_version.restype = C.c_int
+    lib.bayesn_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.bayesn_ctx_destroy.argtypes = [C.c_void_p]
+    lib.bayesn_ctx_destroy.restype = None
+    lib.bayesn_last_error.argtypes = [C.c_void_p]
+    lib.bayesn_last_error.restype = C.c_char_p
+    lib.bayesn_set_model.argtypes = [C.c_void_p, C.POINTER(ModelDesc)]
+    lib.bayesn_bind_dataset.argtypes = [C.c_void_p, C.POINTER(DatasetDesc)]
+    lib.bayesn_param_dim.argtypes = [C.c_void_p]
+    lib.bayesn_logp_grad_fit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bayesn_flux_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 12 + [
+        C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+    lib.bayesn_nuts_workspace_bytes.argtypes = [C.c_void_p, C.POINTER(NutsCfg)]
+    lib.bayesn_nuts_workspace_bytes.restype = C.c_size_t
+    lib.bayesn_nuts_fit.argtypes = [C.c_void_p, C.POINTER(NutsCfg)] + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]
+    lib.bayesn_launch_count.argtypes = [C.c_void_p]
+    lib.bayesn_launch_count.restype = C.c_longlong
+    _lib = lib
+    return lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+class Context:
+    """One device context: model tables + one bound data set."""
+
+    def __init__(self, device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError('bayesn_b200 needs a CUDA device (sm_100a); there is no CPU fallback.')
+        self.lib = load_library()
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = self.lib.bayesn_ctx_create(self.device, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f'bayesn_ctx_create({device}) failed with {rc}')
+        self.h = h
+        self._keep = {}
+        self.D = None
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.bayesn_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f'{what} failed ({rc}): {self.lib.bayesn_last_error(self.h).decode()}')
+
+    def launches(self):
+        return int(self.lib.bayesn_launch_count(self.h))
+
+    # ------------------------------------------------------------------ model
+    def set_model(self, *, tau_knots, KD_t, J_l, hsiao, M_fitz, a_dust, W0, W1, L_Sigma, tauA, Ds_prior_sd,
+                  rv_mode=RV_FIXED, RV=0.0, mu_R=0.0, sigma_R=1.0, trunc_R=1.2, fix_tmax=False, fix_theta=False,
+                  fix_AV=False, theta_val=0.0, AV_val=0.0):
+        arrs = dict(tau_knots=_f32(tau_knots), KD_t=_f32(KD_t), J_l=_f32(J_l), hsiao=_f32(hsiao),
+                    M_fitz=_f32(M_fitz), a_dust=_f32(a_dust), W0=_f32(W0), W1=_f32(W1), L_Sigma=_f32(L_Sigma))
+        L, T = arrs['W0'].shape
+        assert arrs['J_l'].shape == (NBINS, L) and arrs['hsiao'].shape == (NBINS, NPHASE)
+        assert arrs['M_fitz'].shape == (NBINS, 9) and arrs['KD_t'].shape == (T, T)
+        ne = (L - 2) * T
+        assert arrs['L_Sigma'].shape == (ne, ne)
+        d = ModelDesc()
+        d.L, d.T, d.rv_mode = L, T, int(rv_mode)
+        for k, a in arrs.items():
+            setattr(d, k, a.ctypes.data_as(_fp))
+        d.tauA, d.Ds_prior_sd = float(tauA), float(Ds_prior_sd)
+        d.RV, d.mu_R, d.sigma_R, d.trunc_R = float(RV), float(mu_R), float(sigma_R), float(trunc_R)
+        d.fix_tmax, d.fix_theta, d.fix_AV = int(bool(fix_tmax)), int(bool(fix_theta)), int(bool(fix_AV))
+        d.theta_val, d.AV_val = float(theta_val), float(AV_val)
+        self._check(self.lib.bayesn_set_model(self.h, C.byref(d)), 'bayesn_set_model')
+        self.D = int(self.lib.bayesn_param_dim(self.h))
+        self.L, self.T, self.n_eps = L, T, ne
+        return self.D
+
+    # ------------------------------------------------------------------ dataset
+    def bind_dataset(self, packed):
+        """``packed``: dict of torch CUDA tensors from :func:`bayesn_b200.packing.pack_dataset`."""
+        self._keep['data'] = packed
+        d = DatasetDesc()
+        d.N, d.N_obs, d.n_b = int(packed['N']), int(packed['N_obs']), int(packed['n_b'])
+        for k in ('obs4', 'n_valid', 'weights', 'support', 'muhat', 'lconst'):
+            setattr(d, k, packed[k].data_ptr())
+        self._check(self.lib.bayesn_bind_dataset(self.h, C.byref(d)), 'bayesn_bind_dataset')
+        self.N = d.N
+
+    @staticmethod
+    def _stream():
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+
+    def logp_grad(self, q):
+        """q: (N, C, D) float32 CUDA tensor -> (logp (N, C), grad (N, C, D))."""
+        import torch
+        assert q.is_cuda and q.dtype == torch.float32 and q.is_contiguous()
+        N, Cn, D = q.shape
+        assert N == self.N and D == self.D
+        logp = torch.empty((N, Cn), dtype=torch.float32, device=q.device)
+        grad = torch.empty_like(q)
+        self._check(self.lib.bayesn_logp_grad_fit(self.h, Cn, q.data_ptr(), logp.data_ptr(), grad.data_ptr(),
+                                                  self._stream()), 'bayesn_logp_grad_fit')
+        return logp, grad
+
+    def nuts(self, q_init, num_warmup=250, num_samples=250, max_tree_depth=10, target_accept=0.8,
+             init_step_size=1.0, adapt_step_size=True, adapt_mass_matrix=True, regularize_mass_matrix=True, seed=0,
+             out=None):
+        """Run the device NUTS for every (SN, chain).  Returns dict of CUDA tensors."""
+        import torch
+        assert q_init.is_cuda and q_init.dtype == torch.float32 and q_init.is_contiguous()
+        N, Cn, D = q_init.shape
+        assert N == self.N and D == self.D
+        cfg = NutsCfg(int(num_warmup), int(num_samples), int(Cn), int(max_tree_depth), float(target_accept),
+                      float(init_step_size), int(adapt_step_size), int(adapt_mass_matrix),
+                      int(regularize_mass_matrix), int(seed) & 0xFFFFFFFFFFFFFFFF)
+        wb = int(self.lib.bayesn_nuts_workspace_bytes(self.h, C.byref(cfg)))
+        dev = q_init.device
+        if out is None:
+            out = {}
+        ws = out.get('work')
+        if ws is None or ws.numel() * 4 < wb:
+            ws = out['work'] = torch.empty((wb + 3) // 4, dtype=torch.float32, device=dev)
+        for name, shape in (('samples', (N, Cn, num_samples, D)), ('stats', (N, Cn, num_samples, 4)),
+                            ('chain_info', (N, Cn, 4 + D))):
+            t = out.get(name)
+            if t is None or tuple(t.shape) != shape:
+                out[name] = torch.empty(shape, dtype=torch.float32, device=dev)
+        self._check(self.lib.bayesn_nuts_fit(self.h, C.byref(cfg), q_init.data_ptr(), out['samples'].data_ptr(),
+                                             out['stats'].data_ptr(), out['chain_info'].data_ptr(), ws.data_ptr(),
+                                             ws.numel() * 4, self._stream()), 'bayesn_nuts_fit')
+        return out
+
+    def flux_batch(self, M0, theta, AV, W0, W1, eps, Ds, RV, band_indices, mask, J_t, hsiao_interp, weights,
+                   band_log10_scale, mag=False):
+        """Forward model with the reference's array layouts; all array arguments are CUDA tensors."""
+        import torch
+        N_obs, N = band_indices.shape
+        n_b = weights.shape[2]
+        f32 = lambda t: t.to(torch.float32).contiguous()
+        theta, AV, W0, W1, eps, Ds, RV = map(f32, (theta, AV, W0, W1, eps, Ds, RV))
+        J_t, hsiao_interp, weights = map(f32, (J_t, hsiao_interp, weights))
+        band_indices = band_indices.to(torch.int32).contiguous()
+        mask = mask.to(torch.uint8).contiguous()
+        out = torch.empty((N_obs, N), dtype=torch.float32, device=theta.device)
+        bs = np.ascontiguousarray(np.asarray(band_log10_scale, dtype=np.float64))
+        assert bs.shape == (n_b,)
+        self._check(self.lib.bayesn_flux_batch(
+            self.h, N, N_obs, n_b, int(bool(mag)), float(M0), theta.data_ptr(), AV.data_ptr(), W0.data_ptr(),
+            W1.data_ptr(), eps.data_ptr(), Ds.data_ptr(), RV.data_ptr(), band_indices.data_ptr(), mask.data_ptr(),
+            J_t.data_ptr(), hsiao_interp.data_ptr(), weights.data_ptr(), bs.ctypes.data_as(C.POINTER(C.c_double)),
+            out.data_ptr(), self._stream()), 'bayesn_flux_batch')
+        return out

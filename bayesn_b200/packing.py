@@ -1,0 +1,66 @@
+"""Pack the reference's ``obs`` (10, N_obs, N) / ``weights`` (N, 300, n_b) arrays
+(``bayesn/bayesn_model.py:2096-2106``, ``:2711-2730``) into the float32 device layout the
+kernels read (``include/bayesn_b200.h``: ``bayesn_dataset_desc``)."""
+import math
+
+import numpy as np
+
+from .native import BPAD, NBINS
+
+
+def band_log10_scale(zps, offsets):
+    """log10 of the FLUXCAL scale of each band: 0.4 (27.5 - offset) - zp / 2.5 (reference :704-707)."""
+    return 0.4 * (27.5 - np.asarray(offsets, dtype=np.float64)) - np.asarray(zps, dtype=np.float64) / 2.5
+
+
+def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, device='cuda', chunk=8192):
+    """Returns a dict of torch tensors on ``device``.
+
+    * valid (mask != 0) observations are moved to the front of each SN; ``n_valid`` counts them;
+    * the band scale 10^(0.4(27.5-offset) - zp/2.5 - 0.4(M0 + muhat)) is folded into the weight
+      tile in float64 before rounding to float32, so the kernel never forms 10^27-sized factors;
+    * ``support`` is the exact non-zero extent of each (SN, band) row;
+    * ``lconst`` collects every parameter-independent term of the log joint density.
+    """
+    import torch
+    obs = np.asarray(obs, dtype=np.float64)
+    N_obs, N = obs.shape[1], obs.shape[2]
+    n_b = weights.shape[2]
+    assert weights.shape[0] == N and weights.shape[1] == NBINS
+    t, y, sig = obs[0].T, obs[1].T, obs[2].T
+    band = np.rint(obs[-6].T).astype(np.int32)
+    mask = obs[-1].T != 0
+    muhat = np.ascontiguousarray(obs[-3, 0, :])
+    order = np.argsort(~mask, axis=1, kind='stable')
+    take = lambda a: np.take_along_axis(a, order, axis=1)
+    t, y, sig, band, mask = take(t), take(y), take(sig), take(band), take(mask)
+    n_valid = mask.sum(axis=1).astype(np.int32)
+    obs4 = np.zeros((N, N_obs, 4), dtype=np.float32)
+    safe_sig = np.where(mask, sig, 1.0)
+    obs4[..., 0] = np.where(mask, t, 0.0)
+    obs4[..., 1] = np.where(mask, y, 0.0)
+    obs4[..., 2] = np.where(mask, 1.0 / safe_sig, 0.0)
+    obs4[..., 3] = np.where(mask, band, 0).astype(np.int32).view(np.float32)
+    if np.any((band < 0) | (band >= n_b)):
+        raise ValueError('band index out of range of the weights array')
+    half_l2pi = 0.5 * math.log(2 * math.pi)
+    lconst = np.sum(np.where(mask, -np.log(safe_sig) - half_l2pi, 0.0), axis=1)
+    lconst += -half_l2pi * (1 + n_eps) - math.log(tauA) - math.log(Ds_prior_sd) - half_l2pi
+    bscale = band_log10_scale(zps, offsets)
+    assert bscale.shape[0] == n_b
+    wt = torch.zeros((N, n_b, BPAD), dtype=torch.float32, device=device)
+    sup = torch.zeros((N, n_b, 2), dtype=torch.int32, device=device)
+    for s0 in range(0, N, chunk):
+        w = np.asarray(weights[s0:s0 + chunk], dtype=np.float64)                  # (n, 300, n_b)
+        sc = 10.0 ** (bscale[None, :] - 0.4 * (M0 + muhat[s0:s0 + chunk, None]))   # (n, n_b)
+        w32 = (np.transpose(w, (0, 2, 1)) * sc[:, :, None]).astype(np.float32)     # (n, n_b, 300)
+        nz = w32 != 0
+        any_nz = nz.any(axis=2)
+        first = np.where(any_nz, nz.argmax(axis=2), 0)
+        last = np.where(any_nz, NBINS - nz[:, :, ::-1].argmax(axis=2), 0)
+        wt[s0:s0 + chunk, :, :NBINS] = torch.from_numpy(w32).to(device)
+        sup[s0:s0 + chunk] = torch.from_numpy(np.stack([first, last], axis=-1).astype(np.int32)).to(device)
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    return dict(N=N, N_obs=N_obs, n_b=n_b, obs4=to(obs4), n_valid=to(n_valid), weights=wt, support=sup,
+                muhat=to(muhat.astype(np.float32)), lconst=to(lconst.astype(np.float32)),
+                muhat64=muhat, order=order)

@@ -249,7 +249,8 @@ class FilterSet:
             above = np.where(thr > 0.01 * thr.max())[0]
             trans = np.interp(bw, lam, thr, left=0, right=0)
             num = bw * trans * dlam
-            weights.append(num / num.sum())
+            with np.errstate(divide='ignore', invalid='ignore'):
+                weights.append(num / num.sum())
             if val['magsys'] == 'ab':
                 fstd = ab_standard_flam(lam)
             else:

@@ -1,0 +1,144 @@
+/*
+ * bayesn_b200.h - C ABI of libbayesn_b200.so, the B200 (sm_100a) implementation of BayeSN's
+ * data-parallel hot path: SED forward model + analytic gradient inside a device-resident,
+ * batched NUTS sampler.
+ *
+ * The reference (bayesn v0.4.1) has no FFI layer: its seam is the Python method surface of
+ * `SEDmodel`.  Each entry point below names the reference code it replaces (file:line under
+ * /root/reference).  `bayesn_b200/native.py` binds these with ctypes; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; bayesn_last_error(ctx) gives the text.
+ *  - "host" pointers are read during the call and copied; "device" pointers are CUDA device
+ *    memory owned by the caller, must stay valid until the stream work that uses them is done;
+ *    the library never frees them.  Dataset pointers are retained until the next
+ *    bayesn_bind_dataset / bayesn_ctx_destroy.
+ *  - all kernels are launched asynchronously on `stream` (a cudaStream_t passed as void*;
+ *    NULL = legacy default stream).  A ctx is bound to one device; do not use one ctx from two
+ *    host threads at once.
+ *  - FP32 device data, int32 indices.  Wavelength-bin rows are padded to BAYESN_BPAD floats.
+ */
+#ifndef BAYESN_B200_H
+#define BAYESN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BAYESN_NBINS 300      /* spectrum_bins, bayesn/bayesn_model.py:295 */
+#define BAYESN_BPAD 304       /* row stride of every per-bin table (16-byte aligned rows) */
+#define BAYESN_NPHASE 105     /* Hsiao phase grid -19..85, bayesn/bayesn_model.py:274 */
+#define BAYESN_MAX_L 12
+#define BAYESN_MAX_T 10
+
+typedef struct bayesn_ctx bayesn_ctx;
+
+/* RV treatment of the fit model: which numpyro model function the log-density follows. */
+enum { BAYESN_RV_FIXED = 0,    /* fit_model_globalRV  bayesn/bayesn_model.py:883-945  */
+       BAYESN_RV_POP = 1,      /* fit_model_popRV     bayesn/bayesn_model.py:996-1060 */
+       BAYESN_RV_UNIFORM = 2   /* fit_model_uniformRV bayesn/bayesn_model.py:818-881  */ };
+
+/* Static model tables (all HOST pointers, row-major, float32).  Replaces what
+ * SEDmodel.__init__ / _setup_band_weights / _load_hsiao_template keep as attributes
+ * (bayesn/bayesn_model.py:236-252, :483-497, :278-285). */
+typedef struct {
+    int32_t L, T;             /* len(l_knots), len(tau_knots) */
+    int32_t rv_mode;          /* BAYESN_RV_* */
+    const float* tau_knots;   /* [T] */
+    const float* KD_t;        /* [T][T]   invKD_irr(tau_knots) */
+    const float* J_l;         /* [300][L] spline_coeffs_irr(model_wave, l_knots) */
+    const float* hsiao;       /* [300][105] Hsiao template on the model grid */
+    const float* M_fitz;      /* [300][9] F99 spline basis */
+    const float* a_dust;      /* [300] 1 + (M_fitz yk(RV))/RV for the global RV (RV_FIXED only) */
+    const float* W0;          /* [L][T] */
+    const float* W1;          /* [L][T] */
+    const float* L_Sigma;     /* [n_eps][n_eps], n_eps = (L-2)*T */
+    float tauA;               /* A_V ~ Exponential(1/tauA) */
+    float Ds_prior_sd;        /* sqrt(5^2 + sigma0^2), bayesn/bayesn_model.py:937-940 */
+    float RV, mu_R, sigma_R, trunc_R;
+    int32_t fix_tmax, fix_theta, fix_AV;   /* fit() flags, bayesn/bayesn_model.py:914-918 */
+    float theta_val, AV_val;
+} bayesn_model_desc;
+
+/* One data set of N supernovae (all DEVICE pointers).  This is the packed, float32 form of the
+ * reference's `obs` (10, N_obs, N) array and `weights` (N, 300, n_b) array
+ * (bayesn/bayesn_model.py:2096-2106, :2711-2730); bayesn_b200/model.py builds it.
+ *   obs4[s][o]   = {phase t, FLUXCAL y, 1/sigma, band index as float}; valid observations first
+ *   n_valid[s]   = number of unmasked observations of SN s (<= N_obs)
+ *   weights[s][k][BAYESN_BPAD] = band weight * 10^(0.4(27.5-offset_k) - zp_k/2.5 - 0.4(M0+muhat_s))
+ *   support[s][k] = {first, one-past-last} bin with a non-zero weight (exact zeros only)
+ *   muhat[s]     = fiducial distance modulus;  lconst[s] = data-only log-density constant */
+typedef struct {
+    int32_t N, N_obs, n_b;
+    const float* obs4;
+    const int32_t* n_valid;
+    const float* weights;
+    const int32_t* support;
+    const float* muhat;
+    const float* lconst;
+} bayesn_dataset_desc;
+
+/* NUTS configuration: numpyro.infer.NUTS / MCMC arguments at the reference call sites
+ * bayesn/bayesn_model.py:1798-1802, :1830-1833, :2110-2141. */
+typedef struct {
+    int32_t num_warmup, num_samples, num_chains, max_tree_depth;
+    float target_accept, init_step_size;
+    int32_t adapt_step_size, adapt_mass_matrix, regularize_mass_matrix;
+    uint64_t seed;
+} bayesn_nuts_cfg;
+
+int bayesn_ctx_create(int device, bayesn_ctx** out);
+void bayesn_ctx_destroy(bayesn_ctx* ctx);
+const char* bayesn_last_error(bayesn_ctx* ctx);
+int bayesn_abi_version(void);
+
+int bayesn_set_model(bayesn_ctx* ctx, const bayesn_model_desc* model);
+int bayesn_bind_dataset(bayesn_ctx* ctx, const bayesn_dataset_desc* data);
+
+/* Dimension of the unconstrained per-SN parameter vector: n_eps + 4 (+1 if RV is sampled).
+ * Layout: [eps_tform[0..n_eps), theta, log A_V, logit((tmax+10)/20), Ds, (logit RV-transform)]. */
+int bayesn_param_dim(bayesn_ctx* ctx);
+
+/* Log joint density (unconstrained space, incl. log|det J|) and its gradient for every
+ * (SN, chain): one call = what numpyro evaluates per leapfrog through
+ * fit_model_globalRV / popRV / uniformRV + JAX reverse-mode AD.
+ *   q    [N][n_chains][D]  device, in
+ *   logp [N][n_chains]     device, out
+ *   grad [N][n_chains][D]  device, out */
+int bayesn_logp_grad_fit(bayesn_ctx* ctx, int n_chains, const float* q, float* logp, float* grad, void* stream);
+
+/* Forward model only: SEDmodel.get_flux_batch (bayesn/bayesn_model.py:645-709) when mag == 0,
+ * SEDmodel.get_mag_batch (:711-759) when mag != 0.  Same argument meaning and array layouts as
+ * the reference (device float32 / int32):
+ *   theta, AV, Ds, RV [N]; eps [N][L][T]; W0, W1 [L][T]; band_indices [N_obs][N];
+ *   mask [N_obs][N] (uint8); J_t [N][T][N_obs]; hsiao_interp [3][N_obs][N];
+ *   weights [N][300][n_b]; band_log10_scale [n_b] (HOST, double) =
+ *   0.4*(27.5 - offset_k) - zp_k/2.5; out [N_obs][N]. */
+int bayesn_flux_batch(bayesn_ctx* ctx, int N, int N_obs, int n_b, int mag, float M0, const float* theta,
+                      const float* AV, const float* W0, const float* W1, const float* eps, const float* Ds,
+                      const float* RV, const int32_t* band_indices, const uint8_t* mask, const float* J_t,
+                      const float* hsiao_interp, const float* weights, const double* band_log10_scale, float* out,
+                      void* stream);
+
+/* Device-resident batched NUTS over every (SN, chain) of the bound data set: replaces the
+ * numpyro MCMC(NUTS(fit_model_*)) runs at bayesn/bayesn_model.py:1830-1837 and :2128-2141.
+ *   q_init  [N][C][D]           device, in   initial unconstrained positions
+ *   samples [N][C][S][D]        device, out  unconstrained draws after warm-up
+ *   stats   [N][C][S][4]        device, out  {accept_prob, n_leapfrog, diverging, potential_energy}
+ *   chain_info [N][C][4+D]      device, out  {final step size, mean accept (sampling), total
+ *                                              leapfrogs, divergences, inverse mass diag[D]}
+ *   work, work_bytes            device scratch of at least bayesn_nuts_workspace_bytes() */
+size_t bayesn_nuts_workspace_bytes(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg);
+int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_init, float* samples, float* stats,
+                    float* chain_info, void* work, size_t work_bytes, void* stream);
+
+/* Number of kernel launches this ctx has issued (for bench accounting). */
+long long bayesn_launch_count(bayesn_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
