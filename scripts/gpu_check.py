@@ -13,7 +13,7 @@ def run(model_name, bands, t, N=8, C=3, rv=None, seed=1):
     np.random.seed(seed)
     ref = RefSED(model_name, bands=bands)
     z = np.random.uniform(0.015, 0.08, N)
-    data, yerr, pd, (tt, bidx, bw) = ref.simulate_light_curve(t, N, bands, yerr=0.05, z=z, mu='z', mag=False)
+    data, yerr, pd, (tt, bidx, bw) = ref.simulate_light_curve(t, N, bands, yerr=0.05, z=z, mu='z', mag=False, RV=(None if ref.model_type=='fixed_RV' else ref.mu_R))
     N_obs = data.shape[0]
     obs = np.zeros((10, N_obs, N)); obs[0]=tt; obs[1]=data; obs[2]=yerr; obs[4]=bidx; obs[5]=z[None]; obs[6]=1e-4
     obs[7]=ref.distmod(z)[None]; obs[9]=1
@@ -51,3 +51,12 @@ run('M20_model', ['B_CSP','V_CSP','r_CSP','i_CSP','Y_RC','J_RC1','H_RC'], t12, C
 run('pop_RV_model', ['g_PS1','r_PS1','i_PS1','z_PS1'], t12, C=4)
 run('T21_model', ['g_PS1','r_PS1','i_PS1','z_PS1'], t12, rv='uniform', C=2)
 run('G25_85day_model', ['g_PS1','r_PS1','i_PS1','z_PS1'], t12, C=4)
+
+# ---- short NUTS run on SN 2016W -------------------------------------------------------------
+import time
+m = SEDmodel(load_model='T21_model')
+t0 = time.time()
+samples, sn_props = m.fit_from_file(m.example_lc, filt_map={'g': 'g_PS1', 'r': 'r_PS1', 'i': 'i_PS1', 'z': 'z_PS1'})
+print('fit wall', time.time() - t0)
+for k in ['AV', 'Ds', 'theta', 'tmax', 'mu']:
+    print(k, samples[k].mean(), samples[k].std())

@@ -21,8 +21,9 @@ def make_case(model_name, bands, t, N=8, seed=1, mask_some=True, ebv_mw=0.0, zra
     ref = ref_model(model_name, bands)
     z = np.random.uniform(zrange[0], zrange[1], N)
     ebv = np.full(N, ebv_mw)
+    RV = None if ref.model_type == 'fixed_RV' else ref.mu_R
     data, yerr_a, pd, (tt, bidx, bw) = ref.simulate_light_curve(t, N, bands, yerr=yerr, z=z, mu='z', mag=mag,
-                                                                ebv_mw=ebv, err_type='mag')
+                                                                ebv_mw=ebv, err_type='mag', RV=RV)
     N_obs = data.shape[0]
     obs = np.zeros((10, N_obs, N))
     obs[0], obs[1], obs[2], obs[4] = tt, data, yerr_a, bidx
