@@ -1,4 +1,5 @@
 // bayesn_capi.cu - extern "C" boundary of libbayesn_b200.so (see include/bayesn_b200.h).
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -285,6 +286,49 @@ int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_
     for (size_t i = 0; i < 24; ++i) nd.win_end[i] = i < ends.size() ? ends[i] : 0x7fffffff;
     NutsCall call{ctx, nd, q_init, samples, stats, chain_info, (float*)work, (cudaStream_t)stream};
     return dispatch(ctx, /*stage=*/cfg->num_chains >= 2, call);
+}
+
+int bayesn_init_to_median(bayesn_ctx* ctx, int n_chains, uint64_t seed, float* q, void* stream) {
+    if (!ctx) return -1;
+    if (!ctx->have_model || !ctx->have_data) return fail(ctx, -1, "set_model and bind_dataset first");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    InitArgs A{};
+    A.N = ctx->D.N; A.C = n_chains; A.D = ctx->M.D; A.n_eps = ctx->M.n_eps; A.rv_mode = ctx->M.rv_mode;
+    A.tauA = 1.f / ctx->M.inv_tauA; A.sdD = 1.f / sqrtf(ctx->M.inv_sd2); A.muhat = ctx->D.muhat;
+    A.seed_lo = (unsigned)(seed & 0xffffffffu); A.seed_hi = (unsigned)(seed >> 32); A.q = q;
+    const long long total = (long long)A.N * A.C * A.D;
+    init_median_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+int bayesn_ffma_peak(bayesn_ctx* ctx, double* tflops_out) {
+    if (!ctx || !tflops_out) return -1;
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CU_CHECK(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float* d = nullptr;
+    CU_CHECK(ctx, cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        ffma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999f, 1e-3f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    CU_CHECK(ctx, cudaGetLastError());
+    *tflops_out = best;
+    return 0;
 }
 
 int bayesn_flux_batch(bayesn_ctx* ctx, int N, int N_obs, int n_b, int mag, float M0, const float* theta,

@@ -294,7 +294,7 @@ __device__ __forceinline__ float vget(const float (&v)[VPL], int i) {
 // ------------------------------------------------------------------------------------------
 template <int LP, int TP, int VPL, bool RVFREE>
 __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx& c, const float* __restrict__ hs,
-                                               const float (&q)[VPL], float& logp_out, float (&grad)[VPL], int lane) {
+                                               const float (&q)[VPL], double& logp_out, float (&grad)[VPL], int lane) {
     using DM = Dims<LP, TP>;
     constexpr int LP4 = DM::LP4, UST = DM::UST, NPAIR = DM::NPAIR;
     const int L = M.L, T = M.T, ne = M.n_eps;
@@ -303,7 +303,10 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     const float theta_s = vget<VPL>(q, ne + 0);
     const float uAV = vget<VPL>(q, ne + 1);
     const float ut = vget<VPL>(q, ne + 2);
-    const float Ds = vget<VPL>(q, ne + 3);
+    // element ne+3 is the SHIFTED distance dD = Ds - muhat: with Ds ~ 35 the float32 spacing
+    // (3.8e-6) times the gradient far from the mode (1e6) is a potential-energy noise of order 1,
+    // enough to stall step-size adaptation; around 0 the spacing is 30x finer.
+    const float dD = vget<VPL>(q, ne + 3);
     const float AV_s = expf(uAV);
     const float sg = 1.f / (1.f + expf(-ut));
     const float tmax_s = -10.f + 20.f * sg;
@@ -326,7 +329,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         }
     }
     const float AVc = -C2 * AV;
-    const float S = exp2f(-C2 * (Ds - c.muhat));
+    const float S = exp2f(-C2 * dD);
 
     // ---- eps = L_Sigma eps_tform, W = W0 + theta W1 + eps ---------------------------------
 #pragma unroll
@@ -420,7 +423,10 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     __syncwarp();
 
     // ---- band-pass integrals, lanes over wavelength bins --------------------------------------
-    float logL = 0.f, gDs = 0.f, gAV = 0.f, gT = 0.f, gRV = 0.f;
+    // log L is accumulated in double: far from the mode |log L| reaches 1e6 while NUTS needs energy
+    // differences to ~1e-2, which float32 partial sums cannot hold (ulp(7.5e5) = 0.06)
+    double logL = 0.0;
+    float gDs = 0.f, gAV = 0.f, gT = 0.f, gRV = 0.f;
     for (int o = 0; o < c.nobs; ++o) {
         const float4 ob = c.obs[o];
         const int k = __float_as_int(ob.w);
@@ -476,7 +482,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         const float flux = S * F;
         const float resid = ob.y - flux;
         const float chi = resid * ob.z;
-        logL = fmaf(-0.5f * chi, chi, logL);
+        logL += (double)(-0.5f * chi * chi);
         const float r = chi * ob.z;
         const float coef = r * S;
         gDs = fmaf(-KAPPA * r, flux, gDs);
@@ -518,7 +524,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     __syncwarp();
 
     // ---- priors, Jacobians, assemble gradient in the unconstrained space ---------------------
-    float lp = logL + c.lconst;
+    double lp = logL + (double)c.lconst;
     float ss = 0.f;
 #pragma unroll
     for (int s = 0; s < VPL; ++s) {
@@ -545,7 +551,6 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     lp += logf(sg) + logf(1.f - sg);
     float g_ut = (M.fix_tmax ? 0.f : -gT) * 20.f * sg * (1.f - sg) + (1.f - 2.f * sg);
     // Ds ~ N(muhat, sd)
-    float dD = Ds - c.muhat;
     lp += -0.5f * dD * dD * M.inv_sd2;
     float g_Ds = gDs - dD * M.inv_sd2;
     float g_uR = 0.f;

@@ -24,10 +24,11 @@ __global__ void __launch_bounds__(WPB * 32) logp_grad_kernel(ModelDev M, DataDev
     for (int s = 0; s < VPL; ++s) {
         int i = lane + 32 * s;
         q[s] = (i < M.D) ? q_in[unit * M.D + i] : 0.f;
+        if (i == M.n_eps + 3) q[s] -= c.muhat;     // the evaluator works with Ds - muhat
     }
-    float lp;
+    double lp;
     eval_logp_grad<LP, TP, VPL, RVFREE>(M, c, M.hs, q, lp, g, lane);
-    if (lane == 0) logp_out[unit] = lp;
+    if (lane == 0) logp_out[unit] = (float)lp;
 #pragma unroll
     for (int s = 0; s < VPL; ++s) {
         int i = lane + 32 * s;
@@ -179,7 +180,7 @@ __device__ __forceinline__ float logaddexpf(float a, float b) {
 }
 
 template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
-__global__ void __launch_bounds__(WPB * 32) nuts_kernel(ModelDev M, DataDev Dd, NutsDev cfg, int ntile,
+__global__ void __launch_bounds__(WPB * 32, 4) nuts_kernel(ModelDev M, DataDev Dd, NutsDev cfg, int ntile,
                                                         const float* __restrict__ q_init, float* __restrict__ samples,
                                                         float* __restrict__ stats, float* __restrict__ chain_info,
                                                         float* __restrict__ work) {
@@ -203,20 +204,14 @@ __global__ void __launch_bounds__(WPB * 32) nuts_kernel(ModelDev M, DataDev Dd, 
 #pragma unroll
     for (int s = 0; s < VPL; ++s) {
         z[s] = own[s] ? q_init[unit * D + lane + 32 * s] : 0.f;
+        if (lane + 32 * s == M.n_eps + 3) z[s] -= c.muhat;   // sample Ds - muhat (float32 resolution)
         im[s] = own[s] ? 1.f : 0.f;
         tmp[s] = 0.f;
     }
     io.st(V_WMEAN, tmp);
     io.st(V_WM2, tmp);
-    float pe;   // potential energy = -log p
-    {
-        float lp;
-        eval_logp_grad<LP, TP, VPL, RVFREE>(M, c, M.hs, z, lp, g, lane);
-        pe = -lp;
-#pragma unroll
-        for (int s = 0; s < VPL; ++s) g[s] = -g[s];
-    }
     // adaptation state (numpyro warmup_adapter / dual_averaging / welford_covariance)
+    double pe = 0.0;   // potential energy = -log p (double: see eval_logp_grad)
     float step = cfg.init_step;
     float da_x = 0.f, da_xavg = 0.f, da_gavg = 0.f, da_prox = logf(10.f * step);
     int da_t = 0, wf_n = 0, window = 0;
@@ -225,128 +220,185 @@ __global__ void __launch_bounds__(WPB * 32) nuts_kernel(ModelDev M, DataDev Dd, 
     int n_div = 0;
     const int n_iter = cfg.num_warmup + cfg.num_samples;
 
-    for (int it = 0; it < n_iter; ++it) {
-        uint32_t rk = 0;   // draw counter within this transition
-        // ---- momentum refresh r ~ N(0, M) -------------------------------------------------
-        {
-            uint4 ra = philox4x32(make_uint4((uint32_t)it, 0x40000000u, (uint32_t)lane, (uint32_t)unit), key);
-            float n0 = sqrtf(-2.f * logf(u01(ra.x) + 5.9604644775390625e-8f));
-            float n1 = sqrtf(-2.f * logf(u01(ra.z) + 5.9604644775390625e-8f));
-            float sn0, cs0, sn1, cs1;
-            sincospif(2.f * u01(ra.y), &sn0, &cs0);
-            sincospif(2.f * u01(ra.w), &sn1, &cs1);
-            float nrm[4] = {n0 * cs0, n0 * sn0, n1 * cs1, n1 * sn1};
+    // per-transition / per-doubling state
+    int it = 0;
+    uint32_t rk = 0;
+    double E0 = 0.0, prop_pe = 0.0, sprop_pe = 0.0;
+    float w_main = 0.f, sum_acc = 0.f;
+    int depth = 0, n_prop = 0;
+    bool turning = false, diverging = false;
+    bool going_right = false;
+    float u_main = 0.f, eps_dir = 0.f;
+    int n_max = 1, n_sub = 0;
+    bool s_turn = false, s_div = false;
+    float w_sub = -INFINITY, s_acc = 0.f;
+
+    auto begin_transition = [&]() {
+        rk = 0;
+        // momentum refresh r ~ N(0, M)
+        uint4 ra = philox4x32(make_uint4((uint32_t)it, 0x40000000u, (uint32_t)lane, (uint32_t)unit), key);
+        float n0 = sqrtf(-2.f * logf(u01(ra.x) + 5.9604644775390625e-8f));
+        float n1 = sqrtf(-2.f * logf(u01(ra.z) + 5.9604644775390625e-8f));
+        float sn0, cs0, sn1, cs1;
+        sincospif(2.f * u01(ra.y), &sn0, &cs0);
+        sincospif(2.f * u01(ra.w), &sn1, &cs1);
+        float nrm[4] = {n0 * cs0, n0 * sn0, n1 * cs1, n1 * sn1};
 #pragma unroll
-            for (int s = 0; s < VPL; ++s) r[s] = own[s] ? nrm[s & 3] * rsqrtf(im[s]) : 0.f;
-        }
-        const float E0 = pe + 0.5f * vdot_im<VPL>(im, r, r);
+        for (int s = 0; s < VPL; ++s) r[s] = own[s] ? nrm[s & 3] * rsqrtf(im[s]) : 0.f;
+        E0 = pe + 0.5 * (double)vdot_im<VPL>(im, r, r);
         io.st(V_ZL, z); io.st(V_RL, r); io.st(V_GL, g);
         io.st(V_ZR, z); io.st(V_RR, r); io.st(V_GR, g);
         io.st(V_ZP, z); io.st(V_GP, g); io.st(V_RSUM, r);
-        float prop_pe = pe;
-        float w_main = 0.f, sum_acc = 0.f;
-        int depth = 0, n_prop = 0;
-        bool turning = false, diverging = false;
+        prop_pe = pe;
+        w_main = 0.f; sum_acc = 0.f;
+        depth = 0; n_prop = 0;
+        turning = false; diverging = false;
+    };
+    auto begin_doubling = [&]() {
+        uint4 rd = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, (uint32_t)unit), key);
+        going_right = (rd.x >> 31) != 0;
+        u_main = u01(rd.y);
+        if (going_right) { io.ld(V_ZR, z); io.ld(V_RR, r); io.ld(V_GR, g); }
+        else { io.ld(V_ZL, z); io.ld(V_RL, r); io.ld(V_GL, g); }
+        eps_dir = going_right ? step : -step;
+        n_max = 1 << depth;
+        n_sub = 0;
+        s_turn = false; s_div = false;
+        w_sub = -INFINITY; s_acc = 0.f; sprop_pe = 0.0;
+    };
 
-        while (depth < cfg.max_depth && !turning && !diverging) {
-            uint4 rd = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, (uint32_t)unit), key);
-            const bool going_right = (rd.x >> 31) != 0;
-            const float u_main = u01(rd.y);
-            if (going_right) { io.ld(V_ZR, z); io.ld(V_RR, r); io.ld(V_GR, g); }
-            else { io.ld(V_ZL, z); io.ld(V_RL, r); io.ld(V_GL, g); }
-            const float eps_dir = going_right ? step : -step;
-            const int n_max = 1 << depth;
-            int n_sub = 0;
-            bool s_turn = false, s_div = false;
-            float w_sub = -INFINITY, s_acc = 0.f, sprop_pe = 0.f;
-            while (n_sub < n_max && !s_turn && !s_div) {
-                // leapfrog (velocity Verlet)
+    // Flat state machine: every pass through this loop does exactly one log p + gradient
+    // evaluation (the very first one initialises the chain, all others are leapfrog steps).
+    bool first = true;
+    int init_tries = 0;
+    while (true) {
+        if (!first) {
 #pragma unroll
-                for (int s = 0; s < VPL; ++s) {
-                    r[s] = fmaf(-0.5f * eps_dir, g[s], r[s]);
-                    z[s] = fmaf(eps_dir * im[s], r[s], z[s]);
-                }
-                float lp;
-                eval_logp_grad<LP, TP, VPL, RVFREE>(M, c, M.hs, z, lp, g, lane);
-                const float pe_new = -lp;
+            for (int s = 0; s < VPL; ++s) {
+                r[s] = fmaf(-0.5f * eps_dir, g[s], r[s]);
+                z[s] = fmaf(eps_dir * im[s], r[s], z[s]);
+            }
+        }
+        double lp;
+        eval_logp_grad<LP, TP, VPL, RVFREE>(M, c, M.hs, z, lp, g, lane);
+        const double pe_new = -lp;
 #pragma unroll
-                for (int s = 0; s < VPL; ++s) {
-                    g[s] = -g[s];
-                    r[s] = fmaf(-0.5f * eps_dir, g[s], r[s]);
-                }
-                const float E_new = pe_new + 0.5f * vdot_im<VPL>(im, r, r);
-                float dE = E_new - E0;
-                if (!(dE == dE)) dE = INFINITY;
-                const float leaf_w = -dE;
-                s_div = dE > 1000.f;
-                s_acc += fminf(1.f, expf(-dE));
-                if (n_sub == 0) {
+        for (int s = 0; s < VPL; ++s) g[s] = -g[s];
+        if (first) {
+            // numpyro rejects initial points with a non-finite potential or gradient and retries
+            // with init_to_uniform(radius=2) (infer/util.py find_valid_initial_params); same here.
+            bool ok = isfinite(pe_new);
 #pragma unroll
-                    for (int s = 0; s < VPL; ++s) rsum[s] = r[s];
-                    w_sub = leaf_w;
+            for (int s = 0; s < VPL; ++s) ok = ok && isfinite(g[s]);
+            ok = __all_sync(FULL, ok);
+            if (!ok && init_tries < 100) {
+                uint4 ra = philox4x32(make_uint4((uint32_t)init_tries, 0x20000000u, (uint32_t)lane, (uint32_t)unit), key);
+                float uu[4] = {u01(ra.x), u01(ra.y), u01(ra.z), u01(ra.w)};
+#pragma unroll
+                for (int s = 0; s < VPL; ++s) z[s] = own[s] ? (4.f * uu[s & 3] - 2.f) : 0.f;
+                ++init_tries;
+                continue;
+            }
+            first = false;
+            pe = pe_new;
+            begin_transition();
+            begin_doubling();
+            continue;
+        }
+        // ---- finish the leapfrog, account for the new leaf --------------------------------------
+#pragma unroll
+        for (int s = 0; s < VPL; ++s) r[s] = fmaf(-0.5f * eps_dir, g[s], r[s]);
+        {
+            const double E_new = pe_new + 0.5 * (double)vdot_im<VPL>(im, r, r);
+            float dE = (float)(E_new - E0);
+            if (!(dE == dE)) dE = INFINITY;
+            const float leaf_w = -dE;
+            s_div = dE > 1000.f;
+            s_acc += fminf(1.f, expf(-dE));
+            if (n_sub == 0) {
+#pragma unroll
+                for (int s = 0; s < VPL; ++s) rsum[s] = r[s];
+                w_sub = leaf_w;
+                io.st(V_SZP, z); io.st(V_SGP, g);
+                sprop_pe = pe_new;
+            } else {
+#pragma unroll
+                for (int s = 0; s < VPL; ++s) rsum[s] += r[s];
+                uint4 rl = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, (uint32_t)unit), key);
+                const float tp = 1.f / (1.f + expf(-(leaf_w - w_sub)));   // uniform transition kernel
+                if (u01(rl.x) < tp) {
                     io.st(V_SZP, z); io.st(V_SGP, g);
                     sprop_pe = pe_new;
-                } else {
-#pragma unroll
-                    for (int s = 0; s < VPL; ++s) rsum[s] += r[s];
-                    uint4 rl = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, (uint32_t)unit), key);
-                    const float tp = 1.f / (1.f + expf(-(leaf_w - w_sub)));   // uniform transition kernel
-                    if (u01(rl.x) < tp) {
-                        io.st(V_SZP, z); io.st(V_SGP, g);
-                        sprop_pe = pe_new;
-                    }
-                    w_sub = logaddexpf(w_sub, leaf_w);
                 }
-                const int leaf = n_sub;
-                ++n_sub;
-                // checkpoint indices (numpyro _leaf_idx_to_ckpt_idxs)
-                const int idx_max = __popc(leaf >> 1);
-                const int n_sub_trees = __ffs(~leaf) - 1;   // trailing ones
-                const int idx_min = idx_max - n_sub_trees + 1;
-                if ((leaf & 1) == 0) {
-                    io.st(V_CKPT + 2 * idx_max, r);
-                    io.st(V_CKPT + 2 * idx_max + 1, rsum);
-                }
-                for (int i = idx_max; i >= idx_min && !s_turn; --i) {
-                    io.ld(V_CKPT + 2 * i, tmp);          // r_ckpt
-                    io.ld(V_CKPT + 2 * i + 1, tmp2);     // r_sum_ckpt
-#pragma unroll
-                    for (int s = 0; s < VPL; ++s) tmp2[s] = rsum[s] - tmp2[s] + tmp[s];
-                    s_turn = is_turning<VPL>(im, tmp, r, tmp2);
-                }
+                w_sub = logaddexpf(w_sub, leaf_w);
             }
-            total_steps += n_sub;
-            // ---- merge the new subtree into the trajectory (biased progressive sampling) ------
-            if (going_right) { io.st(V_ZR, z); io.st(V_RR, r); io.st(V_GR, g); }
-            else { io.st(V_ZL, z); io.st(V_RL, r); io.st(V_GL, g); }
-            io.ld(V_RSUM, tmp);
+            const int leaf = n_sub;
+            ++n_sub;
+            // checkpoint indices (numpyro _leaf_idx_to_ckpt_idxs)
+            const int idx_max = __popc(leaf >> 1);
+            const int n_sub_trees = __ffs(~leaf) - 1;   // trailing ones
+            const int idx_min = idx_max - n_sub_trees + 1;
+            if ((leaf & 1) == 0) {
+                io.st(V_CKPT + 2 * idx_max, r);
+                io.st(V_CKPT + 2 * idx_max + 1, rsum);
+            }
+            for (int i = idx_max; i >= idx_min && !s_turn; --i) {
+                io.ld(V_CKPT + 2 * i, tmp);          // r_ckpt
+                io.ld(V_CKPT + 2 * i + 1, tmp2);     // r_sum_ckpt
 #pragma unroll
-            for (int s = 0; s < VPL; ++s) tmp[s] += rsum[s];
-            io.st(V_RSUM, tmp);
-            float tp = (s_turn || s_div) ? 0.f : fminf(1.f, expf(w_sub - w_main));
+                for (int s = 0; s < VPL; ++s) tmp2[s] = rsum[s] - tmp2[s] + tmp[s];
+                s_turn = is_turning<VPL>(im, tmp, r, tmp2);
+            }
+        }
+        if (n_sub < n_max && !s_turn && !s_div) continue;
+
+        // ---- subtree finished: merge into the trajectory (biased progressive sampling) ----------
+        total_steps += n_sub;
+        if (going_right) { io.st(V_ZR, z); io.st(V_RR, r); io.st(V_GR, g); }
+        else { io.st(V_ZL, z); io.st(V_RL, r); io.st(V_GL, g); }
+        io.ld(V_RSUM, tmp);
+#pragma unroll
+        for (int s = 0; s < VPL; ++s) tmp[s] += rsum[s];
+        io.st(V_RSUM, tmp);
+        {
+            const float tp = (s_turn || s_div) ? 0.f : fminf(1.f, expf(w_sub - w_main));
             if (u_main < tp) {
                 io.ld(V_SZP, tmp2); io.st(V_ZP, tmp2);
                 io.ld(V_SGP, tmp2); io.st(V_GP, tmp2);
                 prop_pe = sprop_pe;
             }
-            if (s_turn) turning = true;
-            else {
-                float rl_[VPL], rr_[VPL];
-                io.ld(V_RL, rl_); io.ld(V_RR, rr_);
-                turning = is_turning<VPL>(im, rl_, rr_, tmp);
-            }
-            w_main = logaddexpf(w_main, w_sub);
-            diverging = s_div;
-            sum_acc += s_acc;
-            n_prop += n_sub;
-            ++depth;
         }
+        if (s_turn) turning = true;
+        else {
+            io.ld(V_RL, tmp2);
+            float rr_[VPL];
+            io.ld(V_RR, rr_);
+            turning = is_turning<VPL>(im, tmp2, rr_, tmp);
+        }
+        w_main = logaddexpf(w_main, w_sub);
+        diverging = s_div;
+        sum_acc += s_acc;
+        n_prop += n_sub;
+        ++depth;
+        if (depth < cfg.max_depth && !turning && !diverging) {
+            begin_doubling();
+            continue;
+        }
+
+        // ---- transition finished ---------------------------------------------------------------
         const float accept = sum_acc / (float)max(n_prop, 1);
         io.ld(V_ZP, z); io.ld(V_GP, g);
         pe = prop_pe;
-
+        if (lane == 0) {
+            float* srow = stats + (unit * (size_t)n_iter + it) * 5;
+            srow[0] = accept;
+            srow[1] = (float)n_prop;
+            srow[2] = diverging ? 1.f : 0.f;
+            srow[3] = (float)pe;
+            srow[4] = step;     // step size this transition was run with
+        }
         if (it < cfg.num_warmup) {
-            // ---- warm-up adaptation (numpyro warmup_adapter.update_fn) --------------------------
+            // warm-up adaptation (numpyro warmup_adapter.update_fn)
             if (cfg.adapt_step) {
                 ++da_t;
                 const float gg = cfg.target_accept - accept;
@@ -394,16 +446,13 @@ __global__ void __launch_bounds__(WPB * 32) nuts_kernel(ModelDev M, DataDev Dd, 
             const size_t row = unit * cfg.num_samples + k;
 #pragma unroll
             for (int s = 0; s < VPL; ++s)
-                if (own[s]) samples[row * D + lane + 32 * s] = z[s];
-            if (lane == 0) {
-                stats[row * 4 + 0] = accept;
-                stats[row * 4 + 1] = (float)n_prop;
-                stats[row * 4 + 2] = diverging ? 1.f : 0.f;
-                stats[row * 4 + 3] = pe;
-            }
+                if (own[s]) samples[row * D + lane + 32 * s] = z[s] + ((lane + 32 * s == M.n_eps + 3) ? c.muhat : 0.f);
             mean_acc += (accept - mean_acc) / (float)(k + 1);
             n_div += diverging ? 1 : 0;
         }
+        if (++it >= n_iter) break;
+        begin_transition();
+        begin_doubling();
     }
     float* ci = chain_info + unit * (4 + D);
     if (lane == 0) {
@@ -415,6 +464,84 @@ __global__ void __launch_bounds__(WPB * 32) nuts_kernel(ModelDev M, DataDev Dd, 
 #pragma unroll
     for (int s = 0; s < VPL; ++s)
         if (own[s]) ci[4 + lane + 32 * s] = im[s];
+}
+
+
+// ------------------------------------------------------------------------------------------
+// (4) numpyro init_to_median(num_samples=15): per chain and site, the median of 15 prior draws,
+//     mapped to the unconstrained space (reference call sites :1757, :2110).
+// ------------------------------------------------------------------------------------------
+struct InitArgs {
+    int N, C, D, n_eps, rv_mode;
+    float tauA, sdD;
+    const float* muhat;
+    unsigned seed_lo, seed_hi;
+    float* q;
+};
+
+__device__ __forceinline__ float median15(float (&v)[15]) {
+    // selection of the 8th smallest by partial insertion sort
+#pragma unroll
+    for (int i = 1; i < 15; ++i) {
+        float x = v[i];
+        int j = i - 1;
+        while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; }
+        v[j + 1] = x;
+    }
+    return v[7];
+}
+
+__global__ void init_median_kernel(InitArgs A) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)A.N * A.C * A.D;
+    if (idx >= total) return;
+    const int i = (int)(idx % A.D);
+    const long long unit = idx / A.D;
+    const int sn = (int)(unit / A.C);
+    const uint2 key = make_uint2(A.seed_lo ^ 0x5bd1e995u, A.seed_hi + 0x1234567u);
+    float v[15];
+    const int kind = (i < A.n_eps) ? 0 : (i - A.n_eps + 1);   // 0 eps, 1 theta, 2 AV, 3 tmax, 4 Ds, 5 RV
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        uint4 ra = philox4x32(make_uint4((uint32_t)b, (uint32_t)i, 0x80000000u, (uint32_t)unit), key);
+        float u[4] = {u01(ra.x), u01(ra.y), u01(ra.z), u01(ra.w)};
+        float n0 = sqrtf(-2.f * logf(u[0] + 5.9604644775390625e-8f));
+        float n1 = sqrtf(-2.f * logf(u[2] + 5.9604644775390625e-8f));
+        float sn0, cs0, sn1, cs1;
+        sincospif(2.f * u[1], &sn0, &cs0);
+        sincospif(2.f * u[3], &sn1, &cs1);
+        float nr[4] = {n0 * cs0, n0 * sn0, n1 * cs1, n1 * sn1};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int j = 4 * b + k;
+            if (j < 15) v[j] = (kind == 2 || kind == 3 || kind == 5) ? u[k] : nr[k];
+        }
+    }
+    float med = median15(v);
+    float out;
+    if (kind == 0 || kind == 1) out = med;
+    else if (kind == 2) out = logf(-A.tauA * logf(fmaxf(1.f - med, 1e-7f)));       // Exponential draw, then log
+    else if (kind == 4) out = A.muhat[sn] + A.sdD * med;
+    else { float u = fminf(fmaxf(med, 1e-6f), 1.f - 1e-6f); out = logf(u) - log1pf(-u); }   // uniform -> logit
+    A.q[idx] = out;
+}
+
+// ------------------------------------------------------------------------------------------
+// (5) FP32 FMA peak microbenchmark: the roofline denominator for the SIMT kernels above
+//     (MEASURED_PEAKS.json has no FP32 figure).  8 independent FFMA chains per thread.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f,
+          x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 }  // namespace bayesn

@@ -303,11 +303,12 @@ class SEDmodel(object):
                 samples[k] = v.transpose(1, 2, 3, 0) if k == 'eps' else v.transpose(1, 2, 0, 3)
             else:
                 samples[k] = v.transpose(1, 2, 0)
-        stats = out['stats'].cpu().numpy()
+        stats = out['stats'][:, :, num_warmup:].cpu().numpy()
         samples['diverging'] = stats[..., 2].transpose(1, 2, 0) > 0
         extras = {'accept_prob': stats[..., 0].transpose(1, 2, 0), 'num_steps': stats[..., 1].transpose(1, 2, 0),
                   'potential_energy': stats[..., 3].transpose(1, 2, 0),
-                  'chain_info': out['chain_info'].cpu().numpy(), 'launches': ctx.launches()}
+                  'chain_info': out['chain_info'].cpu().numpy(), 'launches': ctx.launches(),
+                  'all_stats': out['stats'].cpu().numpy()}
         return samples, extras
 
     def fit(self, t, flux, flux_err, filters, z, ebv_mw=0, peak_mjd=None, filt_map={}, print_summary=True,

@@ -42,7 +42,8 @@ class NutsCfg(C.Structure):
 
 EXPORTS = ['bayesn_abi_version', 'bayesn_ctx_create', 'bayesn_ctx_destroy', 'bayesn_last_error',
            'bayesn_set_model', 'bayesn_bind_dataset', 'bayesn_param_dim', 'bayesn_logp_grad_fit',
-           'bayesn_flux_batch', 'bayesn_nuts_workspace_bytes', 'bayesn_nuts_fit', 'bayesn_launch_count']
+           'bayesn_flux_batch', 'bayesn_nuts_workspace_bytes', 'bayesn_nuts_fit', 'bayesn_launch_count',
+           'bayesn_init_to_median', 'bayesn_ffma_peak']
 
 _lib = None
 
@@ -72,6 +73,8 @@ def load_library():
     lib.bayesn_nuts_workspace_bytes.restype = C.c_size_t
     lib.bayesn_nuts_fit.argtypes = [C.c_void_p, C.POINTER(NutsCfg)] + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]
     lib.bayesn_launch_count.argtypes = [C.c_void_p]
+    lib.bayesn_init_to_median.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.bayesn_ffma_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.bayesn_launch_count.restype = C.c_longlong
     _lib = lib
     return lib
@@ -156,6 +159,20 @@ class Context:
         import torch
         return torch.cuda.current_stream().cuda_stream
 
+    def init_to_median(self, n_chains, seed=0, out=None):
+        """Initial unconstrained positions (N, C, D) for the bound data set (device kernel)."""
+        import torch
+        if out is None:
+            out = torch.empty((self.N, n_chains, self.D), dtype=torch.float32, device=f'cuda:{self.device}')
+        self._check(self.lib.bayesn_init_to_median(self.h, int(n_chains), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                   out.data_ptr(), self._stream()), 'bayesn_init_to_median')
+        return out
+
+    def ffma_peak_tflops(self):
+        v = C.c_double()
+        self._check(self.lib.bayesn_ffma_peak(self.h, C.byref(v)), 'bayesn_ffma_peak')
+        return float(v.value)
+
     def logp_grad(self, q):
         """q: (N, C, D) float32 CUDA tensor -> (logp (N, C), grad (N, C, D))."""
         import torch
@@ -186,7 +203,7 @@ class Context:
         ws = out.get('work')
         if ws is None or ws.numel() * 4 < wb:
             ws = out['work'] = torch.empty((wb + 3) // 4, dtype=torch.float32, device=dev)
-        for name, shape in (('samples', (N, Cn, num_samples, D)), ('stats', (N, Cn, num_samples, 4)),
+        for name, shape in (('samples', (N, Cn, num_samples, D)), ('stats', (N, Cn, num_warmup + num_samples, 5)),
                             ('chain_info', (N, Cn, 4 + D))):
             t = out.get(name)
             if t is None or tuple(t.shape) != shape:

@@ -127,13 +127,22 @@ int bayesn_flux_batch(bayesn_ctx* ctx, int N, int N_obs, int n_b, int mag, float
  * numpyro MCMC(NUTS(fit_model_*)) runs at bayesn/bayesn_model.py:1830-1837 and :2128-2141.
  *   q_init  [N][C][D]           device, in   initial unconstrained positions
  *   samples [N][C][S][D]        device, out  unconstrained draws after warm-up
- *   stats   [N][C][S][4]        device, out  {accept_prob, n_leapfrog, diverging, potential_energy}
+ *   stats   [N][C][W+S][5]      device, out  per transition incl. warm-up: {accept_prob, n_leapfrog,
+ *                                              diverging, potential_energy, step_size}
  *   chain_info [N][C][4+D]      device, out  {final step size, mean accept (sampling), total
  *                                              leapfrogs, divergences, inverse mass diag[D]}
  *   work, work_bytes            device scratch of at least bayesn_nuts_workspace_bytes() */
 size_t bayesn_nuts_workspace_bytes(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg);
 int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_init, float* samples, float* stats,
                     float* chain_info, void* work, size_t work_bytes, void* stream);
+
+/* numpyro init_to_median(num_samples=15) (reference bayesn/bayesn_model.py:1757, :2110): initial
+ * unconstrained positions q [N][n_chains][D] (device, out) for the bound data set. */
+int bayesn_init_to_median(bayesn_ctx* ctx, int n_chains, uint64_t seed, float* q, void* stream);
+
+/* FP32 FMA peak of this device in TFLOP/s, measured with an FFMA-only kernel: the roofline
+ * denominator for the SIMT kernels (no reference counterpart; measurement aid). */
+int bayesn_ffma_peak(bayesn_ctx* ctx, double* tflops_out);
 
 /* Number of kernel launches this ctx has issued (for bench accounting). */
 long long bayesn_launch_count(bayesn_ctx* ctx);
