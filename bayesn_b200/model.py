@@ -208,7 +208,7 @@ class SEDmodel(object):
         ctx = self._ctxs.get(key)
         if ctx is None:
             ctx = self._ctxs[key] = self._context(native.RV_FIXED)
-        to = lambda a, dt=torch.float32: torch.as_tensor(np.asarray(a), device=dev).to(dt)
+        to = lambda a, dt=torch.float32: torch.as_tensor(np.array(a), device=dev).to(dt)
         theta = to(theta)
         N = theta.shape[0]
         RV = np.broadcast_to(np.asarray(RV, dtype=np.float64), (N,))

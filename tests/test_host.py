@@ -1,0 +1,125 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every declared symbol, the
+product path fails loudly without a GPU, dataset packing, multi-rank sharding over gloo."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_in_header(built_library):
+    hdr = open(os.path.join(ROOT, 'include', 'bayesn_b200.h')).read()
+    declared = set(re.findall(r'\b(bayesn_[a-z_0-9]+)\s*\(', hdr))
+    declared -= {'bayesn_ctx'}
+    assert {'bayesn_logp_grad_fit', 'bayesn_nuts_fit', 'bayesn_flux_batch', 'bayesn_set_model'} <= declared
+    for name in declared:
+        assert hasattr(built_library, name), name
+    assert built_library.bayesn_abi_version() == 1
+    from bayesn_b200 import native
+    assert set(native.EXPORTS) == declared
+
+
+def test_library_is_sm100a_with_tma_and_no_tensor_fallback(built_library):
+    from bayesn_b200 import native
+    out = subprocess.run(['cuobjdump', '-lelf', native.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_product_path_fails_loudly_without_gpu():
+    from bayesn_b200 import native
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        native.Context(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'bayesn_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert 'oracle' not in re.sub(r'#.*', '', src).replace('"""', ''), fn
+
+
+def test_pack_dataset_layout():
+    from bayesn_b200 import packing
+    rng = np.random.RandomState(0)
+    N, N_obs, n_b = 3, 5, 4
+    obs = np.zeros((10, N_obs, N))
+    obs[0] = rng.uniform(-8, 30, (N_obs, N))
+    obs[1] = rng.uniform(1e3, 1e4, (N_obs, N))
+    obs[2] = rng.uniform(10, 100, (N_obs, N))
+    obs[4] = rng.randint(1, n_b, (N_obs, N))
+    obs[7] = np.array([34.0, 35.0, 36.0])[None]
+    obs[9] = 1
+    obs[9, 1, 0] = 0
+    obs[9, :, 2] = 0                    # an SN with no valid observation at all
+    w = np.zeros((N, 300, n_b))
+    w[:, 40:90, 1] = 0.01
+    w[:, 100:101, 2] = 0.5
+    w[:, :, 0] = 1 / 300
+    zps = np.array([10.0, -20.8, -21.4, -21.8])
+    off = np.zeros(n_b)
+    p = packing.pack_dataset(obs, w, zps, off, -19.5, 5.0, 0.2, 24, device='cpu')
+    assert p['n_valid'].tolist() == [4, 5, 0]
+    o4 = p['obs4'].numpy()
+    assert np.all(o4[2] == 0)
+    # masked observation moved behind the valid ones
+    assert np.allclose(np.sort(o4[0, :4, 0]), np.sort(np.delete(obs[0, :, 0], 1)), rtol=1e-6)
+    band = o4[..., 3].view(np.int32)
+    assert np.all(band[0, :4] == np.delete(obs[4, :, 0], 1).astype(int))
+    sup = p['support'].numpy()
+    assert sup[0, 1].tolist() == [40, 90] and sup[0, 2].tolist() == [100, 101] and sup[0, 3].tolist() == [0, 0]
+    assert p['weights'].shape == (N, n_b, 304) and float(p['weights'][0, 1, 300:].abs().sum()) == 0
+    sc = 10 ** (0.4 * 27.5 + 20.8 / 2.5 - 0.4 * (-19.5 + 34.0))
+    assert np.isclose(float(p['weights'][0, 1, 50]), 0.01 * sc, rtol=1e-6)
+    with pytest.raises(ValueError):
+        obs[4, 0, 1] = 7
+        packing.pack_dataset(obs, w, zps, off, -19.5, 5.0, 0.2, 24, device='cpu')
+
+
+def test_shard_bounds_cover_everything():
+    from bayesn_b200.distributed import shard_bounds
+    for n in [0, 1, 7, 1000, 100000]:
+        for world in [1, 2, 3, 8]:
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from bayesn_b200.distributed import shard_obs, gather_rows, shard_bounds
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%s' % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+N = 7
+obs = np.arange(10 * 3 * N, dtype=np.float64).reshape(10, 3, N)
+w = np.arange(N * 300 * 2, dtype=np.float64).reshape(N, 300, 2)
+o, ww, (lo, hi) = shard_obs(obs, w, rank, 2)
+assert o.shape[-1] == hi - lo == ww.shape[0]
+# stand-in for the per-SN fit: a deterministic function of each SN's own data only
+local = np.stack([o[1].sum(axis=0), ww.sum(axis=(1, 2))], axis=1)
+full = gather_rows(local, N)
+want = np.stack([obs[1].sum(axis=0), w.sum(axis=(1, 2))], axis=1)
+assert full.shape == (N, 2) and np.array_equal(full, want), (rank, full, want)
+dist.barrier(); dist.destroy_process_group()
+print('ok', rank)
+'''
+
+
+def test_two_rank_sharding_over_gloo(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and 'ok' in o, o
