@@ -191,11 +191,12 @@ int bayesn_set_model(bayesn_ctx* ctx, const bayesn_model_desc* m) {
     free_owned(ctx);
     ctx->have_model = false;
     const int LP = ctx->LP, TP = ctx->TP;
-    std::vector<float> Jl((size_t)LP * BP, 0.f), hs((size_t)NPH * BP, 0.f), Mf((size_t)9 * BP, 0.f), ad(BP, 0.f);
+    const int RS = jl_row_stride(LP);
+    std::vector<float> Jl((size_t)JROWS * RS, 0.f), hs((size_t)NPH * BP + 64, 0.f), Mf((size_t)9 * BP, 0.f), ad(JROWS, 0.f);
     std::vector<float> W0((size_t)LP * TP, 0.f), W1((size_t)LP * TP, 0.f), KD((size_t)TP * TP, 0.f), tau(TP, 0.f);
     std::vector<float> Ls((size_t)ne * ne), LsT((size_t)ne * ne);
     for (int b = 0; b < NB; ++b) {
-        for (int l = 0; l < L; ++l) Jl[(size_t)l * BP + b] = m->J_l[(size_t)b * L + l];
+        for (int l = 0; l < L; ++l) Jl[(size_t)b * RS + l] = m->J_l[(size_t)b * L + l];
         for (int i = 0; i < NPH; ++i) hs[(size_t)i * BP + b] = m->hsiao[(size_t)b * NPH + i];
         for (int j = 0; j < 9; ++j) Mf[(size_t)j * BP + b] = m->M_fitz[(size_t)b * 9 + j];
         if (m->a_dust) ad[b] = m->a_dust[b];
@@ -351,7 +352,7 @@ int bayesn_flux_batch(bayesn_ctx* ctx, int N, int N_obs, int n_b, int mag, float
     A.N = N; A.N_obs = N_obs; A.n_b = n_b; A.L = ctx->M.L; A.T = ctx->M.T; A.mag = mag; A.M0 = M0;
     A.theta = theta; A.AV = AV; A.W0 = W0; A.W1 = W1; A.eps = eps; A.Ds = Ds; A.RV = RV;
     A.band = band_indices; A.mask = mask; A.J_t = J_t; A.hsi = hsiao_interp; A.weights = weights;
-    A.bscale = dbs; A.Jl = ctx->M.Jl; A.hs = ctx->M.hs; A.Mf = ctx->M.Mf; A.LPs = ctx->LP; A.out = out;
+    A.bscale = dbs; A.Jl = ctx->M.Jl; A.hs = ctx->M.hs; A.Mf = ctx->M.Mf; A.LPs = jl_row_stride(ctx->LP); A.out = out;
     const long long items = (long long)N * N_obs;
     flux_kernel<<<(unsigned)((items + 3) / 4), 128, 0, st>>>(A);
     ctx->launches++;

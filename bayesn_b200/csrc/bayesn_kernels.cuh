@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(WPB * 32) logp_grad_kernel(ModelDev M, DataDev
         if (i == M.n_eps + 3) q[s] -= c.muhat;     // the evaluator works with Ds - muhat
     }
     double lp;
-    eval_logp_grad<LP, TP, VPL, RVFREE>(M, c, M.hs, q, lp, g, lane);
+    eval_logp_grad<LP, TP, VPL, RVFREE, STAGE>(M, c, M.hs, q, lp, g, lane);
     if (lane == 0) logp_out[unit] = (float)lp;
 #pragma unroll
     for (int s = 0; s < VPL; ++s) {
@@ -48,8 +48,8 @@ struct FluxArgs {
     const uint8_t* mask;
     const float *J_t, *hsi, *weights;
     const double* bscale;   // [n_b] log2 of the band scale (double: the exponent is ~+60)
-    const float *Jl, *hs, *Mf;   // model tables: [LP][BP], [NPH][BP], [9][BP]
-    int LPs;                // row count of Jl
+    const float *Jl, *hs, *Mf;   // model tables: [JROWS][RS], [NPH][BP], [9][BP]
+    int LPs;                // row stride RS of Jl
     float* out;
 };
 
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128) flux_kernel(FluxArgs A) {
     float F = 0.f;
     for (int b = lane; b < NB; b += 32) {
         float g = 0.f;
-        for (int l = 0; l < L; ++l) g = fmaf(A.Jl[l * BP + b], su[warp][l], g);
+        for (int l = 0; l < L; ++l) g = fmaf(A.Jl[b * A.LPs + l], su[warp][l], g);
         float my = 0.f;
 #pragma unroll
         for (int j = 0; j < 9; ++j) my = fmaf(A.Mf[j * BP + b], syk[warp][j], my);
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(WPB * 32, 4) nuts_kernel(ModelDev M, DataDev D
             }
         }
         double lp;
-        eval_logp_grad<LP, TP, VPL, RVFREE>(M, c, M.hs, z, lp, g, lane);
+        eval_logp_grad<LP, TP, VPL, RVFREE, STAGE>(M, c, M.hs, z, lp, g, lane);
         const double pe_new = -lp;
 #pragma unroll
         for (int s = 0; s < VPL; ++s) g[s] = -g[s];

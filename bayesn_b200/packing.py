@@ -48,7 +48,10 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
     lconst += -half_l2pi * (1 + n_eps) - math.log(tauA) - math.log(Ds_prior_sd) - half_l2pi
     bscale = band_log10_scale(zps, offsets)
     assert bscale.shape[0] == n_b
-    wt = torch.zeros((N, n_b, BPAD), dtype=torch.float32, device=device)
+    # one spare row after the last tile: the kernels' last 32-bin round may read (and discard) up
+    # to 31 floats past a row's end
+    wt_store = torch.zeros((N * n_b + 1, BPAD), dtype=torch.float32, device=device)
+    wt = wt_store[:N * n_b].view(N, n_b, BPAD)
     sup = torch.zeros((N, n_b, 2), dtype=torch.int32, device=device)
     for s0 in range(0, N, chunk):
         w = np.asarray(weights[s0:s0 + chunk], dtype=np.float64)                  # (n, 300, n_b)
@@ -63,4 +66,4 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
     return dict(N=N, N_obs=N_obs, n_b=n_b, obs4=to(obs4), n_valid=to(n_valid), weights=wt, support=sup,
                 muhat=to(muhat.astype(np.float32)), lconst=to(lconst.astype(np.float32)),
-                muhat64=muhat, order=order)
+                muhat64=muhat, order=order, _weights_storage=wt_store)

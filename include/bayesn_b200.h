@@ -68,7 +68,8 @@ typedef struct {
  * (bayesn/bayesn_model.py:2096-2106, :2711-2730); bayesn_b200/model.py builds it.
  *   obs4[s][o]   = {phase t, FLUXCAL y, 1/sigma, band index as float}; valid observations first
  *   n_valid[s]   = number of unmasked observations of SN s (<= N_obs)
- *   weights[s][k][BAYESN_BPAD] = band weight * 10^(0.4(27.5-offset_k) - zp_k/2.5 - 0.4(M0+muhat_s))
+ *   weights[s][k][BAYESN_BPAD] = band weight * 10^(0.4(27.5-offset_k) - zp_k/2.5 - 0.4(M0+muhat_s));
+ *                  the allocation must extend 32 floats past the last row (read, never used)
  *   support[s][k] = {first, one-past-last} bin with a non-zero weight (exact zeros only)
  *   muhat[s]     = fiducial distance modulus;  lconst[s] = data-only log-density constant */
 typedef struct {
