@@ -192,7 +192,7 @@ int bayesn_set_model(bayesn_ctx* ctx, const bayesn_model_desc* m) {
     ctx->have_model = false;
     const int LP = ctx->LP, TP = ctx->TP;
     const int RS = jl_row_stride(LP);
-    std::vector<float> Jl((size_t)JROWS * RS, 0.f), hs((size_t)NPH * BP + 64, 0.f), Mf((size_t)9 * BP, 0.f), ad(JROWS, 0.f);
+    std::vector<float> Jl((size_t)JROWS * RS, 0.f), hs((size_t)(NPH + 1) * BP + OVERRUN + 32, 0.f), Mf((size_t)9 * BP, 0.f), ad(JROWS, 0.f);
     std::vector<float> W0((size_t)LP * TP, 0.f), W1((size_t)LP * TP, 0.f), KD((size_t)TP * TP, 0.f), tau(TP, 0.f);
     std::vector<float> Ls((size_t)ne * ne), LsT((size_t)ne * ne);
     for (int b = 0; b < NB; ++b) {

@@ -116,6 +116,39 @@ __device__ __forceinline__ float treduce16(float (&v)[16], int lane) {
     return v[0];
 }
 
+// The same within each 16-lane half of the warp (the two halves work on two different
+// observations): 15 shuffles; on return lane hl = lane & 15 holds its half's total of value hl.
+__device__ __forceinline__ float treduce16h(float (&v)[16], int lane) {
+    bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float send = up ? v[i] : v[i + 8];
+        float keep = up ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+    up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float send = up ? v[i] : v[i + 4];
+        float keep = up ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+    up = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float send = up ? v[i] : v[i + 2];
+        float keep = up ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+    up = lane & 1;
+    {
+        float send = up ? v[0] : v[1];
+        float keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(FULL, send, 1);
+    }
+    return v[0];
+}
+
 // mbarrier + 1-D TMA bulk copy (global -> shared)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -174,6 +207,7 @@ struct Dims {
     static constexpr int RS = ((LP4 / 4) % 2 == 1) ? LP4 : LP4 + 4;
 };
 constexpr int JROWS = BP + 32;   // per-bin tables carry 32 zero rows so the last round may overrun
+constexpr int OVERRUN = 320;     // bins a lane may read past the end of its band's support (values discarded)
 __host__ __device__ constexpr int jl_row_stride(int LP) { return ((((LP + 3) & ~3) / 4) % 2 == 1) ? ((LP + 3) & ~3) : ((LP + 3) & ~3) + 4; }
 
 struct SmemPlan {
@@ -210,12 +244,17 @@ __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b
     p.wWs = wtake(LP * TP);
     p.wEv = wtake(n_eps);
     p.wEps = wtake(n_eps);
-    p.wRec = wtake(N_obs * rec);
+    p.wRec = wtake(((N_obs + 1) & ~1) * rec);    // observations are processed in pairs
     p.wSc = wtake(8);
     p.wAd = wtake(rvfree ? JROWS : 0);
     p.wDad = wtake(rvfree ? JROWS : 0);
     p.warpStride = w;
-    p.totalFloats = o + WPB * w;
+    // Lanes that have run past their band's support keep reading (and discard) up to OVERRUN bins
+    // beyond it while the other half-warp finishes a wider band: keep those reads inside the CTA's
+    // allocation.
+    p.totalFloats = o + WPB * w + OVERRUN;
+    const int jl_reach = p.oJl + (NB + OVERRUN) * jl_row_stride(LP);
+    if (p.totalFloats < jl_reach) p.totalFloats = jl_reach;
     return p;
 }
 
@@ -404,9 +443,13 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     __syncwarp();
 
     // ---- per-observation setup, lanes over observations -------------------------------------
+    // Observations are processed in pairs (one per half-warp); an odd count is completed by a
+    // dummy copy of the last observation with 1/sigma = 0, which contributes exactly nothing.
+    const int npair = (c.nobs + 1) >> 1;
     if (lane == 0) c.sc[0] = S;
-    for (int o = lane; o < c.nobs; o += 32) {
-        const float4 ob = c.obs[o];
+    for (int o = lane; o < 2 * npair; o += 32) {
+        const bool dummy = o >= c.nobs;
+        const float4 ob = c.obs[dummy ? c.nobs - 1 : o];
         float t = ob.x - tmax;
         float J[TP], dJ[TP];
         spline_row<TP>(t, T, c.sTau, c.sKD, J, dJ);
@@ -425,36 +468,39 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
                 }
             }
             rc[l] = -C2 * u;
-            rc[DM::R_DU + l] = -C2 * du;
+            rc[DM::R_DU + l] = du;              // (W J_t')[l], used once at the end for d/dtmax
         }
         float fl = floorf(t);
         int i0 = 19 + (int)fl, i1 = 19 + (int)ceilf(t);
         i0 = min(max(i0, 0), NPH - 1);
         i1 = min(max(i1, 0), NPH - 1);
-        rc[DM::R_F] = t - fl;
-        rc[DM::R_IDX] = __int_as_float(i0 | (i1 << 8));
-        rc[DM::R_Y] = ob.y;
-        rc[DM::R_IS] = ob.z;
+        // the upper Hsiao row is read at i0 + 1; when ceil == floor (integer phase) or the index
+        // is clamped the interpolation degenerates to row i0 and d/dt of it vanishes
+        const bool interp = i1 != i0;
+        rc[DM::R_F] = interp ? (t - fl) : 0.f;
+        rc[DM::R_IDX] = __int_as_float(i0 | (interp ? 256 : 0));
+        rc[DM::R_Y] = dummy ? 0.f : ob.y;
+        rc[DM::R_IS] = dummy ? 0.f : ob.z;
         rc[DM::R_BAND] = ob.w;
     }
     __syncwarp();
 
-    // ---- band-pass integrals, lanes over wavelength bins --------------------------------------
+    // ---- band-pass integrals: half-warp per observation, 16 lanes over wavelength bins ---------
     // log L is accumulated in double: far from the mode |log L| reaches 1e6 while NUTS needs energy
     // differences to ~1e-2, which float32 partial sums cannot hold (ulp(7.5e5) = 0.06)
     double logL = 0.0;
     float gDs = 0.f, gAV = 0.f, gT = 0.f, gRV = 0.f;
     const float* wtile = STAGE ? c.wt_s : c.wt_g;
-    for (int o = 0; o < c.nobs; ++o) {
-        float* rc = c.rec + o * REC;
-        float u[LP4], du[LP4];
+    const int hl = lane & 15, hb = lane & 16;
+    for (int p = 0; p < npair; ++p) {
+        float* rc = c.rec + (2 * p + (lane >> 4)) * REC;
+        float u[LP4];
         {
             const float4* up = reinterpret_cast<const float4*>(rc);
 #pragma unroll
             for (int j = 0; j < LP4 / 4; ++j) {
-                float4 a = up[j], b = up[LP4 / 4 + j];
+                float4 a = up[j];
                 u[4 * j] = a.x; u[4 * j + 1] = a.y; u[4 * j + 2] = a.z; u[4 * j + 3] = a.w;
-                du[4 * j] = b.x; du[4 * j + 1] = b.y; du[4 * j + 2] = b.z; du[4 * j + 3] = b.w;
             }
         }
         const float f = rc[DM::R_F];
@@ -462,10 +508,11 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         const float yo = rc[DM::R_Y], iso = rc[DM::R_IS];
         const int k = __float_as_int(rc[DM::R_BAND]);
         const int2 sp = c.sup[k];
+        int nr = (sp.y - sp.x + 15) >> 4;
+        nr = max(nr, __shfl_xor_sync(FULL, nr, 16));
         // running pointers: one add per array per round instead of rebuilding addresses
-        const int b_first = sp.x + lane;
+        const int b_first = sp.x + hl;
         const float* p0 = hs + (pk & 0xff) * BP + b_first;
-        const float* p1 = hs + (pk >> 8) * BP + b_first;
         const float* pw = wtile + k * BP + b_first;
         const float4* pj = reinterpret_cast<const float4*>(c.sJl) + b_first * (RS / 4);
         const float* pa = adv + b_first;
@@ -474,7 +521,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         float acc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-        for (int b0 = sp.x; b0 < sp.y; b0 += 32) {
+        for (int it = 0; it < nr; ++it) {
             float jl[LP4];
 #pragma unroll
             for (int j = 0; j < LP4 / 4; ++j) {
@@ -482,38 +529,32 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
                 jl[4 * j] = v.x; jl[4 * j + 1] = v.y; jl[4 * j + 2] = v.z; jl[4 * j + 3] = v.w;
             }
             const float wl = STAGE ? *pw : __ldg(pw);
-            const float h0 = __ldg(p0), h1 = __ldg(p1);
+            const float h0 = __ldg(p0), h1 = __ldg(p0 + BP);
             const float a = *pa;
-            const float w = (rem > 0) ? wl : 0.f;
-            // two independent FFMA chains per dot product (4-cycle dependent-issue latency)
-            float g0 = 0.f, g1 = 0.f, d0 = 0.f, d1 = 0.f;
+            // two independent FFMA chains (4-cycle dependent-issue latency)
+            float g0 = 0.f, g1 = 0.f;
 #pragma unroll
             for (int l = 0; l < LP; l += 2) {
                 g0 = fmaf(jl[l], u[l], g0);
-                d0 = fmaf(jl[l], du[l], d0);
-                if (l + 1 < LP) {
-                    g1 = fmaf(jl[l + 1], u[l + 1], g1);
-                    d1 = fmaf(jl[l + 1], du[l + 1], d1);
-                }
+                if (l + 1 < LP) g1 = fmaf(jl[l + 1], u[l + 1], g1);
             }
-            const float g = g0 + g1, gd = d0 + d1;
             const float dh = h1 - h0;
             const float H = fmaf(f, dh, h0);
-            const float e = ex2_approx(fmaf(AVc, a, g));
-            const float we = w * e;
+            const float e = ex2_approx(fmaf(AVc, a, g0 + g1));
+            const float we = (rem > 0) ? wl * e : 0.f;     // select, not multiply: e may be garbage past the support
             const float P = we * H;
             acc[0] += P;
             acc[1] = fmaf(P, a, acc[1]);
-            acc[2] += fmaf(P, gd * LN2, we * dh);
-            if (RVFREE) { acc[3] = fmaf(P, *pda, acc[3]); pda += 32; }
+            acc[2] = fmaf(we, dh, acc[2]);
+            if (RVFREE) { acc[3] = fmaf(P, *pda, acc[3]); pda += 16; }
 #pragma unroll
             for (int l = 0; l < LP; ++l) acc[4 + l] = fmaf(jl[l], P, acc[4 + l]);
-            p0 += 32; p1 += 32; pw += 32; pj += 32 * (RS / 4); pa += 32; rem -= 32;
+            p0 += 16; pw += 16; pj += 16 * (RS / 4); pa += 16; rem -= 16;
         }
-        const float val = treduce16(acc, lane);
-        const float F = __shfl_sync(FULL, val, 0);
-        const float FA = __shfl_sync(FULL, val, 2);
-        const float FT = __shfl_sync(FULL, val, 4);
+        const float val = treduce16h(acc, lane);
+        const float F = __shfl_sync(FULL, val, hb);
+        const float FA = __shfl_sync(FULL, val, hb | 1);
+        const float FT = __shfl_sync(FULL, val, hb | 2);
         const float Sv = c.sc[0];
         const float flux = Sv * F;
         const float resid = yo - flux;
@@ -523,16 +564,33 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         const float coef = r * Sv;
         gDs = fmaf(-KAPPA * r, flux, gDs);
         gAV = fmaf(-KAPPA * coef, FA, gAV);
-        gT = fmaf(coef, FT, gT);
-        if (RVFREE) gRV = fmaf(-KAPPA * AV * coef, __shfl_sync(FULL, val, 6), gRV);
+        gT = fmaf((pk & 256) ? coef : 0.f, FT, gT);
+        if (RVFREE) gRV = fmaf(-KAPPA * AV * coef, __shfl_sync(FULL, val, hb | 3), gRV);
         // d logL / d(sum_m W[l][m] Jt[m]) for this observation, overwriting u (no longer needed)
         __syncwarp();
-        {
-            const int vi = lane >> 1;
-            if (!(lane & 1) && vi >= 4 && vi < 4 + LP) rc[vi - 4] = -KAPPA * coef * val;
-        }
+        if (hl >= 4 && hl < 4 + LP) rc[hl - 4] = -KAPPA * coef * val;
     }
+    // the two halves hold the sums over their own observations
+    logL += __shfl_xor_sync(FULL, logL, 16);
+    gDs += __shfl_xor_sync(FULL, gDs, 16);
+    gAV += __shfl_xor_sync(FULL, gAV, 16);
+    gT += __shfl_xor_sync(FULL, gT, 16);
+    if (RVFREE) gRV += __shfl_xor_sync(FULL, gRV, 16);
     __syncwarp();
+
+    // ---- d/dtmax through the time spline: sum_o sum_l dU[o][l] (W J_t'(t_o))[l], lanes over obs --
+    {
+        float gw = 0.f;
+        for (int o = lane; o < c.nobs; o += 32) {
+            const float4* a4 = reinterpret_cast<const float4*>(c.rec + o * REC);
+#pragma unroll
+            for (int j = 0; j < LP4 / 4; ++j) {
+                const float4 a = a4[j], b = a4[LP4 / 4 + j];
+                gw = fmaf(a.x, b.x, gw); gw = fmaf(a.y, b.y, gw); gw = fmaf(a.z, b.z, gw); gw = fmaf(a.w, b.w, gw);
+            }
+        }
+        gT += wsum(gw);
+    }
 
     // ---- reverse: dW, theta, eps_tform -------------------------------------------------------
     float dW[NPAIR];

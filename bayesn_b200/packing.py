@@ -31,7 +31,30 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
     band = np.rint(obs[-6].T).astype(np.int32)
     mask = obs[-1].T != 0
     muhat = np.ascontiguousarray(obs[-3, 0, :])
-    order = np.argsort(~mask, axis=1, kind='stable')
+    if np.any(mask & ((band < 0) | (band >= n_b))):
+        raise ValueError('band index out of range of the weights array')
+    bscale = band_log10_scale(zps, offsets)
+    assert bscale.shape[0] == n_b
+    # spare rows after the last tile: lanes past the end of a band's support keep reading (and
+    # discard) up to OVERRUN = 320 floats while the other half-warp finishes a wider band
+    wt_store = torch.zeros((N * n_b + 3, BPAD), dtype=torch.float32, device=device)
+    wt = wt_store[:N * n_b].view(N, n_b, BPAD)
+    sup_h = np.zeros((N, n_b, 2), dtype=np.int32)
+    for s0 in range(0, N, chunk):
+        w = np.asarray(weights[s0:s0 + chunk], dtype=np.float64)                  # (n, 300, n_b)
+        sc = 10.0 ** (bscale[None, :] - 0.4 * (M0 + muhat[s0:s0 + chunk, None]))   # (n, n_b)
+        w32 = (np.transpose(w, (0, 2, 1)) * sc[:, :, None]).astype(np.float32)     # (n, n_b, 300)
+        nz = w32 != 0
+        any_nz = nz.any(axis=2)
+        sup_h[s0:s0 + chunk, :, 0] = np.where(any_nz, nz.argmax(axis=2), 0)
+        sup_h[s0:s0 + chunk, :, 1] = np.where(any_nz, NBINS - nz[:, :, ::-1].argmax(axis=2), 0)
+        wt[s0:s0 + chunk, :, :NBINS] = torch.from_numpy(w32).to(device)
+    # valid observations first, widest band support first: the kernel processes observations in
+    # pairs (one per half-warp) and a pair costs as many rounds as its wider member
+    band_c = np.clip(band, 0, n_b - 1)
+    width = np.take_along_axis(sup_h[:, :, 1] - sup_h[:, :, 0], band_c, axis=1)
+    key = np.where(mask, -width.astype(np.int64) * n_b - band_c, np.iinfo(np.int64).max)
+    order = np.argsort(key, axis=1, kind='stable')
     take = lambda a: np.take_along_axis(a, order, axis=1)
     t, y, sig, band, mask = take(t), take(y), take(sig), take(band), take(mask)
     n_valid = mask.sum(axis=1).astype(np.int32)
@@ -41,29 +64,10 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
     obs4[..., 1] = np.where(mask, y, 0.0)
     obs4[..., 2] = np.where(mask, 1.0 / safe_sig, 0.0)
     obs4[..., 3] = np.where(mask, band, 0).astype(np.int32).view(np.float32)
-    if np.any((band < 0) | (band >= n_b)):
-        raise ValueError('band index out of range of the weights array')
     half_l2pi = 0.5 * math.log(2 * math.pi)
     lconst = np.sum(np.where(mask, -np.log(safe_sig) - half_l2pi, 0.0), axis=1)
     lconst += -half_l2pi * (1 + n_eps) - math.log(tauA) - math.log(Ds_prior_sd) - half_l2pi
-    bscale = band_log10_scale(zps, offsets)
-    assert bscale.shape[0] == n_b
-    # one spare row after the last tile: the kernels' last 32-bin round may read (and discard) up
-    # to 31 floats past a row's end
-    wt_store = torch.zeros((N * n_b + 1, BPAD), dtype=torch.float32, device=device)
-    wt = wt_store[:N * n_b].view(N, n_b, BPAD)
-    sup = torch.zeros((N, n_b, 2), dtype=torch.int32, device=device)
-    for s0 in range(0, N, chunk):
-        w = np.asarray(weights[s0:s0 + chunk], dtype=np.float64)                  # (n, 300, n_b)
-        sc = 10.0 ** (bscale[None, :] - 0.4 * (M0 + muhat[s0:s0 + chunk, None]))   # (n, n_b)
-        w32 = (np.transpose(w, (0, 2, 1)) * sc[:, :, None]).astype(np.float32)     # (n, n_b, 300)
-        nz = w32 != 0
-        any_nz = nz.any(axis=2)
-        first = np.where(any_nz, nz.argmax(axis=2), 0)
-        last = np.where(any_nz, NBINS - nz[:, :, ::-1].argmax(axis=2), 0)
-        wt[s0:s0 + chunk, :, :NBINS] = torch.from_numpy(w32).to(device)
-        sup[s0:s0 + chunk] = torch.from_numpy(np.stack([first, last], axis=-1).astype(np.int32)).to(device)
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
-    return dict(N=N, N_obs=N_obs, n_b=n_b, obs4=to(obs4), n_valid=to(n_valid), weights=wt, support=sup,
+    return dict(N=N, N_obs=N_obs, n_b=n_b, obs4=to(obs4), n_valid=to(n_valid), weights=wt, support=to(sup_h),
                 muhat=to(muhat.astype(np.float32)), lconst=to(lconst.astype(np.float32)),
                 muhat64=muhat, order=order, _weights_storage=wt_store)

@@ -69,7 +69,7 @@ typedef struct {
  *   obs4[s][o]   = {phase t, FLUXCAL y, 1/sigma, band index as float}; valid observations first
  *   n_valid[s]   = number of unmasked observations of SN s (<= N_obs)
  *   weights[s][k][BAYESN_BPAD] = band weight * 10^(0.4(27.5-offset_k) - zp_k/2.5 - 0.4(M0+muhat_s));
- *                  the allocation must extend 32 floats past the last row (read, never used)
+ *                  the allocation must extend 3 rows (3*BAYESN_BPAD floats) past the last row (read, never used)
  *   support[s][k] = {first, one-past-last} bin with a non-zero weight (exact zeros only)
  *   muhat[s]     = fiducial distance modulus;  lconst[s] = data-only log-density constant */
 typedef struct {

@@ -71,7 +71,15 @@ def test_pack_dataset_layout():
     # masked observation moved behind the valid ones
     assert np.allclose(np.sort(o4[0, :4, 0]), np.sort(np.delete(obs[0, :, 0], 1)), rtol=1e-6)
     band = o4[..., 3].view(np.int32)
-    assert np.all(band[0, :4] == np.delete(obs[4, :, 0], 1).astype(int))
+    # valid observations are ordered by decreasing band-support width (pairs of observations share
+    # a half-warp round count), each one keeping its own (t, y, 1/sigma, band)
+    order = p['order'][0, :4]
+    assert sorted(order.tolist()) == [0, 2, 3, 4]
+    assert np.all(band[0, :4] == obs[4, order, 0].astype(int))
+    assert np.allclose(o4[0, :4, 0], obs[0, order, 0], rtol=1e-6) and np.allclose(o4[0, :4, 2], 1 / obs[2, order, 0], rtol=1e-6)
+    width = {1: 50, 2: 1, 3: 0}
+    ws = [width[b] for b in band[0, :4]]
+    assert ws == sorted(ws, reverse=True)
     sup = p['support'].numpy()
     assert sup[0, 1].tolist() == [40, 90] and sup[0, 2].tolist() == [100, 101] and sup[0, 3].tolist() == [0, 0]
     assert p['weights'].shape == (N, n_b, 304) and float(p['weights'][0, 1, 300:].abs().sum()) == 0
