@@ -57,7 +57,7 @@ int ntile_for(int C) { return (C % WPB == 0) ? 1 : (C == 1 ? WPB : 2); }
 template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
 int launch_logp(bayesn_ctx* ctx, int C, const float* q, float* logp, float* grad, cudaStream_t st) {
     const int ntile = ntile_for(C);
-    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ntile, RVFREE, STAGE);
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE);
     const size_t bytes = (size_t)P.totalFloats * 4;
     auto kern = logp_grad_kernel<LP, TP, VPL, RVFREE, STAGE>;
     if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
@@ -75,7 +75,7 @@ int launch_nuts(bayesn_ctx* ctx, const NutsDev& cfg, const float* q0, float* sam
                 float* work, cudaStream_t st) {
     const int C = cfg.num_chains;
     const int ntile = ntile_for(C);
-    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ntile, RVFREE, STAGE);
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE);
     const size_t bytes = (size_t)P.totalFloats * 4;
     auto kern = nuts_kernel<LP, TP, VPL, RVFREE, STAGE>;
     if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
@@ -210,14 +210,17 @@ int bayesn_set_model(bayesn_ctx* ctx, const bayesn_model_desc* m) {
         tau[a] = m->tau_knots[a];
         for (int b = 0; b < T; ++b) KD[(size_t)a * TP + b] = m->KD_t[(size_t)a * T + b];
     }
+    bool lower = true;
     for (int i = 0; i < ne; ++i)
         for (int j = 0; j < ne; ++j) {
             Ls[(size_t)i * ne + j] = m->L_Sigma[(size_t)i * ne + j];
             LsT[(size_t)j * ne + i] = m->L_Sigma[(size_t)i * ne + j];
+            if (j > i && m->L_Sigma[(size_t)i * ne + j] != 0.f) lower = false;
         }
     ModelDev& M = ctx->M;
     M = ModelDev{};
     M.L = L; M.T = T; M.n_eps = ne; M.D = D; M.n_sc = n_sc; M.rv_mode = m->rv_mode;
+    M.ls_lower = lower ? 1 : 0;
     M.fix_tmax = m->fix_tmax; M.fix_theta = m->fix_theta; M.fix_AV = m->fix_AV;
     M.theta_val = m->theta_val; M.AV_val = m->AV_val;
     M.inv_tauA = 1.f / m->tauA;
@@ -238,14 +241,15 @@ int bayesn_set_model(bayesn_ctx* ctx, const bayesn_model_desc* m) {
 int bayesn_bind_dataset(bayesn_ctx* ctx, const bayesn_dataset_desc* d) {
     if (!ctx || !d) return -1;
     if (d->N <= 0 || d->N_obs <= 0 || d->n_b <= 0) return fail(ctx, -1, "empty dataset");
-    if ((d->n_b * BP * 4) % 16 || ((uintptr_t)d->obs4 & 15) || ((uintptr_t)d->weights & 15))
-        return fail(ctx, -1, "dataset arrays must be 16-byte aligned");
+    if (d->wt_stride <= 0 || (d->wt_stride % 4) || ((uintptr_t)d->obs4 & 15) || ((uintptr_t)d->weights & 15) ||
+        ((uintptr_t)d->support & 15))
+        return fail(ctx, -1, "dataset arrays must be 16-byte aligned and wt_stride a positive multiple of 4");
     DataDev& D = ctx->D;
-    D.N = d->N; D.N_obs = d->N_obs; D.n_b = d->n_b;
+    D.N = d->N; D.N_obs = d->N_obs; D.n_b = d->n_b; D.wt_stride = d->wt_stride;
     D.obs4 = reinterpret_cast<const float4*>(d->obs4);
     D.n_valid = d->n_valid;
     D.wt = d->weights;
-    D.sup = reinterpret_cast<const int2*>(d->support);
+    D.sup = reinterpret_cast<const int4*>(d->support);
     D.muhat = d->muhat;
     D.lconst = d->lconst;
     ctx->have_data = true;

@@ -33,6 +33,7 @@ constexpr unsigned FULL = 0xffffffffu;
 
 struct ModelDev {
     int L, T, n_eps, D, n_sc, rv_mode;
+    int ls_lower;       // L_Sigma is exactly lower triangular (true for every shipped model): halve the mat-vecs
     int fix_tmax, fix_theta, fix_AV;
     float theta_val, AV_val;
     float inv_tauA, inv_sd2, RV, mu_R, sigma_R, phi_alpha;
@@ -52,8 +53,9 @@ struct DataDev {
     int N, N_obs, n_b;
     const float4* obs4;     // [N][N_obs]
     const int* n_valid;     // [N]
-    const float* wt;        // [N][n_b][BP]
-    const int2* sup;        // [N][n_b]
+    int wt_stride;          // floats per SN in the compact weight tiles (multiple of 4)
+    const float* wt;        // [N][wt_stride]  band rows packed back to back over their supports
+    const int4* sup;        // [N][n_b]        {first bin, one-past-last bin, offset of the row in the tile, 0}
     const float* muhat;     // [N]
     const float* lconst;    // [N]
 };
@@ -196,19 +198,23 @@ __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.96
 template <int LP, int TP>
 struct Dims {
     static constexpr int LP4 = (LP + 3) & ~3;
-    // per-observation record in shared memory: [u (LP4) | u' (LP4) | J_t (TP) | frac, hsiao idx, y, 1/sigma, band]
-    static constexpr int REC_RAW = (2 * LP4 + TP + 5 + 3) & ~3;
+    // per-observation record in shared memory:
+    //   [u (LP4) | J_t (TP) | J_t' (TP) | pad | frac, hsiao idx + flags + band, y, 1/sigma]
+    static constexpr int R_JT = LP4, R_DJ = LP4 + TP, R_SC = (LP4 + 2 * TP + 3) & ~3;
+    static constexpr int REC_RAW = R_SC + 4;
     static constexpr int REC = ((REC_RAW / 4) % 2 == 1) ? REC_RAW : REC_RAW + 4;   // odd #16B words: fewer conflicts
-    static constexpr int R_DU = LP4, R_JT = 2 * LP4, R_F = 2 * LP4 + TP, R_IDX = R_F + 1, R_Y = R_F + 2,
-                         R_IS = R_F + 3, R_BAND = R_F + 4;
     static constexpr int NPAIR = (LP * TP + 31) / 32;   // (l, m) pairs per lane
     // J_l is stored bin-major, one row of RS floats per wavelength bin, read as LDS.128; an odd
     // number of 16-byte words per row keeps the 8-lane phases of LDS.128 bank-conflict free
     static constexpr int RS = ((LP4 / 4) % 2 == 1) ? LP4 : LP4 + 4;
 };
 constexpr int JROWS = BP + 32;   // per-bin tables carry 32 zero rows so the last round may overrun
-constexpr int OVERRUN = 320;     // bins a lane may read past the end of its band's support (values discarded)
+constexpr int OVERRUN = BAYESN_OVERRUN;     // bins a lane may read past the end of its band's support (values discarded)
 __host__ __device__ constexpr int jl_row_stride(int LP) { return ((((LP + 3) & ~3) / 4) % 2 == 1) ? ((LP + 3) & ~3) : ((LP + 3) & ~3) + 4; }
+__host__ __device__ constexpr int rec_stride(int LP, int TP) {
+    int raw = ((((LP + 3) & ~3) + 2 * TP + 3) & ~3) + 4;
+    return ((raw / 4) % 2 == 1) ? raw : raw + 4;
+}
 
 struct SmemPlan {
     // CTA-shared (float offsets)
@@ -219,12 +225,10 @@ struct SmemPlan {
     int totalFloats;
 };
 
-__host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b, int N_obs, int ntile, bool rvfree,
-                                              bool stage) {
+__host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b, int N_obs, int wt_stride, int ntile,
+                                              bool rvfree, bool stage) {
     SmemPlan p;
-    int LP4 = (LP + 3) & ~3;
-    int rec = (2 * LP4 + TP + 5 + 3) & ~3;
-    if ((rec / 4) % 2 == 0) rec += 4;
+    const int rec = rec_stride(LP, TP);
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
     p.oJl = take(JROWS * jl_row_stride(LP));
@@ -234,8 +238,8 @@ __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b
     p.oW1 = take(LP * TP);
     p.oKD = take(TP * TP);
     p.oTau = take(TP);
-    p.oWt = take(stage ? ntile * n_b * BP + 32 : 0);
-    p.oSup = take(ntile * n_b * 2);
+    p.oWt = take(stage ? ntile * wt_stride : 0);
+    p.oSup = take(ntile * n_b * 4);
     p.oObs = take(ntile * N_obs * 4);
     p.oBar = take(4);
     p.oWarp = o;
@@ -263,7 +267,7 @@ struct WarpCtx {
     const float *sJl, *sAd, *sMf, *sW0, *sW1, *sKD, *sTau;
     const float* wt_s;    // this SN's weight tile staged in shared memory (STAGE) ...
     const float* wt_g;    // ... or in global memory (read through L1)
-    const int2* sup;      // this SN's band supports (shared)
+    const int4* sup;      // this SN's band supports (shared)
     const float4* obs;    // this SN's observations (shared)
     float *Ws, *ev, *eps, *rec, *sc, *wad, *wdad;
     int nobs;
@@ -386,11 +390,15 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         if (i < ne) c.ev[i] = q[s];
     }
     __syncwarp();
-    for (int i = lane; i < ne; i += 32) {
+    for (int i0 = 0; i0 < ne; i0 += 32) {
+        const int i = i0 + lane;
+        const int jend = M.ls_lower ? min(ne, i0 + 32) : ne;      // eps_i = sum_{j <= i} L[i][j] e_j
         float acc = 0.f;
-        const float* col = M.LsT + i;
-        for (int j = 0; j < ne; ++j) acc = fmaf(__ldg(col + j * ne), c.ev[j], acc);
-        c.eps[i] = acc;
+        if (i < ne) {
+            const float* col = M.LsT + i;
+            for (int j = 0; j < jend; ++j) acc = fmaf(__ldg(col + j * ne), c.ev[j], acc);
+            c.eps[i] = acc;
+        }
     }
     __syncwarp();
     for (int p = lane; p < LP * TP; p += 32) {
@@ -455,20 +463,18 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         spline_row<TP>(t, T, c.sTau, c.sKD, J, dJ);
         float* rc = c.rec + o * REC;
 #pragma unroll
-        for (int m = 0; m < TP; ++m) rc[DM::R_JT + m] = J[m];
+        for (int m = 0; m < TP; ++m) {
+            rc[DM::R_JT + m] = J[m];
+            rc[DM::R_DJ + m] = dJ[m];
+        }
 #pragma unroll
         for (int l = 0; l < LP4; ++l) {
-            float u = 0.f, du = 0.f;
+            float u = 0.f;
             if (l < LP) {
 #pragma unroll
-                for (int m = 0; m < TP; ++m) {
-                    float w = c.Ws[l * TP + m];
-                    u = fmaf(w, J[m], u);
-                    du = fmaf(w, dJ[m], du);
-                }
+                for (int m = 0; m < TP; ++m) u = fmaf(c.Ws[l * TP + m], J[m], u);
             }
             rc[l] = -C2 * u;
-            rc[DM::R_DU + l] = du;              // (W J_t')[l], used once at the end for d/dtmax
         }
         float fl = floorf(t);
         int i0 = 19 + (int)fl, i1 = 19 + (int)ceilf(t);
@@ -477,11 +483,9 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         // the upper Hsiao row is read at i0 + 1; when ceil == floor (integer phase) or the index
         // is clamped the interpolation degenerates to row i0 and d/dt of it vanishes
         const bool interp = i1 != i0;
-        rc[DM::R_F] = interp ? (t - fl) : 0.f;
-        rc[DM::R_IDX] = __int_as_float(i0 | (interp ? 256 : 0));
-        rc[DM::R_Y] = dummy ? 0.f : ob.y;
-        rc[DM::R_IS] = dummy ? 0.f : ob.z;
-        rc[DM::R_BAND] = ob.w;
+        *reinterpret_cast<float4*>(rc + DM::R_SC) =
+            make_float4(interp ? (t - fl) : 0.f, __int_as_float(i0 | (interp ? 256 : 0) | (__float_as_int(ob.w) << 16)),
+                        dummy ? 0.f : ob.y, dummy ? 0.f : ob.z);
     }
     __syncwarp();
 
@@ -492,6 +496,11 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     float gDs = 0.f, gAV = 0.f, gT = 0.f, gRV = 0.f;
     const float* wtile = STAGE ? c.wt_s : c.wt_g;
     const int hl = lane & 15, hb = lane & 16;
+    // lane hl = 4 + l ends every reduction holding Q_l; it also keeps row l of W for the d/dtmax term
+    float wrow[TP];
+#pragma unroll
+    for (int m = 0; m < TP; ++m) wrow[m] = (hl >= 4 && hl < 4 + LP) ? c.Ws[(hl - 4) * TP + m] : 0.f;
+    float gTW = 0.f;
     for (int p = 0; p < npair; ++p) {
         float* rc = c.rec + (2 * p + (lane >> 4)) * REC;
         float u[LP4];
@@ -503,17 +512,17 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
                 u[4 * j] = a.x; u[4 * j + 1] = a.y; u[4 * j + 2] = a.z; u[4 * j + 3] = a.w;
             }
         }
-        const float f = rc[DM::R_F];
-        const int pk = __float_as_int(rc[DM::R_IDX]);
-        const float yo = rc[DM::R_Y], iso = rc[DM::R_IS];
-        const int k = __float_as_int(rc[DM::R_BAND]);
-        const int2 sp = c.sup[k];
+        const float4 scal = *reinterpret_cast<const float4*>(rc + DM::R_SC);
+        const float f = scal.x;
+        const int pk = __float_as_int(scal.y);
+        const float yo = scal.z, iso = scal.w;
+        const int4 sp = c.sup[pk >> 16];
         int nr = (sp.y - sp.x + 15) >> 4;
         nr = max(nr, __shfl_xor_sync(FULL, nr, 16));
         // running pointers: one add per array per round instead of rebuilding addresses
         const int b_first = sp.x + hl;
         const float* p0 = hs + (pk & 0xff) * BP + b_first;
-        const float* pw = wtile + k * BP + b_first;
+        const float* pw = wtile + sp.z + hl;
         const float4* pj = reinterpret_cast<const float4*>(c.sJl) + b_first * (RS / 4);
         const float* pa = adv + b_first;
         const float* pda = RVFREE ? (c.wdad + b_first) : nullptr;
@@ -566,9 +575,15 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         gAV = fmaf(-KAPPA * coef, FA, gAV);
         gT = fmaf((pk & 256) ? coef : 0.f, FT, gT);
         if (RVFREE) gRV = fmaf(-KAPPA * AV * coef, __shfl_sync(FULL, val, hb | 3), gRV);
-        // d logL / d(sum_m W[l][m] Jt[m]) for this observation, overwriting u (no longer needed)
+        // d logL / d(sum_m W[l][m] Jt[m]) for this observation, overwriting u (no longer needed),
+        // and its product with (W J_t'(t))[l] for the gradient through the time spline
+        const float dU = -KAPPA * coef * val;
+        float du = 0.f;
+#pragma unroll
+        for (int m = 0; m < TP; ++m) du = fmaf(wrow[m], rc[DM::R_DJ + m], du);
+        gTW = fmaf(dU, du, gTW);
         __syncwarp();
-        if (hl >= 4 && hl < 4 + LP) rc[hl - 4] = -KAPPA * coef * val;
+        if (hl >= 4 && hl < 4 + LP) rc[hl - 4] = dU;
     }
     // the two halves hold the sums over their own observations
     logL += __shfl_xor_sync(FULL, logL, 16);
@@ -578,19 +593,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     if (RVFREE) gRV += __shfl_xor_sync(FULL, gRV, 16);
     __syncwarp();
 
-    // ---- d/dtmax through the time spline: sum_o sum_l dU[o][l] (W J_t'(t_o))[l], lanes over obs --
-    {
-        float gw = 0.f;
-        for (int o = lane; o < c.nobs; o += 32) {
-            const float4* a4 = reinterpret_cast<const float4*>(c.rec + o * REC);
-#pragma unroll
-            for (int j = 0; j < LP4 / 4; ++j) {
-                const float4 a = a4[j], b = a4[LP4 / 4 + j];
-                gw = fmaf(a.x, b.x, gw); gw = fmaf(a.y, b.y, gw); gw = fmaf(a.z, b.z, gw); gw = fmaf(a.w, b.w, gw);
-            }
-        }
-        gT += wsum(gw);
-    }
+    gT += wsum(gTW);
 
     // ---- reverse: dW, theta, eps_tform -------------------------------------------------------
     float dW[NPAIR];
@@ -627,7 +630,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         if (i < ne) {
             float acc = 0.f;
             const float* col = M.Ls + i;
-            for (int j = 0; j < ne; ++j) acc = fmaf(__ldg(col + j * ne), c.ev[j], acc);
+            for (int j = M.ls_lower ? 32 * s : 0; j < ne; ++j) acc = fmaf(__ldg(col + j * ne), c.ev[j], acc);
             gi = acc - q[s];
             ss = fmaf(q[s], q[s], ss);
         }
@@ -671,7 +674,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
 template <int LP, int TP, bool RVFREE, bool STAGE>
 __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, int n_chains, int ntile, float* smem,
                                           WarpCtx& c, int& sn, int& chain) {
-    const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, ntile, RVFREE, STAGE);
+    const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE);
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long unit0 = (long long)blockIdx.x * WPB;
     const long long total = (long long)Dd.N * n_chains;
@@ -689,13 +692,13 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
         constexpr uint32_t kJlBytes = JROWS * Dims<LP, TP>::RS * 4;
         uint32_t bytes = kJlBytes + (RVFREE ? 9 * BP * 4 : JROWS * 4);
         bytes += nt * Dd.N_obs * 16;
-        if (STAGE) bytes += nt * Dd.n_b * BP * 4;
+        if (STAGE) bytes += nt * Dd.wt_stride * 4;
         mbar_expect_tx(bar, bytes);
         tma_load_1d(sJl, M.Jl, kJlBytes, bar);
         if (RVFREE) tma_load_1d(smem + P.oMf, M.Mf, 9 * BP * 4, bar);
         else tma_load_1d(smem + P.oAd, M.ad, JROWS * 4, bar);
         tma_load_1d(smem + P.oObs, Dd.obs4 + (size_t)s_first * Dd.N_obs, nt * Dd.N_obs * 16, bar);
-        if (STAGE) tma_load_1d(smem + P.oWt, Dd.wt + (size_t)s_first * Dd.n_b * BP, nt * Dd.n_b * BP * 4, bar);
+        if (STAGE) tma_load_1d(smem + P.oWt, Dd.wt + (size_t)s_first * Dd.wt_stride, nt * Dd.wt_stride * 4, bar);
     }
     // small tables with plain loads while the bulk copies are in flight
     for (int i = tid; i < LP * TP; i += blockDim.x) {
@@ -704,7 +707,7 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
     }
     for (int i = tid; i < TP * TP; i += blockDim.x) smem[P.oKD + i] = M.KD[i];
     for (int i = tid; i < TP; i += blockDim.x) smem[P.oTau + i] = M.tau[i];
-    int2* sSup = reinterpret_cast<int2*>(smem + P.oSup);
+    int4* sSup = reinterpret_cast<int4*>(smem + P.oSup);
     for (int i = tid; i < nt * Dd.n_b; i += blockDim.x) sSup[i] = Dd.sup[(size_t)s_first * Dd.n_b + i];
     mbar_wait(bar, 0);
     __syncthreads();
@@ -729,9 +732,9 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
     c.sW1 = smem + P.oW1;
     c.sKD = smem + P.oKD;
     c.sTau = smem + P.oTau;
-    c.wt_s = at(P.oWt + slot * Dd.n_b * BP);
-    c.wt_g = Dd.wt + (size_t)sn * Dd.n_b * BP;
-    c.sup = reinterpret_cast<const int2*>(at(P.oSup + slot * Dd.n_b * 2));
+    c.wt_s = at(P.oWt + slot * Dd.wt_stride);
+    c.wt_g = Dd.wt + (size_t)sn * Dd.wt_stride;
+    c.sup = reinterpret_cast<const int4*>(at(P.oSup + slot * Dd.n_b * 4));
     c.obs = reinterpret_cast<const float4*>(smem + P.oObs) + slot * Dd.N_obs;
     c.Ws = smem + wbase + P.wWs;
     c.ev = smem + wbase + P.wEv;

@@ -132,6 +132,9 @@ __global__ void __launch_bounds__(128) flux_kernel(FluxArgs A) {
 //     SURVEY.md Appendix C): multinomial sampling, checkpointed U-turn test, dual averaging,
 //     Stan-style windowed diagonal mass matrix.
 // ------------------------------------------------------------------------------------------
+#ifndef NUTS_MIN_CTAS
+#define NUTS_MIN_CTAS 4
+#endif
 enum { V_ZL = 0, V_RL, V_GL, V_ZR, V_RR, V_GR, V_ZP, V_GP, V_RSUM, V_SZP, V_SGP, V_WMEAN, V_WM2, V_CKPT };
 __host__ __device__ inline int nuts_num_vectors(int max_depth) { return V_CKPT + 2 * max_depth; }
 
@@ -180,7 +183,7 @@ __device__ __forceinline__ float logaddexpf(float a, float b) {
 }
 
 template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
-__global__ void __launch_bounds__(WPB * 32, 4) nuts_kernel(ModelDev M, DataDev Dd, NutsDev cfg, int ntile,
+__global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev M, DataDev Dd, NutsDev cfg, int ntile,
                                                         const float* __restrict__ q_init, float* __restrict__ samples,
                                                         float* __restrict__ stats, float* __restrict__ chain_info,
                                                         float* __restrict__ work) {

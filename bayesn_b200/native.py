@@ -9,9 +9,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libbayesn_b200.so')
+LIB_PATH = os.environ.get('BAYESN_B200_LIB', os.path.join(_HERE, 'csrc', 'libbayesn_b200.so'))
 
-NBINS, BPAD, NPHASE = 300, 304, 105
+NBINS, BPAD, NPHASE, OVERRUN = 300, 304, 105, 320
 RV_FIXED, RV_POP, RV_UNIFORM = 0, 1, 2
 
 _fp = C.POINTER(C.c_float)
@@ -28,7 +28,7 @@ class ModelDesc(C.Structure):
 
 
 class DatasetDesc(C.Structure):
-    _fields_ = [('N', C.c_int32), ('N_obs', C.c_int32), ('n_b', C.c_int32),
+    _fields_ = [('N', C.c_int32), ('N_obs', C.c_int32), ('n_b', C.c_int32), ('wt_stride', C.c_int32),
                 ('obs4', C.c_void_p), ('n_valid', C.c_void_p), ('weights', C.c_void_p), ('support', C.c_void_p),
                 ('muhat', C.c_void_p), ('lconst', C.c_void_p)]
 
@@ -149,6 +149,7 @@ class Context:
         self._keep['data'] = packed
         d = DatasetDesc()
         d.N, d.N_obs, d.n_b = int(packed['N']), int(packed['N_obs']), int(packed['n_b'])
+        d.wt_stride = int(packed['wt_stride'])
         for k in ('obs4', 'n_valid', 'weights', 'support', 'muhat', 'lconst'):
             setattr(d, k, packed[k].data_ptr())
         self._check(self.lib.bayesn_bind_dataset(self.h, C.byref(d)), 'bayesn_bind_dataset')

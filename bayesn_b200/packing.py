@@ -5,7 +5,7 @@ import math
 
 import numpy as np
 
-from .native import BPAD, NBINS
+from .native import NBINS, OVERRUN
 
 
 def band_log10_scale(zps, offsets):
@@ -19,7 +19,8 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
     * valid (mask != 0) observations are moved to the front of each SN; ``n_valid`` counts them;
     * the band scale 10^(0.4(27.5-offset) - zp/2.5 - 0.4(M0 + muhat)) is folded into the weight
       tile in float64 before rounding to float32, so the kernel never forms 10^27-sized factors;
-    * ``support`` is the exact non-zero extent of each (SN, band) row;
+    * ``support`` is the exact non-zero extent of each (SN, band) row and the offset of that row
+      in the SN's compact weight tile (only bands the SN was observed in are stored);
     * ``lconst`` collects every parameter-independent term of the log joint density.
     """
     import torch
@@ -35,20 +36,44 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
         raise ValueError('band index out of range of the weights array')
     bscale = band_log10_scale(zps, offsets)
     assert bscale.shape[0] == n_b
-    # spare rows after the last tile: lanes past the end of a band's support keep reading (and
-    # discard) up to OVERRUN = 320 floats while the other half-warp finishes a wider band
-    wt_store = torch.zeros((N * n_b + 3, BPAD), dtype=torch.float32, device=device)
-    wt = wt_store[:N * n_b].view(N, n_b, BPAD)
-    sup_h = np.zeros((N, n_b, 2), dtype=np.int32)
+    # exact non-zero extent of every (SN, band) weight row after rounding to float32; bands without
+    # a valid observation of that SN (always the NULL band 0) get an empty row
+    used = np.zeros((N, n_b), dtype=bool)
+    rows = np.repeat(np.arange(N), N_obs)
+    used[rows[mask.ravel()], band.ravel()[mask.ravel()]] = True
+    sup_h = np.zeros((N, n_b, 4), dtype=np.int32)
+    tiles = []
+    bins = np.arange(NBINS)[None, None, :]
     for s0 in range(0, N, chunk):
         w = np.asarray(weights[s0:s0 + chunk], dtype=np.float64)                  # (n, 300, n_b)
         sc = 10.0 ** (bscale[None, :] - 0.4 * (M0 + muhat[s0:s0 + chunk, None]))   # (n, n_b)
         w32 = (np.transpose(w, (0, 2, 1)) * sc[:, :, None]).astype(np.float32)     # (n, n_b, 300)
-        nz = w32 != 0
+        nz = (w32 != 0) & used[s0:s0 + chunk, :, None]
         any_nz = nz.any(axis=2)
-        sup_h[s0:s0 + chunk, :, 0] = np.where(any_nz, nz.argmax(axis=2), 0)
-        sup_h[s0:s0 + chunk, :, 1] = np.where(any_nz, NBINS - nz[:, :, ::-1].argmax(axis=2), 0)
-        wt[s0:s0 + chunk, :, :NBINS] = torch.from_numpy(w32).to(device)
+        first = np.where(any_nz, nz.argmax(axis=2), 0)
+        last = np.where(any_nz, NBINS - nz[:, :, ::-1].argmax(axis=2), 0)
+        width = last - first
+        off = np.cumsum(width, axis=1) - width
+        sup_h[s0:s0 + chunk, :, 0], sup_h[s0:s0 + chunk, :, 1], sup_h[s0:s0 + chunk, :, 2] = first, last, off
+        # compact tile: the rows of one SN back to back over their supports (C3: ~470 floats
+        # instead of 9 x 304)
+        n = w32.shape[0]
+        inside = (bins >= first[:, :, None]) & (bins < last[:, :, None])
+        dest = (off[:, :, None] + bins - first[:, :, None])[inside]
+        srow = np.broadcast_to(np.arange(n)[:, None, None], inside.shape)[inside]
+        tile = np.zeros((n, max(4, int(width.sum(axis=1).max()))), dtype=np.float32)
+        tile[srow, dest] = w32[inside]
+        tiles.append(tile)
+    wt_stride = -(-max(t_.shape[1] for t_ in tiles) // 4) * 4     # 16-byte granular for the TMA copy
+    # lanes past the end of a band's support keep reading (and discard) up to OVERRUN floats while
+    # the other half-warp finishes a wider band: spare room after the last tile
+    wt_store = torch.zeros(N * wt_stride + OVERRUN + 32, dtype=torch.float32, device=device)
+    wt = wt_store[:N * wt_stride].view(N, wt_stride)
+    s0 = 0
+    for tile in tiles:
+        wt[s0:s0 + tile.shape[0], :tile.shape[1]] = torch.from_numpy(tile).to(device)
+        s0 += tile.shape[0]
+    del tiles
     # valid observations first, widest band support first: the kernel processes observations in
     # pairs (one per half-warp) and a pair costs as many rounds as its wider member
     band_c = np.clip(band, 0, n_b - 1)
@@ -68,6 +93,6 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
     lconst = np.sum(np.where(mask, -np.log(safe_sig) - half_l2pi, 0.0), axis=1)
     lconst += -half_l2pi * (1 + n_eps) - math.log(tauA) - math.log(Ds_prior_sd) - half_l2pi
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
-    return dict(N=N, N_obs=N_obs, n_b=n_b, obs4=to(obs4), n_valid=to(n_valid), weights=wt, support=to(sup_h),
+    return dict(N=N, N_obs=N_obs, n_b=n_b, wt_stride=wt_stride, obs4=to(obs4), n_valid=to(n_valid), weights=wt, support=to(sup_h),
                 muhat=to(muhat.astype(np.float32)), lconst=to(lconst.astype(np.float32)),
                 muhat64=muhat, order=order, _weights_storage=wt_store)

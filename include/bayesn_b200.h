@@ -30,6 +30,7 @@ extern "C" {
 
 #define BAYESN_NBINS 300      /* spectrum_bins, bayesn/bayesn_model.py:295 */
 #define BAYESN_BPAD 304       /* row stride of every per-bin table (16-byte aligned rows) */
+#define BAYESN_OVERRUN 320    /* floats the kernels may read (and discard) past a band row's support */
 #define BAYESN_NPHASE 105     /* Hsiao phase grid -19..85, bayesn/bayesn_model.py:274 */
 #define BAYESN_MAX_L 12
 #define BAYESN_MAX_T 10
@@ -68,12 +69,16 @@ typedef struct {
  * (bayesn/bayesn_model.py:2096-2106, :2711-2730); bayesn_b200/model.py builds it.
  *   obs4[s][o]   = {phase t, FLUXCAL y, 1/sigma, band index as float}; valid observations first
  *   n_valid[s]   = number of unmasked observations of SN s (<= N_obs)
- *   weights[s][k][BAYESN_BPAD] = band weight * 10^(0.4(27.5-offset_k) - zp_k/2.5 - 0.4(M0+muhat_s));
- *                  the allocation must extend 3 rows (3*BAYESN_BPAD floats) past the last row (read, never used)
- *   support[s][k] = {first, one-past-last} bin with a non-zero weight (exact zeros only)
+ *   weights[s][wt_stride] = compact weight tile of SN s: for every band k that has observations,
+ *                  the non-zero extent [first_k, last_k) of
+ *                  band weight * 10^(0.4(27.5-offset_k) - zp_k/2.5 - 0.4(M0+muhat_s)), rows packed back
+ *                  to back at support[s][k].offset; wt_stride is a multiple of 4 and the allocation
+ *                  must extend BAYESN_OVERRUN floats past the last tile (read, never used)
+ *   support[s][k] = {first, one-past-last, offset, 0}: exact non-zero extent of the band weight
+ *                  (threshold-free: exact zeros only) and where its row starts inside the tile
  *   muhat[s]     = fiducial distance modulus;  lconst[s] = data-only log-density constant */
 typedef struct {
-    int32_t N, N_obs, n_b;
+    int32_t N, N_obs, n_b, wt_stride;
     const float* obs4;
     const int32_t* n_valid;
     const float* weights;

@@ -81,10 +81,23 @@ def test_pack_dataset_layout():
     ws = [width[b] for b in band[0, :4]]
     assert ws == sorted(ws, reverse=True)
     sup = p['support'].numpy()
-    assert sup[0, 1].tolist() == [40, 90] and sup[0, 2].tolist() == [100, 101] and sup[0, 3].tolist() == [0, 0]
-    assert p['weights'].shape == (N, n_b, 304) and float(p['weights'][0, 1, 300:].abs().sum()) == 0
+    # SN 0 observes bands drawn from {1, 2, 3}; band 3 has an all-zero weight row, band 0 is unused
+    used = set(band[0, :4].tolist())
+    exp = {1: [40, 90], 2: [100, 101], 3: [0, 0]}
+    off = 0
+    for k in range(n_b):
+        lo, hi = exp[k] if k in used and k in exp else [0, 0]
+        assert sup[0, k, :2].tolist() == [lo, hi]
+        if hi > lo:
+            assert sup[0, k, 2] == off
+            off += hi - lo
+    ws = p['wt_stride']
+    assert ws % 4 == 0 and p['weights'].shape == (N, ws)
+    assert p['_weights_storage'].numel() >= N * ws + 320
     sc = 10 ** (0.4 * 27.5 + 20.8 / 2.5 - 0.4 * (-19.5 + 34.0))
-    assert np.isclose(float(p['weights'][0, 1, 50]), 0.01 * sc, rtol=1e-6)
+    if 1 in used:
+        assert np.isclose(float(p['weights'][0, sup[0, 1, 2] + 10]), 0.01 * sc, rtol=1e-6)
+    assert float(p['weights'][2].abs().sum()) == 0          # SN without valid observations: empty tile
     with pytest.raises(ValueError):
         obs[4, 0, 1] = 7
         packing.pack_dataset(obs, w, zps, off, -19.5, 5.0, 0.2, 24, device='cpu')
