@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "bayesn_kernels.cuh"
+#include "bayesn_train.cuh"
 
 using namespace bayesn;
 
@@ -18,6 +19,9 @@ struct bayesn_ctx {
     DataDev D{};
     std::vector<void*> owned;   // device allocations made by set_model
     long long launches = 0;
+    TrainDev T{};               // training buffers (allocated on first use for a given (chains, N))
+    std::vector<void*> train_owned;
+    int train_C = 0, train_N = 0;
 };
 
 namespace {
@@ -44,9 +48,59 @@ int upload(bayesn_ctx* ctx, const std::vector<T>& h, const T** out) {
     return 0;
 }
 
+void free_train(bayesn_ctx* ctx) {
+    for (void* p : ctx->train_owned) cudaFree(p);
+    ctx->train_owned.clear();
+    ctx->train_C = ctx->train_N = 0;
+}
+
 void free_owned(bayesn_ctx* ctx) {
     for (void* p : ctx->owned) cudaFree(p);
     ctx->owned.clear();
+    free_train(ctx);
+}
+
+template <typename T>
+int train_alloc(bayesn_ctx* ctx, T** out, size_t n) {
+    void* d = nullptr;
+    CU_CHECK(ctx, cudaMalloc(&d, n * sizeof(T)));
+    CU_CHECK(ctx, cudaMemset(d, 0, n * sizeof(T)));
+    ctx->train_owned.push_back(d);
+    *out = static_cast<T*>(d);
+    return 0;
+}
+
+int train_prepare(bayesn_ctx* ctx, int C) {
+    if (ctx->train_C == C && ctx->train_N == ctx->D.N) return 0;
+    free_train(ctx);
+    TrainDev& T = ctx->T;
+    const int ne = ctx->M.n_eps, L = ctx->M.L, Tn = ctx->M.T;
+    T = TrainDev{};
+    T.C = C;
+    T.n_corr = ne * (ne - 1) / 2;
+    T.G = 2 * L * Tn + ne + T.n_corr + 3;
+    T.Dl = ne + 3;
+    T.LPTP = ctx->LP * ctx->TP;
+    T.PR = train_part_stride(T.LPTP);
+    T.R = train_red_len(T.LPTP, ne);
+    int rc = 0;
+    rc |= train_alloc(ctx, &T.W0, (size_t)C * T.LPTP);
+    rc |= train_alloc(ctx, &T.W1, (size_t)C * T.LPTP);
+    rc |= train_alloc(ctx, &T.Ls, (size_t)C * ne * ne);
+    rc |= train_alloc(ctx, &T.LsT, (size_t)C * ne * ne);
+    rc |= train_alloc(ctx, &T.ad, (size_t)C * JROWS + OVERRUN);
+    rc |= train_alloc(ctx, &T.dad, (size_t)C * JROWS + OVERRUN);
+    rc |= train_alloc(ctx, &T.sc, (size_t)C * 8);
+    rc |= train_alloc(ctx, &T.sig, (size_t)C * ne);
+    rc |= train_alloc(ctx, &T.Lo, (size_t)C * ne * ne);
+    rc |= train_alloc(ctx, &T.tm, (size_t)C * ne * ne);
+    rc |= train_alloc(ctx, &T.cum, (size_t)C * ne * ne);
+    rc |= train_alloc(ctx, &T.lpg, (size_t)C);
+    rc |= train_alloc(ctx, &T.part, (size_t)ctx->D.N * C * T.PR);
+    if (rc) return rc;
+    ctx->train_C = C;
+    ctx->train_N = ctx->D.N;
+    return 0;
 }
 
 struct Combo { int LP, TP, VPL; };
@@ -107,6 +161,30 @@ int dispatch(bayesn_ctx* ctx, bool stage, F&& f) {
 #undef BAYESN_CASE
     return fail(ctx, -4, "no kernel instantiation for this model shape");
 }
+
+template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
+int launch_train_sn(bayesn_ctx* ctx, const float* ql, float* grad_l, cudaStream_t st) {
+    if (RVFREE) return fail(ctx, -1, "training needs a fixed-RV model context (rv_mode = BAYESN_RV_FIXED)");
+    const int C = ctx->T.C;
+    const int ntile = ntile_for(C);
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, false, STAGE);
+    const size_t bytes = (size_t)P.totalFloats * 4;
+    auto kern = train_sn_kernel<LP, TP, (LP * TP - 2 * TP + 3 + 31) / 32, STAGE>;
+    if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
+    CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    const long long units = (long long)ctx->D.N * C;
+    const unsigned grid = (unsigned)((units + WPB - 1) / WPB);
+    kern<<<grid, WPB * 32, bytes, st>>>(ctx->M, ctx->D, ctx->T, ntile, ql, grad_l);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+struct TrainSnCall {
+    bayesn_ctx* ctx; const float* ql; float* grad_l; cudaStream_t st;
+    template <int LP, int TP, int VPL, bool RV, bool ST>
+    int operator()() { return launch_train_sn<LP, TP, VPL, RV, ST>(ctx, ql, grad_l, st); }
+};
 
 struct LogpCall {
     bayesn_ctx* ctx; int C; const float* q; float* logp; float* grad; cudaStream_t st;
@@ -252,6 +330,7 @@ int bayesn_bind_dataset(bayesn_ctx* ctx, const bayesn_dataset_desc* d) {
     D.sup = reinterpret_cast<const int4*>(d->support);
     D.muhat = d->muhat;
     D.lconst = d->lconst;
+    D.muerr2 = d->muhat_err2;
     ctx->have_data = true;
     return 0;
 }
@@ -362,6 +441,50 @@ int bayesn_flux_batch(bayesn_ctx* ctx, int N, int N_obs, int n_b, int mag, float
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     CU_CHECK(ctx, cudaFreeAsync(dbs, st));
+    return 0;
+}
+
+
+int bayesn_train_dims(bayesn_ctx* ctx, int* G, int* Dl, int* R) {
+    if (!ctx || !ctx->have_model) return -1;
+    const int ne = ctx->M.n_eps, L = ctx->M.L, T = ctx->M.T;
+    if (G) *G = 2 * L * T + ne + ne * (ne - 1) / 2 + 3;
+    if (Dl) *Dl = ne + 3;
+    if (R) *R = train_red_len(ctx->LP * ctx->TP, ne);
+    return 0;
+}
+
+int bayesn_train_begin(bayesn_ctx* ctx, int n_chains, const float* qg, const float* ql, float* grad_l, double* red,
+                       void* stream) {
+    if (!ctx) return -1;
+    if (!ctx->have_model || !ctx->have_data) return fail(ctx, -1, "set_model and bind_dataset first");
+    if (ctx->M.rv_mode != BAYESN_RV_FIXED) return fail(ctx, -1, "training needs rv_mode = BAYESN_RV_FIXED");
+    if (!ctx->D.muerr2) return fail(ctx, -1, "training data set needs muhat_err2");
+    if (n_chains < 1) return fail(ctx, -1, "n_chains must be >= 1");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    if (int rc = train_prepare(ctx, n_chains)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    train_globals_kernel<<<n_chains, 128, 0, st>>>(ctx->M, ctx->T, ctx->LP, ctx->TP, qg);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    TrainSnCall call{ctx, ql, grad_l, st};
+    if (int rc = dispatch(ctx, /*stage=*/n_chains >= 2, call)) return rc;
+    dim3 grid((ctx->T.R + 255) / 256, n_chains);
+    train_reduce_kernel<<<grid, 256, 0, st>>>(ctx->M, ctx->T, ctx->D.N, ctx->LP, ctx->TP, ql, red);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+int bayesn_train_finish(bayesn_ctx* ctx, int n_chains, const float* qg, const double* red, double* logp,
+                        float* grad_g, void* stream) {
+    if (!ctx) return -1;
+    if (!ctx->have_model || ctx->train_C != n_chains) return fail(ctx, -1, "bayesn_train_begin first");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    train_finish_kernel<<<n_chains, 128, 0, (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->LP, ctx->TP, qg, red, logp,
+                                                                     grad_g);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
     return 0;
 }
 

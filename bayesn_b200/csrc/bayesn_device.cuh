@@ -58,6 +58,7 @@ struct DataDev {
     const int4* sup;        // [N][n_b]        {first bin, one-past-last bin, offset of the row in the tile, 0}
     const float* muhat;     // [N]
     const float* lconst;    // [N]
+    const float* muerr2;    // [N] training only: squared prior width of muhat from the redshift error (:1174-1175)
 };
 
 struct NutsDev {
@@ -272,6 +273,12 @@ struct WarpCtx {
     float *Ws, *ev, *eps, *rec, *sc, *wad, *wdad;
     int nobs;
     float muhat, lconst;
+    const float *Ls, *LsT;          // L_Sigma (row-major) and its transpose: model tables (fit) or this chain's (training)
+    // training (train_model_globalRV): this chain's global parameters and where the per-SN
+    // contributions to their gradient go
+    const float *ad_g, *dad_g;      // dust basis a[b](RV) and da/dRV, [JROWS] each, global memory
+    float sigma0, tauA, muerr2;
+    float* part;                    // [LP*TP + 5]: dW, d/dsigma0, d/dRV, d/dtauA, log p (two floats of a double)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -344,27 +351,35 @@ __device__ __forceinline__ float vget(const float (&v)[VPL], int i) {
 // ------------------------------------------------------------------------------------------
 // log p and gradient for one (SN, chain): the unit of work of one leapfrog step
 // ------------------------------------------------------------------------------------------
-template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
+// TRAIN = false: fit_model_globalRV / popRV / uniformRV (reference :883-945, :996-1060, :818-881),
+//   q = [eps_tform, theta, log A_V, logit tmax, Ds - muhat, (RV transform)].
+// TRAIN = true: the per-SN part of train_model_globalRV (:1153-1182) for this chain's globals
+//   (W0, W1, L_Sigma, sigma0, R_V, tau_A), q = [eps_tform, theta, log A_V, Ds - muhat]; t_max is
+//   fixed at 0, the likelihood is Gaussian in magnitudes, and besides the latent gradient the
+//   un-reduced contributions to the global gradient are written to c.part.
+template <int LP, int TP, int VPL, bool RVFREE, bool STAGE, bool TRAIN = false>
 __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx& c, const float* __restrict__ hs,
                                                const float (&q)[VPL], double& logp_out, float (&grad)[VPL], int lane) {
     using DM = Dims<LP, TP>;
     constexpr int LP4 = DM::LP4, REC = DM::REC, NPAIR = DM::NPAIR, RS = DM::RS;
+    constexpr bool DRV = RVFREE || TRAIN;     // the derivative with respect to R_V is needed
+    static_assert(!(RVFREE && TRAIN), "training samples one global R_V");
     const int L = M.L, T = M.T, ne = M.n_eps;
 
     // ---- scalars ------------------------------------------------------------------------
     const float theta_s = vget<VPL>(q, ne + 0);
     const float uAV = vget<VPL>(q, ne + 1);
-    const float ut = vget<VPL>(q, ne + 2);
-    // element ne+3 is the SHIFTED distance dD = Ds - muhat: with Ds ~ 35 the float32 spacing
+    const float ut = TRAIN ? 0.f : vget<VPL>(q, ne + 2);
+    // the distance element is the SHIFTED distance dD = Ds - muhat: with Ds ~ 35 the float32 spacing
     // (3.8e-6) times the gradient far from the mode (1e6) is a potential-energy noise of order 1,
     // enough to stall step-size adaptation; around 0 the spacing is 30x finer.
-    const float dD = vget<VPL>(q, ne + 3);
+    const float dD = vget<VPL>(q, ne + (TRAIN ? 2 : 3));
     const float AV_s = expf(uAV);
     const float sg = 1.f / (1.f + expf(-ut));
     const float tmax_s = -10.f + 20.f * sg;
-    const float theta = M.fix_theta ? M.theta_val : theta_s;
-    const float AV = M.fix_AV ? M.AV_val : AV_s;
-    const float tmax = M.fix_tmax ? 0.f : tmax_s;
+    const float theta = (!TRAIN && M.fix_theta) ? M.theta_val : theta_s;
+    const float AV = (!TRAIN && M.fix_AV) ? M.AV_val : AV_s;
+    const float tmax = (TRAIN || M.fix_tmax) ? 0.f : tmax_s;
     float RVv = M.RV, dRV_du = 0.f, sgR = 0.f;
     if (RVFREE) {
         const float uR = vget<VPL>(q, ne + 4);
@@ -392,10 +407,10 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     __syncwarp();
     for (int i0 = 0; i0 < ne; i0 += 32) {
         const int i = i0 + lane;
-        const int jend = M.ls_lower ? min(ne, i0 + 32) : ne;      // eps_i = sum_{j <= i} L[i][j] e_j
+        const int jend = (TRAIN || M.ls_lower) ? min(ne, i0 + 32) : ne;      // eps_i = sum_{j <= i} L[i][j] e_j
         float acc = 0.f;
         if (i < ne) {
-            const float* col = M.LsT + i;
+            const float* col = c.LsT + i;
             for (int j = 0; j < jend; ++j) acc = fmaf(__ldg(col + j * ne), c.ev[j], acc);
             c.eps[i] = acc;
         }
@@ -410,7 +425,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         }
         c.Ws[p] = w;
     }
-    const float* adv = c.sAd;
+    const float* adv = TRAIN ? c.ad_g : c.sAd;
     if (RVFREE) {
         // per-chain dust basis a[b] = 1 + (M_fitz yk(RV))/RV and its RV derivative (reference :604-625)
         float yk[9], dyk[9];
@@ -525,7 +540,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         const float* pw = wtile + sp.z + hl;
         const float4* pj = reinterpret_cast<const float4*>(c.sJl) + b_first * (RS / 4);
         const float* pa = adv + b_first;
-        const float* pda = RVFREE ? (c.wdad + b_first) : nullptr;
+        const float* pda = RVFREE ? (c.wdad + b_first) : (TRAIN ? c.dad_g + b_first : nullptr);
         int rem = sp.y - b_first;                // this lane is inside the support while rem > 0
         float acc[16];
 #pragma unroll
@@ -539,7 +554,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
             }
             const float wl = STAGE ? *pw : __ldg(pw);
             const float h0 = __ldg(p0), h1 = __ldg(p0 + BP);
-            const float a = *pa;
+            const float a = TRAIN ? __ldg(pa) : *pa;
             // two independent FFMA chains (4-cycle dependent-issue latency)
             float g0 = 0.f, g1 = 0.f;
 #pragma unroll
@@ -555,7 +570,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
             acc[0] += P;
             acc[1] = fmaf(P, a, acc[1]);
             acc[2] = fmaf(we, dh, acc[2]);
-            if (RVFREE) { acc[3] = fmaf(P, *pda, acc[3]); pda += 16; }
+            if (DRV) { acc[3] = fmaf(P, TRAIN ? __ldg(pda) : *pda, acc[3]); pda += 16; }
 #pragma unroll
             for (int l = 0; l < LP; ++l) acc[4 + l] = fmaf(jl[l], P, acc[4 + l]);
             p0 += 16; pw += 16; pj += 16 * (RS / 4); pa += 16; rem -= 16;
@@ -566,15 +581,25 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         const float FT = __shfl_sync(FULL, val, hb | 2);
         const float Sv = c.sc[0];
         const float flux = Sv * F;
-        const float resid = yo - flux;
-        const float chi = resid * iso;
+        float chi, r;                      // r = d log L / d flux
+        if (TRAIN) {
+            // magnitude-space likelihood (get_mag_batch :711-759, :1178-1182): m = 27.5 - 2.5 log10 flux.
+            // The host folds 10^(0.4 (ybar_s - 27.5)) into the weights and stores y - ybar_s, so that
+            // both magnitudes are O(1) and their float32 difference keeps ~1e-7 mag (the gradient
+            // multiplies it by n_obs / sigma^2)
+            const float mg = -0.7525749891599529f * log2f(flux);
+            chi = (yo - mg) * iso;
+            r = chi * iso * (-1.0857362047581296f) / flux;
+        } else {
+            chi = (yo - flux) * iso;
+            r = chi * iso;
+        }
         logL += (double)(-0.5f * chi * chi);
-        const float r = chi * iso;
         const float coef = r * Sv;
         gDs = fmaf(-KAPPA * r, flux, gDs);
         gAV = fmaf(-KAPPA * coef, FA, gAV);
         gT = fmaf((pk & 256) ? coef : 0.f, FT, gT);
-        if (RVFREE) gRV = fmaf(-KAPPA * AV * coef, __shfl_sync(FULL, val, hb | 3), gRV);
+        if (DRV) gRV = fmaf(-KAPPA * AV * coef, __shfl_sync(FULL, val, hb | 3), gRV);
         // d logL / d(sum_m W[l][m] Jt[m]) for this observation, overwriting u (no longer needed),
         // and its product with (W J_t'(t))[l] for the gradient through the time spline
         const float dU = -KAPPA * coef * val;
@@ -590,7 +615,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     gDs += __shfl_xor_sync(FULL, gDs, 16);
     gAV += __shfl_xor_sync(FULL, gAV, 16);
     gT += __shfl_xor_sync(FULL, gT, 16);
-    if (RVFREE) gRV += __shfl_xor_sync(FULL, gRV, 16);
+    if (DRV) gRV += __shfl_xor_sync(FULL, gRV, 16);
     __syncwarp();
 
     gT += wsum(gTW);
@@ -629,8 +654,8 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         float gi = 0.f;
         if (i < ne) {
             float acc = 0.f;
-            const float* col = M.Ls + i;
-            for (int j = M.ls_lower ? 32 * s : 0; j < ne; ++j) acc = fmaf(__ldg(col + j * ne), c.ev[j], acc);
+            const float* col = c.Ls + i;
+            for (int j = (TRAIN || M.ls_lower) ? 32 * s : 0; j < ne; ++j) acc = fmaf(__ldg(col + j * ne), c.ev[j], acc);
             gi = acc - q[s];
             ss = fmaf(q[s], q[s], ss);
         }
@@ -640,6 +665,39 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     lp += -0.5f * ss;
     // theta ~ N(0,1)
     lp += -0.5f * theta_s * theta_s;
+    if (TRAIN) {
+        const float inv_tau = 1.f / c.tauA;
+        // A_V = exp(u) ~ Exponential(1/tauA) (+ log|J| = u); the -log tauA term depends on a sampled global
+        lp += -AV_s * inv_tau - logf(c.tauA) + uAV;
+        const float g_uAV = (gAV - inv_tau) * AV_s + 1.f;
+        // Ds ~ N(muhat, sqrt(muhat_err^2 + sigma0^2)) (:1174-1177)
+        const float isd2 = 1.f / (c.muerr2 + c.sigma0 * c.sigma0);
+        lp += -0.5f * dD * dD * isd2 + 0.5f * logf(isd2);
+        const float g_Ds = gDs - dD * isd2;
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < VPL; ++s) {
+            int i = lane + 32 * s;
+            if (i == ne + 0) grad[s] = gth - theta_s;
+            if (i == ne + 1) grad[s] = g_uAV;
+            if (i == ne + 2) grad[s] = g_Ds;
+        }
+        // un-reduced contributions to the gradient of the globals (constrained space)
+#pragma unroll
+        for (int s = 0; s < NPAIR; ++s) {
+            int p = lane + 32 * s;
+            if (p < LP * TP) c.part[p] = dW[s];
+        }
+        if (lane == 0) {
+            float* ps = c.part + LP * TP;
+            ps[0] = (dD * dD * isd2 - 1.f) * isd2 * c.sigma0;          // d/dsigma0
+            ps[1] = gRV;                                                 // d/dRV
+            ps[2] = (AV_s * inv_tau - 1.f) * inv_tau;                    // d/dtauA
+            *reinterpret_cast<double*>(ps + 3 + ((LP * TP + 3) & 1)) = lp;
+        }
+        logp_out = lp;
+        return;
+    }
     float g_theta = (M.fix_theta ? 0.f : gth) - theta_s;
     // A_V = exp(u): Exponential(1/tauA) prior + log|J| = u
     lp += -AV_s * M.inv_tauA + uAV;
@@ -746,6 +804,11 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
     c.nobs = Dd.n_valid[sn];
     c.muhat = Dd.muhat[sn];
     c.lconst = Dd.lconst[sn];
+    c.Ls = M.Ls;
+    c.LsT = M.LsT;
+    c.ad_g = c.dad_g = nullptr;
+    c.part = nullptr;
+    c.sigma0 = c.tauA = c.muerr2 = 0.f;
     return active;
 }
 

@@ -140,6 +140,18 @@ class SEDmodel(object):
     def param_dim(self, rv_mode=native.RV_FIXED):
         return self.n_eps + (4 if rv_mode == native.RV_FIXED else 5)
 
+    def prepare_training(self, obs, weights, band_inds=None):
+        """Upload a training set (``obs[1]``/``obs[2]`` in magnitudes, reference :2711-2730) and
+        return the native context for ``train_logp_grad`` (``train_model_globalRV``, :1115-1182)."""
+        if band_inds is None:
+            band_inds = np.arange(weights.shape[2])
+        ctx = self._context(native.RV_FIXED)
+        packed = packing.pack_dataset(obs, weights, self.zps[band_inds], self.offsets[band_inds], self.M0,
+                                      math.sqrt(25.0 + self.sigma0 ** 2), self.tauA, self.n_eps,
+                                      device=f'cuda:{ctx.device}', train=True, sigma_pec=self.sigma_pec)
+        ctx.bind_dataset(packed)
+        return ctx
+
     def prepare(self, obs, weights, band_inds=None, rv_mode=None, **fix):
         """Upload model + data set; returns the native context ready for ``logp_grad`` / ``nuts``.
         ``obs`` (10, N_obs, N) and ``weights`` (N, 300, n_b) use the reference layouts; the band

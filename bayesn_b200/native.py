@@ -30,7 +30,7 @@ class ModelDesc(C.Structure):
 class DatasetDesc(C.Structure):
     _fields_ = [('N', C.c_int32), ('N_obs', C.c_int32), ('n_b', C.c_int32), ('wt_stride', C.c_int32),
                 ('obs4', C.c_void_p), ('n_valid', C.c_void_p), ('weights', C.c_void_p), ('support', C.c_void_p),
-                ('muhat', C.c_void_p), ('lconst', C.c_void_p)]
+                ('muhat', C.c_void_p), ('lconst', C.c_void_p), ('muhat_err2', C.c_void_p)]
 
 
 class NutsCfg(C.Structure):
@@ -43,7 +43,8 @@ class NutsCfg(C.Structure):
 EXPORTS = ['bayesn_abi_version', 'bayesn_ctx_create', 'bayesn_ctx_destroy', 'bayesn_last_error',
            'bayesn_set_model', 'bayesn_bind_dataset', 'bayesn_param_dim', 'bayesn_logp_grad_fit',
            'bayesn_flux_batch', 'bayesn_nuts_workspace_bytes', 'bayesn_nuts_fit', 'bayesn_launch_count',
-           'bayesn_init_to_median', 'bayesn_ffma_peak']
+           'bayesn_init_to_median', 'bayesn_ffma_peak', 'bayesn_train_dims', 'bayesn_train_begin',
+           'bayesn_train_finish']
 
 _lib = None
 
@@ -76,6 +77,9 @@ def load_library():
     lib.bayesn_init_to_median.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.bayesn_ffma_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.bayesn_launch_count.restype = C.c_longlong
+    lib.bayesn_train_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
+    lib.bayesn_train_begin.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    lib.bayesn_train_finish.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
     _lib = lib
     return lib
 
@@ -152,6 +156,7 @@ class Context:
         d.wt_stride = int(packed['wt_stride'])
         for k in ('obs4', 'n_valid', 'weights', 'support', 'muhat', 'lconst'):
             setattr(d, k, packed[k].data_ptr())
+        d.muhat_err2 = packed['muhat_err2'].data_ptr() if packed.get('muhat_err2') is not None else None
         self._check(self.lib.bayesn_bind_dataset(self.h, C.byref(d)), 'bayesn_bind_dataset')
         self.N = d.N
 
@@ -213,6 +218,47 @@ class Context:
                                              out['stats'].data_ptr(), out['chain_info'].data_ptr(), ws.data_ptr(),
                                              ws.numel() * 4, self._stream()), 'bayesn_nuts_fit')
         return out
+
+    # ------------------------------------------------------------------ training
+    def train_dims(self):
+        """(G, Dl, R): unconstrained global / per-SN latent dimensions and the length of the
+        per-chain reduction buffer."""
+        G, Dl, R = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.bayesn_train_dims(self.h, C.byref(G), C.byref(Dl), C.byref(R)), 'bayesn_train_dims')
+        return G.value, Dl.value, R.value
+
+    def train_logp_grad(self, qg, ql, group=None, out=None):
+        """Log joint density of ``train_model_globalRV`` and its gradient.  ``qg`` (C, G) and ``ql``
+        (N, C, Dl) are float32 CUDA tensors.  With ``group`` (a torch.distributed process group whose
+        ranks hold disjoint SN shards and identical ``qg``) the per-SN sums are all-reduced between
+        the two native calls - the single exchange step of the training path.
+        Returns (logp (C,) float64, grad_g (C, G), grad_l (N, C, Dl))."""
+        import torch
+        assert qg.is_cuda and qg.dtype == torch.float32 and qg.is_contiguous()
+        assert ql.is_cuda and ql.dtype == torch.float32 and ql.is_contiguous()
+        Cn, G = qg.shape
+        N, C2, Dl = ql.shape
+        Gd, Dld, R = self.train_dims()
+        assert (G, Dl, C2, N) == (Gd, Dld, Cn, self.N), ((G, Dl, C2, N), (Gd, Dld, Cn, self.N))
+        out = {} if out is None else out
+        def buf(name, shape, dtype):
+            t = out.get(name)
+            if t is None or tuple(t.shape) != shape:
+                t = out[name] = torch.empty(shape, dtype=dtype, device=qg.device)
+            return t
+        red = buf('red', (Cn, R), torch.float64)
+        grad_l = buf('grad_l', (N, Cn, Dl), torch.float32)
+        grad_g = buf('grad_g', (Cn, G), torch.float32)
+        logp = buf('logp', (Cn,), torch.float64)
+        st = self._stream()
+        self._check(self.lib.bayesn_train_begin(self.h, Cn, qg.data_ptr(), ql.data_ptr(), grad_l.data_ptr(),
+                                                red.data_ptr(), st), 'bayesn_train_begin')
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(red, op=dist.ReduceOp.SUM, group=group)
+        self._check(self.lib.bayesn_train_finish(self.h, Cn, qg.data_ptr(), red.data_ptr(), logp.data_ptr(),
+                                                 grad_g.data_ptr(), st), 'bayesn_train_finish')
+        return logp, grad_g, grad_l
 
     def flux_batch(self, M0, theta, AV, W0, W1, eps, Ds, RV, band_indices, mask, J_t, hsiao_interp, weights,
                    band_log10_scale, mag=False):

@@ -13,7 +13,8 @@ def band_log10_scale(zps, offsets):
     return 0.4 * (27.5 - np.asarray(offsets, dtype=np.float64)) - np.asarray(zps, dtype=np.float64) / 2.5
 
 
-def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, device='cuda', chunk=8192):
+def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, device='cuda', chunk=8192, train=False,
+                 sigma_pec=150 / 3e5):
     """Returns a dict of torch tensors on ``device``.
 
     * valid (mask != 0) observations are moved to the front of each SN; ``n_valid`` counts them;
@@ -22,6 +23,10 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
     * ``support`` is the exact non-zero extent of each (SN, band) row and the offset of that row
       in the SN's compact weight tile (only bands the SN was observed in are stored);
     * ``lconst`` collects every parameter-independent term of the log joint density.
+
+    ``train=True`` packs a training set (``train_model_globalRV``, reference :1153-1182): ``obs[1]``
+    / ``obs[2]`` are magnitudes and their errors, the Ds prior width and tau_A are sampled (their
+    terms are evaluated on the device) and ``muhat_err2`` carries (5/(z ln10))^2 (z_err^2 + sigma_pec^2).
     """
     import torch
     obs = np.asarray(obs, dtype=np.float64)
@@ -36,6 +41,18 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
         raise ValueError('band index out of range of the weights array')
     bscale = band_log10_scale(zps, offsets)
     assert bscale.shape[0] == n_b
+    # the kernels carry the distance as Ds - float32(muhat): fold exactly that rounded muhat into the
+    # weights, otherwise every flux of the SN is off by the rounding (2e-6 mag, which the
+    # magnitude-space training gradient amplifies by n_obs / sigma^2)
+    muhat_f32 = muhat.astype(np.float32).astype(np.float64)
+    if train:
+        # magnitudes relative to the SN's mean magnitude (see eval_logp_grad, TRAIN branch)
+        nval = np.maximum(mask.sum(axis=1), 1)
+        ybar = (np.where(mask, y, 0.0).sum(axis=1) / nval).astype(np.float32).astype(np.float64)
+        y = y - ybar[:, None]
+        fold = muhat_f32 - (ybar - 27.5)
+    else:
+        fold = muhat_f32
     # exact non-zero extent of every (SN, band) weight row after rounding to float32; bands without
     # a valid observation of that SN (always the NULL band 0) get an empty row
     used = np.zeros((N, n_b), dtype=bool)
@@ -46,7 +63,7 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
     bins = np.arange(NBINS)[None, None, :]
     for s0 in range(0, N, chunk):
         w = np.asarray(weights[s0:s0 + chunk], dtype=np.float64)                  # (n, 300, n_b)
-        sc = 10.0 ** (bscale[None, :] - 0.4 * (M0 + muhat[s0:s0 + chunk, None]))   # (n, n_b)
+        sc = 10.0 ** (bscale[None, :] - 0.4 * (M0 + fold[s0:s0 + chunk, None]))   # (n, n_b)
         w32 = (np.transpose(w, (0, 2, 1)) * sc[:, :, None]).astype(np.float32)     # (n, n_b, 300)
         nz = (w32 != 0) & used[s0:s0 + chunk, :, None]
         any_nz = nz.any(axis=2)
@@ -91,8 +108,15 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
     obs4[..., 3] = np.where(mask, band, 0).astype(np.int32).view(np.float32)
     half_l2pi = 0.5 * math.log(2 * math.pi)
     lconst = np.sum(np.where(mask, -np.log(safe_sig) - half_l2pi, 0.0), axis=1)
-    lconst += -half_l2pi * (1 + n_eps) - math.log(tauA) - math.log(Ds_prior_sd) - half_l2pi
+    if train:
+        lconst += -half_l2pi * (2 + n_eps)
+        zs, zerr = obs[-5, 0, :], obs[-4, 0, :]
+        muhat_err2 = (5 / (zs * math.log(10))) ** 2 * (zerr ** 2 + sigma_pec ** 2)
+    else:
+        lconst += -half_l2pi * (1 + n_eps) - math.log(tauA) - math.log(Ds_prior_sd) - half_l2pi
+        muhat_err2 = None
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
     return dict(N=N, N_obs=N_obs, n_b=n_b, wt_stride=wt_stride, obs4=to(obs4), n_valid=to(n_valid), weights=wt, support=to(sup_h),
                 muhat=to(muhat.astype(np.float32)), lconst=to(lconst.astype(np.float32)),
-                muhat64=muhat, order=order, _weights_storage=wt_store)
+                muhat64=muhat, order=order, _weights_storage=wt_store,
+                muhat_err2=None if muhat_err2 is None else to(muhat_err2.astype(np.float32)))

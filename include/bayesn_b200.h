@@ -34,6 +34,7 @@ extern "C" {
 #define BAYESN_NPHASE 105     /* Hsiao phase grid -19..85, bayesn/bayesn_model.py:274 */
 #define BAYESN_MAX_L 12
 #define BAYESN_MAX_T 10
+#define BAYESN_MAX_NEPS ((BAYESN_MAX_L - 2) * BAYESN_MAX_T)
 
 typedef struct bayesn_ctx bayesn_ctx;
 
@@ -76,7 +77,9 @@ typedef struct {
  *                  must extend BAYESN_OVERRUN floats past the last tile (read, never used)
  *   support[s][k] = {first, one-past-last, offset, 0}: exact non-zero extent of the band weight
  *                  (threshold-free: exact zeros only) and where its row starts inside the tile
- *   muhat[s]     = fiducial distance modulus;  lconst[s] = data-only log-density constant */
+ *   muhat[s]     = fiducial distance modulus;  lconst[s] = data-only log-density constant
+ *   muhat_err2[s] = (5 / (z ln 10))^2 (z_err^2 + sigma_pec^2), training only (NULL for fits;
+ *                  bayesn/bayesn_model.py:1174-1175); training data carry magnitudes in obs4.y */
 typedef struct {
     int32_t N, N_obs, n_b, wt_stride;
     const float* obs4;
@@ -85,6 +88,7 @@ typedef struct {
     const int32_t* support;
     const float* muhat;
     const float* lconst;
+    const float* muhat_err2;
 } bayesn_dataset_desc;
 
 /* NUTS configuration: numpyro.infer.NUTS / MCMC arguments at the reference call sites
@@ -141,6 +145,24 @@ int bayesn_flux_batch(bayesn_ctx* ctx, int N, int N_obs, int n_b, int mag, float
 size_t bayesn_nuts_workspace_bytes(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg);
 int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_init, float* samples, float* stats,
                     float* chain_info, void* work, size_t work_bytes, void* stream);
+
+/* Population training: log joint density of train_model_globalRV (bayesn/bayesn_model.py:1115-1182)
+ * in the unconstrained space and its gradient, for n_chains independent parameter vectors.
+ *   qg [C][G]      globals: [W0 vec_F (L T), W1 vec_F (L T), u_sigmaepsilon (n_eps), y_L_Omega
+ *                  (n_eps (n_eps-1)/2, strict lower triangle row-major), u_sigma0, u_RV, u_tauA];
+ *                  interval sites through the affine-sigmoid bijection, L_Omega through numpyro's
+ *                  CorrCholeskyTransform, density LKJCholesky(eta = 1) without its constant
+ *   ql [N][C][Dl]  per-SN latents [eps_tform (n_eps), theta, log A_V, Ds], Dl = n_eps + 3
+ * bayesn_train_begin evaluates this rank's SNe: grad_l [N][C][Dl] is final, red [C][R] (double,
+ * device) holds the SUMS over this rank's SNe that the globals need ([log p, d/dsigma0, d/dRV,
+ * d/dtauA, dW0, dW1, dL_Sigma]).  When SNe are sharded over GPUs the caller all-reduces (sum)
+ * `red` between the two calls - the one exchange step of the training path.  bayesn_train_finish
+ * adds the global priors / Jacobians: logp [C] (double), grad_g [C][G]. */
+int bayesn_train_dims(bayesn_ctx* ctx, int* G, int* Dl, int* R);
+int bayesn_train_begin(bayesn_ctx* ctx, int n_chains, const float* qg, const float* ql, float* grad_l, double* red,
+                       void* stream);
+int bayesn_train_finish(bayesn_ctx* ctx, int n_chains, const float* qg, const double* red, double* logp,
+                        float* grad_g, void* stream);
 
 /* numpyro init_to_median(num_samples=15) (reference bayesn/bayesn_model.py:1757, :2110): initial
  * unconstrained positions q [N][n_chains][D] (device, out) for the bound data set. */

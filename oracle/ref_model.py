@@ -548,6 +548,86 @@ class RefSED:
         lp = lp + torch.sum(torch.where(mask, ll, torch.zeros_like(ll)))
         return lp
 
+    # ---- unconstrained joint density of train_model_globalRV (:1115-1182) ---------------------
+    def train_dims(self):
+        L, T = len(self.l_knots), len(self.tau_knots)
+        ne = (L - 2) * T
+        return dict(L=L, T=T, n_eps=ne, n_corr=ne * (ne - 1) // 2, G=2 * L * T + ne + ne * (ne - 1) // 2 + 3,
+                    Dl=ne + 3)
+
+    @staticmethod
+    def corr_cholesky(y, n):
+        """numpyro ``CorrCholeskyTransform`` (upstream numpyro/distributions/transforms.py, not in
+        the reference tree; restated from its published algorithm): unconstrained vector ``y`` of
+        length n(n-1)/2 -> Cholesky factor of a correlation matrix by tanh + signed stick breaking
+        (strict lower triangle filled row-major), and the log|det J| numpyro adds for it."""
+        t = torch.tanh(y)
+        r = torch.zeros((n, n), dtype=y.dtype)
+        ii, jj = torch.tril_indices(n, n, -1)
+        r = r.index_put((ii, jj), t)
+        z = r * r
+        z1m_cumprod = torch.cumprod(1 - z, dim=-1)
+        shifted = torch.cat([torch.ones((n, 1), dtype=y.dtype), torch.sqrt(z1m_cumprod)[:, :-1]], dim=1)
+        Lo = (r + torch.eye(n, dtype=y.dtype)) * shifted
+        ii2, jj2 = torch.tril_indices(n, n, -2)
+        stick = 0.5 * torch.sum(torch.log(z1m_cumprod[ii2, jj2]))
+        tanh_ld = -2 * torch.sum(y + torch.nn.functional.softplus(-2 * y) - math.log(2.0))
+        return Lo, stick + tanh_ld
+
+    def train_unpack(self, qg):
+        """Unconstrained global vector -> constrained globals and the log prior + log|det J| of the
+        global sites.  Layout of ``qg``: [W0 vec_F (L T), W1 vec_F (L T), u_sigmaepsilon (n_eps),
+        y_L_Omega (n_eps (n_eps-1)/2), u_sigma0, u_RV, u_tauA]; interval supports use numpyro's
+        ``biject_to`` (affine sigmoid).  The LKJ normalising constant is omitted (parameter free)."""
+        d = self.train_dims()
+        L, T, ne, nc = d['L'], d['T'], d['n_eps'], d['n_corr']
+        o = 0
+        W0v = qg[o:o + L * T]; o += L * T
+        W1v = qg[o:o + L * T]; o += L * T
+        u_se = qg[o:o + ne]; o += ne
+        y = qg[o:o + nc]; o += nc
+        u_s0, u_rv, u_ta = qg[o], qg[o + 1], qg[o + 2]
+        lsig = torch.nn.functional.logsigmoid
+        lp = torch.sum(-0.5 * W0v ** 2) + torch.sum(-0.5 * W1v ** 2) - L * T * math.log(2 * math.pi)
+        W0 = W0v.reshape(T, L).T                     # order='F'
+        W1 = W1v.reshape(T, L).T
+        half_pi = math.pi / 2
+        se = torch.tan(half_pi * torch.sigmoid(u_se))                  # U(0, pi/2) then tan (:1137-1139)
+        lp = lp + torch.sum(lsig(u_se) + lsig(-u_se))                   # -log(pi/2) + log|J|
+        Lo, ld = self.corr_cholesky(y, ne)
+        k = torch.arange(1, ne, dtype=qg.dtype)
+        lp = lp + torch.sum((ne - 1 - k) * torch.log(torch.diagonal(Lo)[1:])) + ld     # LKJCholesky(eta = 1)
+        L_Sigma = se[:, None] * Lo                                      # diag(sigma) L_Omega (:1141)
+        sigma0 = 0.1 * torch.tan(half_pi * torch.sigmoid(u_s0))
+        lp = lp + lsig(u_s0) + lsig(-u_s0)
+        RV = 1 + 4 * torch.sigmoid(u_rv)                                # U(1, 5) (:1147)
+        lp = lp + lsig(u_rv) + lsig(-u_rv)
+        tauA = torch.tan(half_pi * torch.sigmoid(u_ta))
+        lp = lp + lsig(u_ta) + lsig(-u_ta)
+        return dict(W0=W0, W1=W1, sigmaepsilon=se, L_Omega=Lo, L_Sigma=L_Sigma, sigma0=sigma0, RV=RV, tauA=tauA), lp
+
+    def train_logp(self, qg, ql, obs, weights):
+        """Unconstrained log joint density of ``train_model_globalRV``.  ``qg`` (G,) as in
+        :meth:`train_unpack`; ``ql`` (N, n_eps + 3) per SN ``[eps_tform..., theta, log AV, Ds]``.
+        J_t and the Hsiao interpolation are fixed at the data phases (``self.J_t`` :2725)."""
+        obs = torch.as_tensor(obs)
+        ne = self.train_dims()['n_eps']
+        g, lp = self.train_unpack(qg)
+        eps_tform, theta, u_AV, Ds = ql[:, :ne], ql[:, ne], ql[:, ne + 1], ql[:, ne + 2]
+        AV = torch.exp(u_AV)
+        J_t, hsiao_interp = self.J_t_and_hsiao(obs[0])
+        lp = lp + torch.sum(u_AV)                                        # log|J| of AV = exp(u)
+        lp = lp + self.train_loglik_terms(g['W0'], g['W1'], g['L_Sigma'], g['sigma0'], g['RV'], g['tauA'], theta, AV,
+                                          eps_tform, Ds, obs, weights, J_t, hsiao_interp)
+        return lp
+
+    def train_logp_grad(self, qg, ql, obs, weights):
+        qg = torch.as_tensor(qg, dtype=torch.float64).clone().requires_grad_(True)
+        ql = torch.as_tensor(ql, dtype=torch.float64).clone().requires_grad_(True)
+        lp = self.train_logp(qg, ql, obs, weights)
+        gg, gl = torch.autograd.grad(lp, (qg, ql))
+        return float(lp.detach()), gg.numpy(), gl.numpy()
+
     # ------------------------------------------------------------ simulate_light_curve :3103-3345
     def sample_epsilon(self, N):
         n_sig = (len(self.l_knots) - 2) * len(self.tau_knots)

@@ -1,0 +1,107 @@
+"""GPU parity of the population-training path (train_model_globalRV, reference
+bayesn/bayesn_model.py:1115-1182): log joint density and gradient of the CUDA kernels, called
+through the C ABI, against the float64 oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): log p relative 1e-5, gradient 1e-4 norm-wise."""
+import numpy as np
+import pytest
+import torch
+
+from tests.common import make_case, product_model
+
+pytestmark = pytest.mark.gpu
+LOGP_TOL, GRAD_TOL = 1e-5, 1e-4
+CSP = ['B_CSP', 'V_CSP', 'r_CSP', 'i_CSP', 'Y_RC', 'J_RC1', 'H_RC']
+PS1 = ['g_PS1', 'r_PS1', 'i_PS1', 'z_PS1']
+
+
+def training_point(ref, case, C, seed, spread=1.0):
+    """Unconstrained points around the trained model: globals (C, G) and latents (N, C, Dl)."""
+    d = ref.train_dims()
+    L, T, ne, nc = d['L'], d['T'], d['n_eps'], d['n_corr']
+    N = case['obs'].shape[2]
+    rng = np.random.RandomState(seed)
+    qg = np.zeros((C, d['G']))
+    qg[:, :L * T] = ref.W0.flatten(order='F')[None] + 0.02 * spread * rng.randn(C, L * T)
+    qg[:, L * T:2 * L * T] = ref.W1.flatten(order='F')[None] + 0.02 * spread * rng.randn(C, L * T)
+    se = 0.1 + 0.02 * rng.rand(C, ne)
+    x = np.arctan(se) / (np.pi / 2)
+    qg[:, 2 * L * T:2 * L * T + ne] = np.log(x) - np.log1p(-x)
+    qg[:, 2 * L * T + ne:2 * L * T + ne + nc] = 0.15 * spread * rng.randn(C, nc)
+    qg[:, -3] = 0.1 * rng.randn(C)
+    qg[:, -2] = 0.3 * rng.randn(C)
+    qg[:, -1] = -1.5 + 0.2 * rng.randn(C)
+    ql = np.zeros((N, C, d['Dl']))
+    ql[..., :ne] = 0.7 * rng.randn(N, C, ne)
+    ql[..., ne] = case['params']['theta'][:, None] + 0.2 * rng.randn(N, C)
+    ql[..., ne + 1] = np.log(case['params']['AV'][:, None] + 0.05) + 0.1 * rng.randn(N, C)
+    ql[..., ne + 2] = (case['params']['mu'] + case['params']['del_M'])[:, None] + 0.03 * rng.randn(N, C)
+    return qg, ql
+
+
+def run_case(model, bands, t, N, C, seed, mask_some=True):
+    case = make_case(model, bands, t, N=N, seed=seed, mag=True, mask_some=mask_some, yerr=0.05)
+    ref = case['ref']
+    m, bi = product_model(case)
+    ctx = m.prepare_training(case['obs'], m._calculate_band_weights(case['z'], case['ebv'], bi), bi)
+    qg, ql = training_point(ref, case, C, seed)
+    qg32 = torch.tensor(qg, dtype=torch.float32, device='cuda').contiguous()
+    ql32 = torch.tensor(ql, dtype=torch.float32, device='cuda').contiguous()
+    lp, gg, gl = ctx.train_logp_grad(qg32, ql32)
+    torch.cuda.synchronize()
+    lp, gg, gl = lp.cpu().numpy(), gg.cpu().numpy().astype(np.float64), gl.cpu().numpy().astype(np.float64)
+    qgk, qlk = qg32.cpu().numpy().astype(np.float64), ql32.cpu().numpy().astype(np.float64)
+    out = []
+    for c in range(C):
+        lpo, ggo, glo = ref.train_logp_grad(qgk[c], qlk[:, c], case['obs'], case['weights'])
+        assert np.isfinite(lpo)
+        e_lp = abs(lp[c] - lpo) / abs(lpo)
+        e_gg = np.max(np.abs(gg[c] - ggo)) / np.max(np.abs(ggo))
+        e_gl = np.max(np.max(np.abs(gl[:, c] - glo), axis=1) / np.max(np.abs(glo), axis=1))
+        # the blocks of the global gradient separately: they differ by orders of magnitude
+        d = ref.train_dims()
+        LT, ne = d['L'] * d['T'], d['n_eps']
+        blocks = {'W0': slice(0, LT), 'W1': slice(LT, 2 * LT), 'sigeps': slice(2 * LT, 2 * LT + ne),
+                  'L_Omega': slice(2 * LT + ne, d['G'] - 3), 'scalars': slice(d['G'] - 3, d['G'])}
+        eb = {k: float(np.max(np.abs(gg[c][sl] - ggo[sl])) / max(np.max(np.abs(ggo[sl])), 1e-30)) for k, sl in blocks.items()}
+        out.append((e_lp, e_gg, e_gl, eb))
+    return out
+
+
+@pytest.mark.parametrize('name,model,bands,t,N,C', [
+    ('C4_M20_csp', 'M20_model', CSP, np.arange(-8, 40, 4.0), 12, 2),
+    ('T21_griz_1chain', 'T21_model', PS1, np.arange(-8, 40, 4.0), 9, 1),
+    ('W22_4chains', 'W22_model', ['g_PS1', 'r_PS1', 'i_PS1', 'z_PS1', 'Y_WFCAM', 'J_WFCAM', 'H_WFCAM'],
+     np.array([-8.0, 2.0, 12.0, 22.0, 32.0]), 7, 4),
+])
+def test_train_logp_grad_parity(name, model, bands, t, N, C):
+    for e_lp, e_gg, e_gl, eb in run_case(model, bands, t, N, C, seed=len(name)):
+        assert e_lp < LOGP_TOL, (name, e_lp)
+        assert e_gl < GRAD_TOL, (name, e_gl)
+        assert e_gg < GRAD_TOL, (name, e_gg, eb)
+        for k, v in eb.items():
+            assert v < 5e-4, (name, k, v)
+
+
+def test_train_reduction_is_additive_over_sn_shards():
+    """The per-SN sums of two disjoint shards add up to the sums of the whole set (the property the
+    multi-GPU all-reduce relies on)."""
+    case = make_case('T21_model', PS1, np.arange(-8, 40, 4.0), N=8, seed=3, mag=True, mask_some=True)
+    ref = case['ref']
+    m, bi = product_model(case)
+    w = m._calculate_band_weights(case['z'], case['ebv'], bi)
+    qg, ql = training_point(ref, case, 2, 5)
+    qg32 = torch.tensor(qg, dtype=torch.float32, device='cuda').contiguous()
+    full = m.prepare_training(case['obs'], w, bi)
+    bufs = {}
+    lp, gg, gl = full.train_logp_grad(qg32, torch.tensor(ql, dtype=torch.float32, device='cuda').contiguous(), out=bufs)
+    red_full = bufs['red'].clone()
+    reds = []
+    for sl in (slice(0, 3), slice(3, 8)):
+        ctx = m.prepare_training(case['obs'][:, :, sl], w[sl], bi)
+        b = {}
+        ctx.train_logp_grad(qg32, torch.tensor(ql[sl], dtype=torch.float32, device='cuda').contiguous(), out=b)
+        reds.append(b['red'].clone())
+    torch.cuda.synchronize()
+    tot = reds[0] + reds[1]
+    assert torch.allclose(tot, red_full, rtol=1e-9, atol=1e-9 * float(red_full.abs().max()))
