@@ -1,5 +1,6 @@
 // bayesn_capi.cu - extern "C" boundary of libbayesn_b200.so (see include/bayesn_b200.h).
 #include <algorithm>
+#include <type_traits>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -7,6 +8,7 @@
 
 #include "bayesn_kernels.cuh"
 #include "bayesn_train.cuh"
+#include "bayesn_train_nuts.cuh"
 
 using namespace bayesn;
 
@@ -22,6 +24,9 @@ struct bayesn_ctx {
     TrainDev T{};               // training buffers (allocated on first use for a given (chains, N))
     std::vector<void*> train_owned;
     int train_C = 0, train_N = 0;
+    TrainNutsDev TN{};          // training sampler state
+    std::vector<void*> tn_owned;
+    bool have_tn = false;
 };
 
 namespace {
@@ -52,6 +57,9 @@ void free_train(bayesn_ctx* ctx) {
     for (void* p : ctx->train_owned) cudaFree(p);
     ctx->train_owned.clear();
     ctx->train_C = ctx->train_N = 0;
+    for (void* p : ctx->tn_owned) cudaFree(p);
+    ctx->tn_owned.clear();
+    ctx->have_tn = false;
 }
 
 void free_owned(bayesn_ctx* ctx) {
@@ -184,6 +192,32 @@ struct TrainSnCall {
     bayesn_ctx* ctx; const float* ql; float* grad_l; cudaStream_t st;
     template <int LP, int TP, int VPL, bool RV, bool ST>
     int operator()() { return launch_train_sn<LP, TP, VPL, RV, ST>(ctx, ql, grad_l, st); }
+};
+
+template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
+int launch_train_nuts_sn(bayesn_ctx* ctx, cudaStream_t st) {
+    if (RVFREE) return fail(ctx, -1, "training needs a fixed-RV model context (rv_mode = BAYESN_RV_FIXED)");
+    const int C = ctx->T.C;
+    const int ntile = ntile_for(C);
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, false, STAGE);
+    const size_t bytes = (size_t)P.totalFloats * 4;
+    constexpr int TVPL = (LP * TP - 2 * TP + 3 + 31) / 32;
+    auto kern = train_nuts_sn_kernel<LP, TP, TVPL, STAGE>;
+    if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
+    if (ctx->TN.VPL != TVPL) return fail(ctx, -1, "internal: latent vector width mismatch");
+    CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    const long long units = (long long)ctx->D.N * C;
+    const unsigned grid = (unsigned)((units + WPB - 1) / WPB);
+    kern<<<grid, WPB * 32, bytes, st>>>(ctx->M, ctx->D, ctx->T, ctx->TN, ntile);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+struct TrainNutsSnCall {
+    bayesn_ctx* ctx; cudaStream_t st;
+    template <int LP, int TP, int VPL, bool RV, bool ST>
+    int operator()() { return launch_train_nuts_sn<LP, TP, VPL, RV, ST>(ctx, st); }
 };
 
 struct LogpCall {
@@ -470,7 +504,8 @@ int bayesn_train_begin(bayesn_ctx* ctx, int n_chains, const float* qg, const flo
     TrainSnCall call{ctx, ql, grad_l, st};
     if (int rc = dispatch(ctx, /*stage=*/n_chains >= 2, call)) return rc;
     dim3 grid((ctx->T.R + 255) / 256, n_chains);
-    train_reduce_kernel<<<grid, 256, 0, st>>>(ctx->M, ctx->T, ctx->D.N, ctx->LP, ctx->TP, ql, red);
+    train_reduce_kernel<<<grid, 256, 0, st>>>(ctx->M, ctx->T, ctx->D.N, ctx->LP, ctx->TP, ql, (size_t)ctx->T.Dl,
+                                              (size_t)n_chains * ctx->T.Dl, red);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -486,6 +521,101 @@ int bayesn_train_finish(bayesn_ctx* ctx, int n_chains, const float* qg, const do
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
+}
+
+
+int bayesn_train_nuts_init(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, int sn_offset, const float* qg0,
+                           const float* ql0, float* samples_g, float* samples_l, float* stats, void* stream) {
+    if (!ctx || !cfg) return -1;
+    if (!ctx->have_model || !ctx->have_data) return fail(ctx, -1, "set_model and bind_dataset first");
+    if (ctx->M.rv_mode != BAYESN_RV_FIXED) return fail(ctx, -1, "training needs rv_mode = BAYESN_RV_FIXED");
+    if (!ctx->D.muerr2) return fail(ctx, -1, "training data set needs muhat_err2");
+    if (cfg->num_chains < 1 || cfg->num_samples < 1 || cfg->num_warmup < 0 || cfg->max_tree_depth < 1 ||
+        cfg->max_tree_depth > 12)
+        return fail(ctx, -1, "bad NUTS configuration");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    const int C = cfg->num_chains;
+    if (int rc = train_prepare(ctx, C)) return rc;
+    for (void* p : ctx->tn_owned) cudaFree(p);
+    ctx->tn_owned.clear();
+    ctx->have_tn = false;
+    TrainNutsDev& TN = ctx->TN;
+    TN = TrainNutsDev{};
+    NutsDev& nd = TN.cfg;
+    nd.num_warmup = cfg->num_warmup; nd.num_samples = cfg->num_samples; nd.num_chains = C;
+    nd.max_depth = cfg->max_tree_depth; nd.target_accept = cfg->target_accept; nd.init_step = cfg->init_step_size;
+    nd.adapt_step = cfg->adapt_step_size; nd.adapt_mass = cfg->adapt_mass_matrix;
+    nd.regularize = cfg->regularize_mass_matrix;
+    nd.seed_lo = (unsigned)(cfg->seed & 0xffffffffu); nd.seed_hi = (unsigned)(cfg->seed >> 32);
+    std::vector<int> ends = adaptation_window_ends(cfg->num_warmup);
+    if (ends.size() > 24) return fail(ctx, -1, "too many adaptation windows");
+    nd.n_windows = (int)ends.size();
+    for (size_t i = 0; i < 24; ++i) nd.win_end[i] = i < ends.size() ? ends[i] : 0x7fffffff;
+    TN.VPL = (ctx->LP * ctx->TP - 2 * ctx->TP + 3 + 31) / 32;
+    TN.sn_offset = sn_offset;
+    TN.samples_g = samples_g; TN.samples_l = samples_l; TN.stats = stats;
+    const int nvec = train_nuts_num_vectors(nd.max_depth);
+    auto alloc = [&](auto** out, size_t n) -> int {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, n * sizeof(**out));
+        if (e != cudaSuccess) return fail(ctx, -2, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        ctx->tn_owned.push_back(d);
+        *out = static_cast<std::remove_reference_t<decltype(**out)>*>(d);
+        return 0;
+    };
+    int rc = 0;
+    rc |= alloc(&TN.ctl, (size_t)C);
+    rc |= alloc(&TN.work_l, (size_t)ctx->D.N * C * nvec * 32 * TN.VPL);
+    rc |= alloc(&TN.work_g, (size_t)C * nvec * ctx->T.G);
+    rc |= alloc(&TN.gtmp, (size_t)C * ctx->T.G);
+    if (rc) return rc;
+    train_nuts_init_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(ctx->M, ctx->T, TN, ctx->D, ctx->LP, ctx->TP, qg0, ql0);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    ctx->have_tn = true;
+    return 0;
+}
+
+int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream) {
+    if (!ctx) return -1;
+    if (!ctx->have_tn) return fail(ctx, -1, "bayesn_train_nuts_init first");
+    cudaStream_t st = (cudaStream_t)stream;
+    TrainNutsSnCall call{ctx, st};
+    if (int rc = dispatch(ctx, /*stage=*/ctx->T.C >= 2, call)) return rc;
+    dim3 grid((ctx->T.R + 255) / 256, ctx->T.C);
+    // the reduction needs theta_s and eps_tform_s of the point just evaluated: the current positions
+    const size_t vec = (size_t)32 * ctx->TN.VPL, nvec = train_nuts_num_vectors(ctx->TN.cfg.max_depth);
+    train_reduce_kernel<<<grid, 256, 0, st>>>(ctx->M, ctx->T, ctx->D.N, ctx->LP, ctx->TP, ctx->TN.work_l + TV_CZ * vec,
+                                              nvec * vec, (size_t)ctx->T.C * nvec * vec, red);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+int bayesn_train_nuts_ctl(bayesn_ctx* ctx, const double* red, void* stream) {
+    if (!ctx) return -1;
+    if (!ctx->have_tn) return fail(ctx, -1, "bayesn_train_nuts_init first");
+    train_nuts_ctl_kernel<<<ctx->T.C, 128, 0, (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->TN, ctx->LP, ctx->TP, red);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+int bayesn_train_nuts_status(bayesn_ctx* ctx, float* out, void* stream) {
+    if (!ctx || !out) return -1;
+    if (!ctx->have_tn) return fail(ctx, -1, "bayesn_train_nuts_init first");
+    const int C = ctx->T.C;
+    std::vector<TrainCtl> h(C);
+    CU_CHECK(ctx, cudaMemcpyAsync(h.data(), ctx->TN.ctl, C * sizeof(TrainCtl), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU_CHECK(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    int done = 0;
+    for (int c = 0; c < C; ++c) {
+        float* o = out + (size_t)c * 8;
+        o[0] = (float)h[c].phase; o[1] = (float)h[c].it; o[2] = h[c].step; o[3] = h[c].mean_acc;
+        o[4] = (float)h[c].total_steps; o[5] = (float)h[c].n_div; o[6] = (float)h[c].pe; o[7] = (float)h[c].depth;
+        done += h[c].phase == 2;
+    }
+    return done == C ? 1 : 0;
 }
 
 }  // extern "C"

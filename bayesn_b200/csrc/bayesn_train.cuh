@@ -34,8 +34,14 @@ struct TrainDev {
     float* part;    // [N][C][PR] per-SN contributions
 };
 
-__host__ __device__ inline int train_part_stride(int LPTP) { return LPTP + 3 + ((LPTP + 3) & 1) + 2; }
-__host__ __device__ inline int train_red_len(int LPTP, int ne) { return 4 + 2 * LPTP + ne * ne; }
+// Per-SN rows and the reduced buffer end with TRAIN_NX sampler partial sums (used by the NUTS
+// kernels below, zero otherwise): [kinetic energy, kinetic energy of a fresh momentum draw,
+// (left, right) U-turn dot products for up to 12 checkpoints, (left, right) for the whole tree].
+constexpr int TRAIN_NX = 2 + 2 * 12 + 2;
+__host__ __device__ inline int train_part_base(int LPTP) { return LPTP + 3 + ((LPTP + 3) & 1) + 2; }
+__host__ __device__ inline int train_part_stride(int LPTP) { return train_part_base(LPTP) + TRAIN_NX; }
+__host__ __device__ inline int train_red_base(int LPTP, int ne) { return 4 + 2 * LPTP + ne * ne; }
+__host__ __device__ inline int train_red_len(int LPTP, int ne) { return train_red_base(LPTP, ne) + TRAIN_NX; }
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -59,14 +65,20 @@ __device__ __forceinline__ double log_sigmoid_pair(double u) {   // log s(u) + l
 //      affine-sigmoid bijection, L_Omega numpyro's CorrCholeskyTransform (tanh + signed stick
 //      breaking) with the LKJCholesky(eta = 1) density (upstream numpyro; restated in oracle/).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) train_globals_kernel(ModelDev M, TrainDev Tr, int LP, int TP,
-                                                            const float* __restrict__ qg_all) {
-    __shared__ double sh[8];
-    __shared__ float s_sig[BAYESN_MAX_NEPS];
-    __shared__ float s_yk[9], s_dyk[9];
-    const int c = blockIdx.x, tid = threadIdx.x;
+struct TrainShared {
+    double sh[8];
+    float sig[BAYESN_MAX_NEPS];
+    float yk[9], dyk[9];
+};
+
+__device__ __forceinline__ void train_globals_dev(const ModelDev& M, const TrainDev& Tr, int LP, int TP, int c,
+                                                  const float* __restrict__ qg, TrainShared& S) {
+    double* sh = S.sh;
+    float* s_sig = S.sig;
+    float* s_yk = S.yk;
+    float* s_dyk = S.dyk;
+    const int tid = threadIdx.x;
     const int L = M.L, T = M.T, ne = M.n_eps;
-    const float* qg = qg_all + (size_t)c * Tr.G;
     const int oW1 = L * T, oSe = 2 * L * T, oY = oSe + ne, oSc = oY + Tr.n_corr;
     double lp = 0.0;
     const double HALF_PI = 1.5707963267948966;
@@ -176,6 +188,12 @@ __global__ void __launch_bounds__(128) train_globals_kernel(ModelDev M, TrainDev
     if (tid == 0) Tr.lpg[c] = tot;
 }
 
+__global__ void __launch_bounds__(128) train_globals_kernel(ModelDev M, TrainDev Tr, int LP, int TP,
+                                                            const float* __restrict__ qg_all) {
+    __shared__ TrainShared S;
+    train_globals_dev(M, Tr, LP, TP, blockIdx.x, qg_all + (size_t)blockIdx.x * Tr.G, S);
+}
+
 // ------------------------------------------------------------------------------------------
 // (T2) per-SN part: the fit evaluator in TRAIN mode
 // ------------------------------------------------------------------------------------------
@@ -222,11 +240,14 @@ __global__ void __launch_bounds__(WPB * 32) train_sn_kernel(ModelDev M, DataDev 
 // (T3) reduction over the SNe of this rank.  red[c] = [log p, d/dsigma0, d/dRV, d/dtauA,
 //      dW0 (padded [LP][TP]), dW1, dL_Sigma (row-major, lower triangle)], all double.
 // ------------------------------------------------------------------------------------------
+//      The latents (theta_s, eps_tform_s) of SN s / chain c are read at lat + c * chain_stride +
+//      s * sn_stride (the caller's ql array, or the sampler's current-position vectors).
 __global__ void __launch_bounds__(256) train_reduce_kernel(ModelDev M, TrainDev Tr, int N, int LP, int TP,
-                                                           const float* __restrict__ ql, double* __restrict__ red) {
+                                                           const float* __restrict__ lat, size_t chain_stride,
+                                                           size_t sn_stride, double* __restrict__ red) {
     const int c = blockIdx.y;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ne = M.n_eps, L = M.L, C = Tr.C, PR = Tr.PR, LPTP = Tr.LPTP, Dl = Tr.Dl;
+    const int ne = M.n_eps, L = M.L, C = Tr.C, PR = Tr.PR, LPTP = Tr.LPTP;
     if (r >= Tr.R) return;
     const size_t stride = (size_t)C * PR;
     const float* base = Tr.part + (size_t)c * PR;
@@ -241,8 +262,11 @@ __global__ void __launch_bounds__(256) train_reduce_kernel(ModelDev M, TrainDev 
         for (int s = 0; s < N; ++s) acc += base[s * stride + p];
     } else if (r < 4 + 2 * LPTP) {
         const int p = r - 4 - LPTP;
-        const float* th = ql + (size_t)c * Dl + ne;                  // theta_s
-        for (int s = 0; s < N; ++s) acc += (double)base[s * stride + p] * th[(size_t)s * C * Dl];
+        const float* th = lat + (size_t)c * chain_stride + ne;       // theta_s
+        for (int s = 0; s < N; ++s) acc += (double)base[s * stride + p] * th[(size_t)s * sn_stride];
+    } else if (r >= train_red_base(LPTP, ne)) {
+        const int x = train_part_base(LPTP) + (r - train_red_base(LPTP, ne));
+        for (int s = 0; s < N; ++s) acc += base[s * stride + x];
     } else {
         const int e = r - 4 - 2 * LPTP;
         const int i = e / ne, j = e - i * ne;
@@ -250,8 +274,8 @@ __global__ void __launch_bounds__(256) train_reduce_kernel(ModelDev M, TrainDev 
             // vec_F index i = (l-1) + (L-2) m  ->  position of dW[l][m] in the padded layout
             const int m = i / (L - 2), l = 1 + (i - m * (L - 2));
             const int p = l * TP + m;
-            const float* ev = ql + (size_t)c * Dl + j;               // eps_tform_s[j]
-            for (int s = 0; s < N; ++s) acc += (double)base[s * stride + p] * ev[(size_t)s * C * Dl];
+            const float* ev = lat + (size_t)c * chain_stride + j;    // eps_tform_s[j]
+            for (int s = 0; s < N; ++s) acc += (double)base[s * stride + p] * ev[(size_t)s * sn_stride];
         }
     }
     red[(size_t)c * Tr.R + r] = acc;
@@ -260,22 +284,18 @@ __global__ void __launch_bounds__(256) train_reduce_kernel(ModelDev M, TrainDev 
 // ------------------------------------------------------------------------------------------
 // (T4) finish: log p = reduced per-SN terms + global priors; chain rule to the unconstrained globals
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) train_finish_kernel(ModelDev M, TrainDev Tr, int LP, int TP,
-                                                           const float* __restrict__ qg_all,
-                                                           const double* __restrict__ red_all,
-                                                           double* __restrict__ logp, float* __restrict__ grad_g) {
-    const int c = blockIdx.x, tid = threadIdx.x;
+// gg = sign * d log p / d qg (sign = -1 gives the gradient of the potential energy)
+__device__ __forceinline__ void train_finish_dev(const ModelDev& M, const TrainDev& Tr, int LP, int TP, int c,
+                                                 const float* __restrict__ qg, const double* __restrict__ red,
+                                                 float* __restrict__ gg, float sign) {
+    const int tid = threadIdx.x;
     const int L = M.L, T = M.T, ne = M.n_eps, LPTP = Tr.LPTP;
-    const float* qg = qg_all + (size_t)c * Tr.G;
-    float* gg = grad_g + (size_t)c * Tr.G;
-    const double* red = red_all + (size_t)c * Tr.R;
     const int oW1 = L * T, oSe = 2 * L * T, oY = oSe + ne, oSc = oY + Tr.n_corr;
     const double HALF_PI = 1.5707963267948966;
-    if (tid == 0) logp[c] = red[0] + Tr.lpg[c];
     for (int p = tid; p < L * T; p += blockDim.x) {
         const int m = p / L, l = p - m * L;          // vec_F index p = l + L m
-        gg[p] = (float)(red[4 + l * TP + m] - (double)qg[p]);
-        gg[oW1 + p] = (float)(red[4 + LPTP + l * TP + m] - (double)qg[oW1 + p]);
+        gg[p] = sign * (float)(red[4 + l * TP + m] - (double)qg[p]);
+        gg[oW1 + p] = sign * (float)(red[4 + LPTP + l * TP + m] - (double)qg[oW1 + p]);
     }
     const double* Gm = red + 4 + 2 * LPTP;            // dL_Sigma [ne][ne]
     const float* Lo = Tr.Lo + (size_t)c * ne * ne;
@@ -289,7 +309,7 @@ __global__ void __launch_bounds__(128) train_finish_kernel(ModelDev M, TrainDev 
         {
             const double u = qg[oSe + i];
             const double sgm = 1.0 / (1.0 + exp(-u));
-            gg[oSe + i] = (float)(dse * (1.0 + se * se) * HALF_PI * sgm * (1.0 - sgm) + (1.0 - 2.0 * sgm));
+            gg[oSe + i] = sign * (float)(dse * (1.0 + se * se) * HALF_PI * sgm * (1.0 - sgm) + (1.0 - 2.0 * sgm));
         }
         if (i == 0) continue;
         // reverse sweep of the stick breaking of row i: c_j = c_{j-1} (1 - t_j^2), L[i][j] = t_j sqrt(c_{j-1}),
@@ -308,7 +328,7 @@ __global__ void __launch_bounds__(128) train_finish_kernel(ModelDev M, TrainDev 
             // t_j: direct through L[i][j], through c_j, and the tanh log-det
             const double om = 1.0 - t * t;
             const double dt = se * Gm[i * ne + j] * sqrt(cjm) + dcj * cjm * (-2.0 * t);
-            gy[j] = (float)(dt * om - 2.0 * t);
+            gy[j] = sign * (float)(dt * om - 2.0 * t);
             dc = dcj * om;
         }
     }
@@ -317,10 +337,20 @@ __global__ void __launch_bounds__(128) train_finish_kernel(ModelDev M, TrainDev 
         const double u0 = qg[oSc], u1 = qg[oSc + 1], u2 = qg[oSc + 2];
         const double s0 = 1.0 / (1.0 + exp(-u0)), s1 = 1.0 / (1.0 + exp(-u1)), s2 = 1.0 / (1.0 + exp(-u2));
         const double sig0 = sc[0], tauA = sc[2];
-        gg[oSc] = (float)(red[1] * 0.1 * (1.0 + 100.0 * sig0 * sig0) * HALF_PI * s0 * (1.0 - s0) + (1.0 - 2.0 * s0));
-        gg[oSc + 1] = (float)(red[2] * 4.0 * s1 * (1.0 - s1) + (1.0 - 2.0 * s1));
-        gg[oSc + 2] = (float)(red[3] * (1.0 + tauA * tauA) * HALF_PI * s2 * (1.0 - s2) + (1.0 - 2.0 * s2));
+        gg[oSc] = sign * (float)(red[1] * 0.1 * (1.0 + 100.0 * sig0 * sig0) * HALF_PI * s0 * (1.0 - s0) + (1.0 - 2.0 * s0));
+        gg[oSc + 1] = sign * (float)(red[2] * 4.0 * s1 * (1.0 - s1) + (1.0 - 2.0 * s1));
+        gg[oSc + 2] = sign * (float)(red[3] * (1.0 + tauA * tauA) * HALF_PI * s2 * (1.0 - s2) + (1.0 - 2.0 * s2));
     }
+}
+
+__global__ void __launch_bounds__(128) train_finish_kernel(ModelDev M, TrainDev Tr, int LP, int TP,
+                                                           const float* __restrict__ qg_all,
+                                                           const double* __restrict__ red_all,
+                                                           double* __restrict__ logp, float* __restrict__ grad_g) {
+    const int c = blockIdx.x;
+    const double* red = red_all + (size_t)c * Tr.R;
+    if (threadIdx.x == 0) logp[c] = red[0] + Tr.lpg[c];
+    train_finish_dev(M, Tr, LP, TP, c, qg_all + (size_t)c * Tr.G, red, grad_g + (size_t)c * Tr.G, 1.f);
 }
 
 }  // namespace bayesn

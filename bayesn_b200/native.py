@@ -44,7 +44,8 @@ EXPORTS = ['bayesn_abi_version', 'bayesn_ctx_create', 'bayesn_ctx_destroy', 'bay
            'bayesn_set_model', 'bayesn_bind_dataset', 'bayesn_param_dim', 'bayesn_logp_grad_fit',
            'bayesn_flux_batch', 'bayesn_nuts_workspace_bytes', 'bayesn_nuts_fit', 'bayesn_launch_count',
            'bayesn_init_to_median', 'bayesn_ffma_peak', 'bayesn_train_dims', 'bayesn_train_begin',
-           'bayesn_train_finish']
+           'bayesn_train_finish', 'bayesn_train_nuts_init', 'bayesn_train_nuts_sn', 'bayesn_train_nuts_ctl',
+           'bayesn_train_nuts_status']
 
 _lib = None
 
@@ -80,6 +81,10 @@ def load_library():
     lib.bayesn_train_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
     lib.bayesn_train_begin.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
     lib.bayesn_train_finish.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    lib.bayesn_train_nuts_init.argtypes = [C.c_void_p, C.POINTER(NutsCfg), C.c_int] + [C.c_void_p] * 6
+    lib.bayesn_train_nuts_sn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bayesn_train_nuts_ctl.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bayesn_train_nuts_status.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
     _lib = lib
     return lib
 
@@ -259,6 +264,93 @@ class Context:
         self._check(self.lib.bayesn_train_finish(self.h, Cn, qg.data_ptr(), red.data_ptr(), logp.data_ptr(),
                                                  grad_g.data_ptr(), st), 'bayesn_train_finish')
         return logp, grad_g, grad_l
+
+    def train_nuts(self, qg0, ql0, num_warmup=500, num_samples=500, max_tree_depth=10, target_accept=0.8,
+                   init_step_size=0.1, adapt_step_size=True, adapt_mass_matrix=True, regularize_mass_matrix=False,
+                   seed=0, group=None, sn_offset=0, passes_per_graph=32, use_graph=True, max_passes=None,
+                   progress=None):
+        """Device-resident NUTS over the joint training posterior (numpyro call at reference
+        :1767-1770, :1913-1919).  ``qg0`` (C, G), ``ql0`` (N, C, Dl) float32 CUDA tensors.  One pass =
+        one leapfrog of every chain = SN kernel + reduction -> [all-reduce over ``group``] -> control
+        kernel; passes are replayed from a CUDA graph and the host only polls the chains' status.
+        Returns dict(samples_g (C, S, G), samples_l (N, C, S, Dl), stats (C, W+S, 5), info (C, 8),
+        passes)."""
+        import torch
+        assert qg0.is_cuda and qg0.dtype == torch.float32 and qg0.is_contiguous()
+        assert ql0.is_cuda and ql0.dtype == torch.float32 and ql0.is_contiguous()
+        Cn, G = qg0.shape
+        N, C2, Dl = ql0.shape
+        Gd, Dld, R = self.train_dims()
+        assert (G, Dl, C2, N) == (Gd, Dld, Cn, self.N)
+        dev = qg0.device
+        cfg = NutsCfg(int(num_warmup), int(num_samples), int(Cn), int(max_tree_depth), float(target_accept),
+                      float(init_step_size), int(adapt_step_size), int(adapt_mass_matrix),
+                      int(regularize_mass_matrix), int(seed) & 0xFFFFFFFFFFFFFFFF)
+        out = dict(samples_g=torch.zeros((Cn, num_samples, G), dtype=torch.float32, device=dev),
+                   samples_l=torch.zeros((N, Cn, num_samples, Dl), dtype=torch.float32, device=dev),
+                   stats=torch.zeros((Cn, num_warmup + num_samples, 5), dtype=torch.float32, device=dev))
+        red = torch.zeros((Cn, R), dtype=torch.float64, device=dev)
+        self._keep['train_nuts'] = (out, red, qg0, ql0)
+        self._check(self.lib.bayesn_train_nuts_init(self.h, C.byref(cfg), int(sn_offset), qg0.data_ptr(),
+                                                    ql0.data_ptr(), out['samples_g'].data_ptr(),
+                                                    out['samples_l'].data_ptr(), out['stats'].data_ptr(),
+                                                    self._stream()), 'bayesn_train_nuts_init')
+        if group is not None:
+            import torch.distributed as dist
+
+        def one_pass():
+            st = self._stream()
+            self._check(self.lib.bayesn_train_nuts_sn(self.h, red.data_ptr(), st), 'bayesn_train_nuts_sn')
+            if group is not None:
+                dist.all_reduce(red, op=dist.ReduceOp.SUM, group=group)
+            self._check(self.lib.bayesn_train_nuts_ctl(self.h, red.data_ptr(), st), 'bayesn_train_nuts_ctl')
+
+        status = (C.c_float * (8 * Cn))()
+
+        def poll():
+            rc = self.lib.bayesn_train_nuts_status(self.h, status, self._stream())
+            if rc < 0:
+                self._check(rc, 'bayesn_train_nuts_status')
+            return rc == 1
+
+        one_pass()                                   # the initial evaluation (also warms every lazy allocation)
+        torch.cuda.synchronize()
+        passes = 1
+        graph = None
+        if use_graph:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                one_pass()
+                passes += 1
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for _ in range(passes_per_graph):
+                    one_pass()
+        done = False
+        while not done:
+            if graph is not None:
+                graph.replay()
+                passes += passes_per_graph
+            else:
+                for _ in range(passes_per_graph):
+                    one_pass()
+                passes += passes_per_graph
+            done = poll()
+            if progress is not None:
+                progress(passes, np.ctypeslib.as_array(status).reshape(Cn, 8).copy())
+            if max_passes is not None and passes >= max_passes:
+                break
+        # flush: the latent slices apply the last transition's actions (final draw) in one more SN pass
+        self._check(self.lib.bayesn_train_nuts_sn(self.h, red.data_ptr(), self._stream()), 'bayesn_train_nuts_sn')
+        torch.cuda.synchronize()
+        poll()
+        out['info'] = np.ctypeslib.as_array(status).reshape(Cn, 8).copy()
+        out['passes'] = passes
+        out['finished'] = bool(done)
+        return out
 
     def flux_batch(self, M0, theta, AV, W0, W1, eps, Ds, RV, band_indices, mask, J_t, hsiao_interp, weights,
                    band_log10_scale, mag=False):

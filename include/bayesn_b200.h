@@ -164,6 +164,28 @@ int bayesn_train_begin(bayesn_ctx* ctx, int n_chains, const float* qg, const flo
 int bayesn_train_finish(bayesn_ctx* ctx, int n_chains, const float* qg, const double* red, double* logp,
                         float* grad_g, void* stream);
 
+/* Device-resident NUTS over the joint training posterior (all globals + the latents of every SN),
+ * replacing numpyro MCMC(NUTS(train_model_globalRV, step_size=0.1, ...)) at
+ * bayesn/bayesn_model.py:1767-1770, :1913-1919.  The sampler state is sharded: (SN, chain) warps own
+ * the latent slices, one CTA per chain owns the globals and all decisions.  One PASS = one leapfrog
+ * of every chain = bayesn_train_nuts_sn (per-SN work + sums over this rank's SNe into red [C][R],
+ * double, device) -> [caller all-reduces red over ranks when SNe are sharded] ->
+ * bayesn_train_nuts_ctl.  All calls are asynchronous on `stream` and capturable in a CUDA graph.
+ *   cfg             num_chains = C; reference training uses init_step_size 0.1, no regularisation
+ *   sn_offset       global index of this rank's first SN (keys the latent momentum streams)
+ *   qg0 [C][G], ql0 [N][C][Dl]   initial unconstrained position (device)
+ *   samples_g [C][S][G], samples_l [N][C][S][Dl], stats [C][W+S][5]   outputs (device), written as
+ *                   the run proceeds; layout of stats rows as in bayesn_nuts_fit
+ * bayesn_train_nuts_status synchronises the stream, fills out [C][8] (HOST) = {phase (2 = done),
+ * transition index, step size, mean accept, leapfrogs so far, divergences, potential energy, depth}
+ * and returns 1 when every chain is done (one more bayesn_train_nuts_sn call then flushes the last
+ * draw of the latents), 0 if not, <0 on error. */
+int bayesn_train_nuts_init(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, int sn_offset, const float* qg0,
+                           const float* ql0, float* samples_g, float* samples_l, float* stats, void* stream);
+int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream);
+int bayesn_train_nuts_ctl(bayesn_ctx* ctx, const double* red, void* stream);
+int bayesn_train_nuts_status(bayesn_ctx* ctx, float* out, void* stream);
+
 /* numpyro init_to_median(num_samples=15) (reference bayesn/bayesn_model.py:1757, :2110): initial
  * unconstrained positions q [N][n_chains][D] (device, out) for the bound data set. */
 int bayesn_init_to_median(bayesn_ctx* ctx, int n_chains, uint64_t seed, float* q, void* stream);

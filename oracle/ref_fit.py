@@ -61,3 +61,29 @@ def constrain(ref, samples, rv_mode='fixed'):
     elif rv_mode == 'pop':
         out['RV_tform'] = 1 / (1 + np.exp(-samples[..., 4]))
     return out
+
+
+def train_cpu(ref, obs, weights, qg0, ql0, chain=0, n_chains=1, num_warmup=0, num_samples=5, max_depth=5,
+              init_step=0.01, seed=0, adapt_step=False, adapt_mass=False, sn_offset=0):
+    """One chain of the joint training posterior (train_model_globalRV) with the float64 oracle
+    density and the same sampler semantics / random streams as the device sampler.  ``qg0`` (G,),
+    ``ql0`` (N, Dl) in the kernel's latent layout.  Returns dict of per-transition records; ``z``
+    rows are [globals, latents...]."""
+    qg0, ql0 = np.asarray(qg0, np.float64), np.asarray(ql0, np.float64)
+    G, (N, Dl) = qg0.shape[0], ql0.shape
+    nrm_fn, unit = ref_nuts.train_momentum_layout(G, N, Dl, n_chains, chain, sn_offset)
+    rec = {k: [] for k in ('z', 'accept', 'n_steps', 'diverging', 'pe', 'step')}
+    gen = ref_nuts.chain_nuts(np.concatenate([qg0, ql0.ravel()]), unit, num_warmup, num_samples, max_depth=max_depth,
+                              init_step=init_step, seed=seed, adapt_step=adapt_step, adapt_mass=adapt_mass,
+                              regularize=False, record=rec, nrm_fn=nrm_fn)
+    z = next(gen)
+    evals = 0
+    try:
+        while True:
+            lp, gg, gl = ref.train_logp_grad(z[:G], z[G:].reshape(N, Dl), obs, weights)
+            evals += 1
+            z = gen.send((lp, np.concatenate([gg, gl.ravel()])))
+    except StopIteration:
+        pass
+    rec['evals'] = evals
+    return rec

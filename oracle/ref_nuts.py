@@ -78,9 +78,20 @@ def _logaddexp(a, b):
     return m + math.log1p(math.exp(-abs(a - b)))
 
 
+def philox_normals(ctr, key):
+    """The four standard normals the device code makes from one Philox block (Box-Muller)."""
+    ra = philox4x32(ctr, key)
+    n0 = math.sqrt(-2.0 * math.log(u01(ra[0]) + 5.9604644775390625e-8))
+    n1 = math.sqrt(-2.0 * math.log(u01(ra[2]) + 5.9604644775390625e-8))
+    a0, a1 = 2 * math.pi * u01(ra[1]), 2 * math.pi * u01(ra[3])
+    return (n0 * math.cos(a0), n0 * math.sin(a0), n1 * math.cos(a1), n1 * math.sin(a1))
+
+
 def chain_nuts(z0, unit, num_warmup, num_samples, max_depth=10, target_accept=0.8, init_step=1.0, seed=0,
-               adapt_step=True, adapt_mass=True, regularize=True, record=None):
-    """Generator: yields positions, receives (logp, grad).  Fills ``record`` (dict of lists)."""
+               adapt_step=True, adapt_mass=True, regularize=True, record=None, nrm_fn=None):
+    """Generator: yields positions, receives (logp, grad).  Fills ``record`` (dict of lists).
+    ``nrm_fn(it, key)`` (optional) supplies the standard normals of the momentum refresh when the
+    state is laid out differently from the per-object fit (training: sharded over SNe)."""
     key = (seed & M32, (seed >> 32) & M32)
     D = z0.shape[0]
     z = z0.astype(np.float64).copy()
@@ -102,7 +113,9 @@ def chain_nuts(z0, unit, num_warmup, num_samples, max_depth=10, target_accept=0.
         # momentum refresh
         nrm = np.empty(D)
         cache = {}
-        for i in range(D):
+        if nrm_fn is not None:
+            nrm = nrm_fn(it, key)
+        for i in range(D if nrm_fn is None else 0):
             ln = int(lanes[i])
             if ln not in cache:
                 ra = philox4x32((it, 0x40000000, ln, unit & M32), key)
@@ -239,6 +252,32 @@ def chain_nuts(z0, unit, num_warmup, num_samples, max_depth=10, target_accept=0.
             record['step'].append(step)
     if record is not None:
         record['inv_mass'] = im.copy()
+
+
+def train_momentum_layout(G, N, Dl, C, chain, sn_offset=0):
+    """Momentum stream of the sharded training sampler (bayesn_train_nuts.cuh): the globals of
+    chain c draw blocks of four from stream 0x7fff0000 + c, SN s draws lane-wise from stream
+    (sn_offset + s) * C + c.  Returns (nrm_fn, unit) for :func:`chain_nuts` on the joint vector
+    [globals (G), latents of SN 0 (Dl), SN 1, ...]."""
+    gkey = (0x7fff0000 + chain) & M32
+
+    def nrm_fn(it, key):
+        out = np.empty(G + N * Dl)
+        for b in range((G + 3) // 4):
+            n4 = philox_normals((it, 0x40000000, b, gkey), key)
+            for k in range(4):
+                if 4 * b + k < G:
+                    out[4 * b + k] = n4[k]
+        for s in range(N):
+            gunit = ((sn_offset + s) * C + chain) & M32
+            cache = {}
+            for e in range(Dl):
+                ln, slot = e % 32, e // 32
+                if ln not in cache:
+                    cache[ln] = philox_normals((it, 0x40000000, ln, gunit), key)
+                out[G + s * Dl + e] = cache[ln][slot & 3]
+        return out
+    return nrm_fn, gkey
 
 
 def run_chains(logp_grad_batch, q_init, num_warmup, num_samples, unit_ids=None, **kw):

@@ -105,3 +105,59 @@ def test_train_reduction_is_additive_over_sn_shards():
     torch.cuda.synchronize()
     tot = reds[0] + reds[1]
     assert torch.allclose(tot, red_full, rtol=1e-9, atol=1e-9 * float(red_full.abs().max()))
+
+
+def _small_training_problem(N=3, C=2, seed=7):
+    case = make_case('T21_model', PS1, np.arange(-8, 40, 4.0), N=N, seed=seed, mag=True, mask_some=True)
+    ref = case['ref']
+    m, bi = product_model(case)
+    ctx = m.prepare_training(case['obs'], m._calculate_band_weights(case['z'], case['ebv'], bi), bi)
+    qg, ql = training_point(ref, case, C, seed, spread=0.3)
+    qg32 = torch.tensor(qg, dtype=torch.float32, device='cuda').contiguous()
+    ql32 = torch.tensor(ql, dtype=torch.float32, device='cuda').contiguous()
+    return case, ref, m, ctx, qg32, ql32
+
+
+def test_train_nuts_trajectories_match_oracle_sampler():
+    """Same Philox streams, same start, adaptation off: the sharded device sampler and the float64
+    oracle sampler build the same trees (leapfrog counts per transition) and land on the same points
+    for the first transitions (float32 chaos separates them eventually)."""
+    from oracle import ref_fit
+    case, ref, m, ctx, qg32, ql32 = _small_training_problem()
+    n_tr = 5
+    out = ctx.train_nuts(qg32, ql32, num_warmup=0, num_samples=n_tr, max_tree_depth=5, init_step_size=0.004,
+                         adapt_step_size=False, adapt_mass_matrix=False, seed=11, passes_per_graph=8)
+    assert out['finished']
+    st = out['stats'].cpu().numpy()
+    sg = out['samples_g'].cpu().numpy().astype(np.float64)
+    sl = out['samples_l'].cpu().numpy().astype(np.float64)
+    qg, ql = qg32.cpu().numpy().astype(np.float64), ql32.cpu().numpy().astype(np.float64)
+    G = qg.shape[1]
+    for c in range(2):
+        rec = ref_fit.train_cpu(ref, case['obs'], case['weights'], qg[c], ql[:, c], chain=c, n_chains=2, num_samples=n_tr,
+                                max_depth=5, init_step=0.004, seed=11)
+        n_gpu, n_cpu = st[c, :, 1], np.array(rec['n_steps'])
+        agree = int(np.argmax(n_gpu != n_cpu)) if np.any(n_gpu != n_cpu) else n_tr
+        assert agree >= 3, (n_gpu, n_cpu)
+        z_cpu = np.array(rec['z'])
+        assert np.max(np.abs(sg[c, :agree] - z_cpu[:agree, :G])) < 5e-3
+        zl = z_cpu[:agree, G:].reshape(agree, ql.shape[0], -1)
+        assert np.max(np.abs(sl[:, c, :agree].transpose(1, 0, 2) - zl)) < 5e-3
+        assert np.allclose(st[c, :agree, 0], np.array(rec['accept'])[:agree], atol=5e-3)
+        assert np.allclose(st[c, :agree, 3], np.array(rec['pe'])[:agree], rtol=1e-5)
+
+
+def test_train_nuts_adapts_and_conserves_energy():
+    """Short adaptive run on a small simulated training set: finite draws, acceptance near the
+    target after warm-up, few divergences, and CUDA-graph replay == eager launches."""
+    case, ref, m, ctx, qg32, ql32 = _small_training_problem(N=16, C=2, seed=4)
+    kw = dict(num_warmup=60, num_samples=30, max_tree_depth=6, seed=3)
+    out = ctx.train_nuts(qg32, ql32, passes_per_graph=16, **kw)
+    assert out['finished']
+    for k in ('samples_g', 'samples_l', 'stats'):
+        assert torch.isfinite(out[k]).all(), k
+    st = out['stats'].cpu().numpy()
+    assert 0.5 < st[:, 60:, 0].mean() < 0.99
+    assert st[:, 60:, 2].sum() <= 3
+    out2 = ctx.train_nuts(qg32, ql32, use_graph=False, passes_per_graph=16, **kw)
+    assert torch.equal(out['samples_g'], out2['samples_g']) and torch.equal(out['samples_l'], out2['samples_l'])
