@@ -103,6 +103,8 @@ int train_prepare(bayesn_ctx* ctx, int C) {
     rc |= train_alloc(ctx, &T.Lo, (size_t)C * ne * ne);
     rc |= train_alloc(ctx, &T.tm, (size_t)C * ne * ne);
     rc |= train_alloc(ctx, &T.cum, (size_t)C * ne * ne);
+    rc |= train_alloc(ctx, &T.clog, (size_t)C * ne * ne);
+    rc |= train_alloc(ctx, &T.scr, (size_t)C * ne * ne);
     rc |= train_alloc(ctx, &T.lpg, (size_t)C);
     rc |= train_alloc(ctx, &T.part, (size_t)ctx->D.N * C * T.PR);
     if (rc) return rc;
@@ -175,7 +177,7 @@ int launch_train_sn(bayesn_ctx* ctx, const float* ql, float* grad_l, cudaStream_
     if (RVFREE) return fail(ctx, -1, "training needs a fixed-RV model context (rv_mode = BAYESN_RV_FIXED)");
     const int C = ctx->T.C;
     const int ntile = ntile_for(C);
-    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, false, STAGE);
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, false, STAGE, true);
     const size_t bytes = (size_t)P.totalFloats * 4;
     auto kern = train_sn_kernel<LP, TP, (LP * TP - 2 * TP + 3 + 31) / 32, STAGE>;
     if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
@@ -199,7 +201,7 @@ int launch_train_nuts_sn(bayesn_ctx* ctx, cudaStream_t st) {
     if (RVFREE) return fail(ctx, -1, "training needs a fixed-RV model context (rv_mode = BAYESN_RV_FIXED)");
     const int C = ctx->T.C;
     const int ntile = ntile_for(C);
-    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, false, STAGE);
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, false, STAGE, true);
     const size_t bytes = (size_t)P.totalFloats * 4;
     constexpr int TVPL = (LP * TP - 2 * TP + 3 + 31) / 32;
     auto kern = train_nuts_sn_kernel<LP, TP, TVPL, STAGE>;
@@ -503,7 +505,7 @@ int bayesn_train_begin(bayesn_ctx* ctx, int n_chains, const float* qg, const flo
     CU_CHECK(ctx, cudaGetLastError());
     TrainSnCall call{ctx, ql, grad_l, st};
     if (int rc = dispatch(ctx, /*stage=*/n_chains >= 2, call)) return rc;
-    dim3 grid((ctx->T.R + 255) / 256, n_chains);
+    dim3 grid((ctx->T.R + 7) / 8, n_chains);
     train_reduce_kernel<<<grid, 256, 0, st>>>(ctx->M, ctx->T, ctx->D.N, ctx->LP, ctx->TP, ql, (size_t)ctx->T.Dl,
                                               (size_t)n_chains * ctx->T.Dl, red);
     ctx->launches++;
@@ -582,7 +584,7 @@ int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     TrainNutsSnCall call{ctx, st};
     if (int rc = dispatch(ctx, /*stage=*/ctx->T.C >= 2, call)) return rc;
-    dim3 grid((ctx->T.R + 255) / 256, ctx->T.C);
+    dim3 grid((ctx->T.R + 7) / 8, ctx->T.C);
     // the reduction needs theta_s and eps_tform_s of the point just evaluated: the current positions
     const size_t vec = (size_t)32 * ctx->TN.VPL, nvec = train_nuts_num_vectors(ctx->TN.cfg.max_depth);
     train_reduce_kernel<<<grid, 256, 0, st>>>(ctx->M, ctx->T, ctx->D.N, ctx->LP, ctx->TP, ctx->TN.work_l + TV_CZ * vec,
@@ -595,7 +597,7 @@ int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream) {
 int bayesn_train_nuts_ctl(bayesn_ctx* ctx, const double* red, void* stream) {
     if (!ctx) return -1;
     if (!ctx->have_tn) return fail(ctx, -1, "bayesn_train_nuts_init first");
-    train_nuts_ctl_kernel<<<ctx->T.C, 128, 0, (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->TN, ctx->LP, ctx->TP, red);
+    train_nuts_ctl_kernel<<<ctx->T.C, 256, 0, (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->TN, ctx->LP, ctx->TP, red);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;

@@ -196,14 +196,16 @@ __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.96
 // ------------------------------------------------------------------------------------------
 // shared-memory plan
 // ------------------------------------------------------------------------------------------
-template <int LP, int TP>
+template <int LP, int TP, bool TRAIN = false>
 struct Dims {
     static constexpr int LP4 = (LP + 3) & ~3;
     // per-observation record in shared memory:
     //   [u (LP4) | J_t (TP) | J_t' (TP) | pad | frac, hsiao idx + flags + band, y, 1/sigma]
-    static constexpr int R_JT = LP4, R_DJ = LP4 + TP, R_SC = (LP4 + 2 * TP + 3) & ~3;
+    // (training has no t_max: J_t' is dropped and the record is kept as small as possible so that
+    //  four CTAs - every SN of a 500-SN training set in ONE wave - fit an SM's shared memory)
+    static constexpr int R_JT = LP4, R_DJ = LP4 + TP, R_SC = (LP4 + (TRAIN ? 1 : 2) * TP + 3) & ~3;
     static constexpr int REC_RAW = R_SC + 4;
-    static constexpr int REC = ((REC_RAW / 4) % 2 == 1) ? REC_RAW : REC_RAW + 4;   // odd #16B words: fewer conflicts
+    static constexpr int REC = (TRAIN || (REC_RAW / 4) % 2 == 1) ? REC_RAW : REC_RAW + 4;   // odd #16B words: fewer conflicts
     static constexpr int NPAIR = (LP * TP + 31) / 32;   // (l, m) pairs per lane
     // J_l is stored bin-major, one row of RS floats per wavelength bin, read as LDS.128; an odd
     // number of 16-byte words per row keeps the 8-lane phases of LDS.128 bank-conflict free
@@ -212,9 +214,9 @@ struct Dims {
 constexpr int JROWS = BP + 32;   // per-bin tables carry 32 zero rows so the last round may overrun
 constexpr int OVERRUN = BAYESN_OVERRUN;     // bins a lane may read past the end of its band's support (values discarded)
 __host__ __device__ constexpr int jl_row_stride(int LP) { return ((((LP + 3) & ~3) / 4) % 2 == 1) ? ((LP + 3) & ~3) : ((LP + 3) & ~3) + 4; }
-__host__ __device__ constexpr int rec_stride(int LP, int TP) {
-    int raw = ((((LP + 3) & ~3) + 2 * TP + 3) & ~3) + 4;
-    return ((raw / 4) % 2 == 1) ? raw : raw + 4;
+__host__ __device__ constexpr int rec_stride(int LP, int TP, bool train = false) {
+    int raw = ((((LP + 3) & ~3) + (train ? 1 : 2) * TP + 3) & ~3) + 4;
+    return (train || (raw / 4) % 2 == 1) ? raw : raw + 4;
 }
 
 struct SmemPlan {
@@ -227,9 +229,9 @@ struct SmemPlan {
 };
 
 __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b, int N_obs, int wt_stride, int ntile,
-                                              bool rvfree, bool stage) {
+                                              bool rvfree, bool stage, bool train = false) {
     SmemPlan p;
-    const int rec = rec_stride(LP, TP);
+    const int rec = rec_stride(LP, TP, train);
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
     p.oJl = take(JROWS * jl_row_stride(LP));
@@ -256,8 +258,8 @@ __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b
     p.warpStride = w;
     // Lanes that have run past their band's support keep reading (and discard) up to OVERRUN bins
     // beyond it while the other half-warp finishes a wider band: keep those reads inside the CTA's
-    // allocation.
-    p.totalFloats = o + WPB * w + OVERRUN;
+    // allocation (only the per-chain dust arrays of the sampled-RV fits sit at its very end).
+    p.totalFloats = o + WPB * w + (rvfree ? OVERRUN : 0);
     const int jl_reach = p.oJl + (NB + OVERRUN) * jl_row_stride(LP);
     if (p.totalFloats < jl_reach) p.totalFloats = jl_reach;
     return p;
@@ -360,7 +362,7 @@ __device__ __forceinline__ float vget(const float (&v)[VPL], int i) {
 template <int LP, int TP, int VPL, bool RVFREE, bool STAGE, bool TRAIN = false>
 __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx& c, const float* __restrict__ hs,
                                                const float (&q)[VPL], double& logp_out, float (&grad)[VPL], int lane) {
-    using DM = Dims<LP, TP>;
+    using DM = Dims<LP, TP, TRAIN>;
     constexpr int LP4 = DM::LP4, REC = DM::REC, NPAIR = DM::NPAIR, RS = DM::RS;
     constexpr bool DRV = RVFREE || TRAIN;     // the derivative with respect to R_V is needed
     static_assert(!(RVFREE && TRAIN), "training samples one global R_V");
@@ -480,7 +482,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
 #pragma unroll
         for (int m = 0; m < TP; ++m) {
             rc[DM::R_JT + m] = J[m];
-            rc[DM::R_DJ + m] = dJ[m];
+            if (!TRAIN) rc[DM::R_DJ + m] = dJ[m];
         }
 #pragma unroll
         for (int l = 0; l < LP4; ++l) {
@@ -603,10 +605,12 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         // d logL / d(sum_m W[l][m] Jt[m]) for this observation, overwriting u (no longer needed),
         // and its product with (W J_t'(t))[l] for the gradient through the time spline
         const float dU = -KAPPA * coef * val;
-        float du = 0.f;
+        if (!TRAIN) {
+            float du = 0.f;
 #pragma unroll
-        for (int m = 0; m < TP; ++m) du = fmaf(wrow[m], rc[DM::R_DJ + m], du);
-        gTW = fmaf(dU, du, gTW);
+            for (int m = 0; m < TP; ++m) du = fmaf(wrow[m], rc[DM::R_DJ + m], du);
+            gTW = fmaf(dU, du, gTW);
+        }
         __syncwarp();
         if (hl >= 4 && hl < 4 + LP) rc[hl - 4] = dU;
     }
@@ -729,10 +733,10 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
 // ------------------------------------------------------------------------------------------
 // CTA prologue shared by the log p kernel and the NUTS kernel: stage tables with TMA, carve smem
 // ------------------------------------------------------------------------------------------
-template <int LP, int TP, bool RVFREE, bool STAGE>
+template <int LP, int TP, bool RVFREE, bool STAGE, bool TRAIN = false>
 __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, int n_chains, int ntile, float* smem,
                                           WarpCtx& c, int& sn, int& chain) {
-    const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE);
+    const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE, TRAIN);
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long unit0 = (long long)blockIdx.x * WPB;
     const long long total = (long long)Dd.N * n_chains;

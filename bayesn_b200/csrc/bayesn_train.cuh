@@ -29,7 +29,9 @@ struct TrainDev {
     float* sig;     // [C][ne] sigma_epsilon
     float* Lo;      // [C][ne*ne] L_Omega
     float* tm;      // [C][ne*ne] tanh(y) laid out as a strict lower triangle
-    float* cum;     // [C][ne*ne] cumulative products prod_{k<=j} (1 - t_ik^2)
+    float* cum;     // [C][ne*ne] cumulative products c_ij = prod_{k<=j} (1 - t_ik^2)
+    float* clog;    // [C][ne*ne] their logarithms
+    float* scr;     // [C][ne*ne] scratch of the reverse sweep
     double* lpg;    // [C] log prior + log|det J| of the global sites
     float* part;    // [N][C][PR] per-SN contributions
 };
@@ -52,6 +54,25 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
     double t = 0.0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
     return t;
+}
+
+// In-place running sum of row[0..n) by one warp (reverse = suffix sums): coalesced loads and a
+// shuffle scan instead of one thread walking the row through global memory.
+__device__ __forceinline__ void warp_row_cumsum(float* row, int n, int lane, bool reverse) {
+    float carry = 0.f;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        const int idx = reverse ? n - 1 - j : j;
+        float v = (j < n) ? row[idx] : 0.f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(FULL, v, o);
+            if (lane >= o) v += t;
+        }
+        v += carry;
+        if (j < n) row[idx] = v;
+        carry = __shfl_sync(FULL, v, 31);
+    }
 }
 
 __device__ __forceinline__ double log_sigmoid_pair(double u) {   // log s(u) + log s(-u)
@@ -106,37 +127,52 @@ __device__ __forceinline__ void train_globals_dev(const ModelDev& M, const Train
         lp += log_sigmoid_pair(u);
     }
     __syncthreads();
-    // rows of L_Omega by signed stick breaking; L_Sigma = diag(sigma_epsilon) L_Omega
+    // rows of L_Omega by signed stick breaking; L_Sigma = diag(sigma_epsilon) L_Omega.  Row i:
+    // t_j = tanh(y_ij), c_j = prod_{k<=j} (1 - t_k^2), L[i][j] = t_j sqrt(c_{j-1}), L[i][i] = sqrt(c_{i-1}).
+    // Three sweeps: element-parallel transcendental work, a per-row running sum of log(1 - t^2),
+    // element-parallel assembly - instead of one thread walking a row through tanh / log / sqrt.
     float* Ls = Tr.Ls + (size_t)c * ne * ne;
     float* LsT = Tr.LsT + (size_t)c * ne * ne;
     float* Lo = Tr.Lo + (size_t)c * ne * ne;
     float* tm = Tr.tm + (size_t)c * ne * ne;
     float* cum = Tr.cum + (size_t)c * ne * ne;
-    for (int i = tid; i < ne; i += blockDim.x) {
-        const float* y = qg + oY + (size_t)i * (i - 1) / 2;
-        double cprod = 1.0;
-        const float se = s_sig[i];
-        for (int j = 0; j < ne; ++j) {
-            float lo = 0.f, t = 0.f;
+    float* clog = Tr.clog + (size_t)c * ne * ne;
+    for (int e = tid; e < Tr.n_corr; e += blockDim.x) {
+        int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)e)) * 0.5f);
+        while (i * (i - 1) / 2 > e) --i;
+        while ((i + 1) * i / 2 <= e) ++i;
+        const int j = e - i * (i - 1) / 2;
+        const double yv = qg[oY + e];
+        const double l1m = 2.0 * (0.6931471805599453 - fabs(yv) - log1p(exp(-2.0 * fabs(yv))));   // log(1 - tanh^2)
+        tm[i * ne + j] = (float)tanh(yv);
+        clog[i * ne + j] = (float)l1m;
+        lp += l1m;                                   // tanh log-det
+    }
+    __syncthreads();
+    for (int i = tid >> 5; i < ne; i += blockDim.x >> 5) warp_row_cumsum(clog + i * ne, i, tid & 31, false);
+    __syncthreads();
+    for (int e = tid; e < ne * ne; e += blockDim.x) {
+        const int i = e / ne, j = e - i * ne;
+        float lo = 0.f, t = 0.f, cj = 1.f;
+        if (j <= i) {
+            const float clp = (j > 0) ? clog[i * ne + j - 1] : 0.f;       // log c_{j-1}
             if (j < i) {
-                const double yv = y[j];
-                const double td = tanh(yv);
-                t = (float)td;
-                lo = (float)(td * sqrt(cprod));
-                const double om = 1.0 - td * td;
-                cprod *= om;
-                // tanh log-det + stick-breaking log-det (columns 0..i-2) + LKJ (diagonal element)
-                lp += 2.0 * (0.6931471805599453 - fabs(yv) - log1p(exp(-2.0 * fabs(yv))));
-                lp += (j <= i - 2) ? 0.5 * log(cprod) : 0.5 * (double)(ne - 1 - i) * log(cprod);
-            } else if (j == i) {
-                lo = (float)sqrt(cprod);
+                t = tm[e];
+                const float cl = clog[e];
+                cj = expf(cl);
+                lo = t * expf(0.5f * clp);
+                // stick-breaking log-det (columns 0..i-2) + LKJCholesky(eta = 1) on the diagonal element
+                lp += (j <= i - 2) ? 0.5 * (double)cl : 0.5 * (double)(ne - 1 - i) * (double)cl;
+            } else {
+                lo = expf(0.5f * clp);
             }
-            Lo[i * ne + j] = lo;
-            tm[i * ne + j] = t;
-            cum[i * ne + j] = (float)cprod;
-            Ls[i * ne + j] = se * lo;
-            LsT[j * ne + i] = se * lo;
         }
+        const float se = s_sig[i];
+        Lo[e] = lo;
+        if (j >= i) tm[e] = 0.f;
+        cum[e] = cj;
+        Ls[e] = se * lo;
+        LsT[j * ne + i] = se * lo;
     }
     // sigma0 = 0.1 tan(.), RV = 1 + 4 sigmoid(.), tauA = tan(.)
     if (tid == 0) {
@@ -204,7 +240,7 @@ __global__ void __launch_bounds__(WPB * 32) train_sn_kernel(ModelDev M, DataDev 
     WarpCtx c;
     int sn, chain;
     const int C = Tr.C;
-    const bool active = cta_setup<LP, TP, false, STAGE>(M, Dd, C, ntile, smem, c, sn, chain);
+    const bool active = cta_setup<LP, TP, false, STAGE, true>(M, Dd, C, ntile, smem, c, sn, chain);
     if (!active) return;
     const int lane = threadIdx.x & 31;
     const size_t unit = (size_t)sn * C + chain;
@@ -246,7 +282,8 @@ __global__ void __launch_bounds__(256) train_reduce_kernel(ModelDev M, TrainDev 
                                                            const float* __restrict__ lat, size_t chain_stride,
                                                            size_t sn_stride, double* __restrict__ red) {
     const int c = blockIdx.y;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // one warp per output, lanes over SNe
     const int ne = M.n_eps, L = M.L, C = Tr.C, PR = Tr.PR, LPTP = Tr.LPTP;
     if (r >= Tr.R) return;
     const size_t stride = (size_t)C * PR;
@@ -254,19 +291,19 @@ __global__ void __launch_bounds__(256) train_reduce_kernel(ModelDev M, TrainDev 
     double acc = 0.0;
     if (r == 0) {
         const int off = LPTP + 3 + ((LPTP + 3) & 1);
-        for (int s = 0; s < N; ++s) acc += *reinterpret_cast<const double*>(base + s * stride + off);
+        for (int s = lane; s < N; s += 32) acc += *reinterpret_cast<const double*>(base + s * stride + off);
     } else if (r < 4) {
-        for (int s = 0; s < N; ++s) acc += base[s * stride + LPTP + (r - 1)];
+        for (int s = lane; s < N; s += 32) acc += base[s * stride + LPTP + (r - 1)];
     } else if (r < 4 + LPTP) {
         const int p = r - 4;
-        for (int s = 0; s < N; ++s) acc += base[s * stride + p];
+        for (int s = lane; s < N; s += 32) acc += base[s * stride + p];
     } else if (r < 4 + 2 * LPTP) {
         const int p = r - 4 - LPTP;
         const float* th = lat + (size_t)c * chain_stride + ne;       // theta_s
-        for (int s = 0; s < N; ++s) acc += (double)base[s * stride + p] * th[(size_t)s * sn_stride];
+        for (int s = lane; s < N; s += 32) acc += (double)base[s * stride + p] * th[(size_t)s * sn_stride];
     } else if (r >= train_red_base(LPTP, ne)) {
         const int x = train_part_base(LPTP) + (r - train_red_base(LPTP, ne));
-        for (int s = 0; s < N; ++s) acc += base[s * stride + x];
+        for (int s = lane; s < N; s += 32) acc += base[s * stride + x];
     } else {
         const int e = r - 4 - 2 * LPTP;
         const int i = e / ne, j = e - i * ne;
@@ -275,10 +312,11 @@ __global__ void __launch_bounds__(256) train_reduce_kernel(ModelDev M, TrainDev 
             const int m = i / (L - 2), l = 1 + (i - m * (L - 2));
             const int p = l * TP + m;
             const float* ev = lat + (size_t)c * chain_stride + j;    // eps_tform_s[j]
-            for (int s = 0; s < N; ++s) acc += (double)base[s * stride + p] * ev[(size_t)s * sn_stride];
+            for (int s = lane; s < N; s += 32) acc += (double)base[s * stride + p] * ev[(size_t)s * sn_stride];
         }
     }
-    red[(size_t)c * Tr.R + r] = acc;
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    if (lane == 0) red[(size_t)c * Tr.R + r] = acc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -301,36 +339,49 @@ __device__ __forceinline__ void train_finish_dev(const ModelDev& M, const TrainD
     const float* Lo = Tr.Lo + (size_t)c * ne * ne;
     const float* tm = Tr.tm + (size_t)c * ne * ne;
     const float* cum = Tr.cum + (size_t)c * ne * ne;
-    for (int i = tid; i < ne; i += blockDim.x) {
-        const double se = Tr.sig[(size_t)c * ne + i];
-        // d/dsigma_i = sum_j G[i][j] L_Omega[i][j];  d/dL_Omega[i][j] = sigma_i G[i][j]
+    float* scr = Tr.scr + (size_t)c * ne * ne;
+    // Reverse sweep of the stick breaking.  With gL_ij = sigma_i G[i][j] (d/dL_Omega[i][j]) and
+    // A_j the weight of log c_j in the density, d/dc_j obeys dc_j = a_j / c_j + (1 - t_{j+1}^2) dc_{j+1},
+    // a_j = A_j + sqrt(c_j)/2 * (j == i-1 ? gL_ii : gL_{i,j+1} t_{j+1}); multiplying by c_j turns it
+    // into a plain suffix sum S_j = sum_{k >= j} a_k, and
+    //   d/dy_ij = gL_ij sqrt(c_{j-1}) (1 - t_j^2) - 2 t_j (S_j + 1).
+    for (int e = tid; e < ne * ne; e += blockDim.x) {
+        const int i = e / ne, j = e - i * ne;
+        float a = 0.f;
+        if (j < i) {
+            const float se = Tr.sig[(size_t)c * ne + i];
+            const float A = (j <= i - 2) ? 0.5f : 0.5f * (float)(ne - 1 - i);
+            const float nxt = (j == i - 1) ? (float)Gm[i * ne + i] : (float)Gm[e + 1] * tm[e + 1];
+            a = A + 0.5f * sqrtf(cum[e]) * se * nxt;
+        }
+        scr[e] = a;
+    }
+    __syncthreads();
+    for (int i = tid >> 5; i < ne; i += blockDim.x >> 5) {     // one warp per row
+        const int lane = tid & 31;
+        // d/dsigma_i = sum_j G[i][j] L_Omega[i][j], and the suffix sums of row i
         double dse = 0.0;
-        for (int j = 0; j <= i; ++j) dse += Gm[i * ne + j] * (double)Lo[i * ne + j];
-        {
+        for (int j = lane; j <= i; j += 32) dse += Gm[i * ne + j] * (double)Lo[i * ne + j];
+        for (int o = 16; o; o >>= 1) dse += __shfl_xor_sync(FULL, dse, o);
+        warp_row_cumsum(scr + i * ne, i, lane, true);
+        if (lane == 0) {
+            const double se = Tr.sig[(size_t)c * ne + i];
             const double u = qg[oSe + i];
             const double sgm = 1.0 / (1.0 + exp(-u));
             gg[oSe + i] = sign * (float)(dse * (1.0 + se * se) * HALF_PI * sgm * (1.0 - sgm) + (1.0 - 2.0 * sgm));
         }
-        if (i == 0) continue;
-        // reverse sweep of the stick breaking of row i: c_j = c_{j-1} (1 - t_j^2), L[i][j] = t_j sqrt(c_{j-1}),
-        // L[i][i] = sqrt(c_{i-1}); log-density terms A_j log c_j + log(1 - t_j^2)
-        float* gy = gg + oY + (size_t)i * (i - 1) / 2;
-        double dc = 0.0;                               // d/dc_j flowing down from columns > j
-        for (int j = i - 1; j >= 0; --j) {
-            const double cj = cum[i * ne + j];
-            const double cjm = (j > 0) ? (double)cum[i * ne + j - 1] : 1.0;
-            const double t = tm[i * ne + j];
-            // contributions to d/dc_j
-            const double A = (j <= i - 2) ? 0.5 : 0.5 * (double)(ne - 1 - i);
-            double dcj = dc + A / cj;
-            if (j == i - 1) dcj += se * Gm[i * ne + i] * 0.5 / sqrt(cj);
-            else dcj += se * Gm[i * ne + j + 1] * (double)tm[i * ne + j + 1] * 0.5 / sqrt(cj);
-            // t_j: direct through L[i][j], through c_j, and the tanh log-det
-            const double om = 1.0 - t * t;
-            const double dt = se * Gm[i * ne + j] * sqrt(cjm) + dcj * cjm * (-2.0 * t);
-            gy[j] = sign * (float)(dt * om - 2.0 * t);
-            dc = dcj * om;
-        }
+    }
+    __syncthreads();
+    for (int e = tid; e < Tr.n_corr; e += blockDim.x) {
+        int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)e)) * 0.5f);
+        while (i * (i - 1) / 2 > e) --i;
+        while ((i + 1) * i / 2 <= e) ++i;
+        const int j = e - i * (i - 1) / 2;
+        const int m = i * ne + j;
+        const float t = tm[m];
+        const float cjm = (j > 0) ? cum[m - 1] : 1.f;
+        const float se = Tr.sig[(size_t)c * ne + i];
+        gg[oY + e] = sign * (se * (float)Gm[m] * sqrtf(cjm) * (1.f - t * t) - 2.f * t * (scr[m] + 1.f));
     }
     if (tid == 0) {
         const float* sc = Tr.sc + (size_t)c * 8;

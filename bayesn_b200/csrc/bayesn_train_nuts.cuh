@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) train_nuts_sn_kernel(
     WarpCtx c;
     int sn, chain;
     const int C = Tr.C;
-    const bool active = cta_setup<LP, TP, false, STAGE>(M, Dd, C, ntile, smem, c, sn, chain);
+    const bool active = cta_setup<LP, TP, false, STAGE, true>(M, Dd, C, ntile, smem, c, sn, chain);
     if (!active) return;
     const int lane = threadIdx.x & 31;
     const size_t unit = (size_t)sn * C + chain;
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) train_nuts_sn_kernel(
 }
 
 // ------------------------------------------------------------------------------------------
-// per chain CTA (128 threads): globals + every scalar decision
+// per chain CTA (256 threads): globals + every scalar decision
 // ------------------------------------------------------------------------------------------
 struct GVec {
     float* base;   // [nvec][G]
@@ -248,7 +248,7 @@ __device__ __forceinline__ void gcopy(const GVec& W, int dst, int src) {
 
 // block-wide sums of NV per-thread partials (NV <= 32); every thread gets all totals in out[]
 template <int NV>
-__device__ __forceinline__ void block_sums(float (&v)[NV], float* sh /* [4][NV] */, float (&out)[NV]) {
+__device__ __forceinline__ void block_sums(float (&v)[NV], float* sh /* [8][NV] */, float (&out)[NV]) {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -270,10 +270,10 @@ __device__ __forceinline__ void block_sums(float (&v)[NV], float* sh /* [4][NV] 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(128) train_nuts_ctl_kernel(ModelDev M, TrainDev Tr, TrainNutsDev Nt, int LP, int TP,
+__global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDev Tr, TrainNutsDev Nt, int LP, int TP,
                                                              const double* __restrict__ red_all) {
     __shared__ TrainShared S;
-    __shared__ float shsum[4 * TRAIN_NX];
+    __shared__ float shsum[8 * TRAIN_NX];
     __shared__ TrainCtl sctl;
     const int c = blockIdx.x, tid = threadIdx.x;
     const int G = Tr.G;
@@ -297,7 +297,6 @@ __global__ void __launch_bounds__(128) train_nuts_ctl_kernel(ModelDev M, TrainDe
     __syncthreads();
     const double pe_new = -(red[0] + Tr.lpg[c]);
     const float eps = sctl.eps_dir;
-    const int act_prev = sctl.act;
     const int leaf = sctl.leaf;
     const int idx_max = __popc(leaf >> 1);
     const int idx_min = idx_max - (__ffs(~leaf) - 1) + 1;

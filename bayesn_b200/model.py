@@ -152,6 +152,45 @@ class SEDmodel(object):
         ctx.bind_dataset(packed)
         return ctx
 
+    def train(self, obs, weights, band_inds=None, num_chains=4, num_warmup=500, num_samples=500, max_tree_depth=10,
+              initialisation='M20_model', seed=0, group=None, outputdir=None, mode='training_globalRV',
+              progress=None):
+        """Population training with ``train_model_globalRV`` (reference :1115-1182) sampled by the
+        device-resident NUTS - what ``run`` does for ``mode: training_globalRV`` (:1766-1770,
+        :1913-1924): ``NUTS(step_size=0.1, target_accept_prob=0.8, dense_mass=False,
+        regularize_mass_matrix=False)``, every chain started from ``initial_guess`` (:1568-1654).
+
+        ``obs`` (10, N_obs, N) / ``weights`` are the FULL training set on every rank; with ``group``
+        (torch.distributed) each rank keeps a contiguous block of SNe, the per-leapfrog sums are
+        all-reduced over the group and the latent draws are gathered at the end.  Returns (samples
+        dict with the reference's site names, ``(chains, draws, ...)`` shapes; extras dict)."""
+        import torch
+        from . import train as btrain
+        from .distributed import shard_bounds
+        obs = np.asarray(obs)
+        N = obs.shape[-1]
+        rank, world = 0, 1
+        if group is not None:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        lo, hi = shard_bounds(N, rank, world)
+        ctx = self.prepare_training(obs[:, :, lo:hi], weights[lo:hi], band_inds)
+        dev = f'cuda:{ctx.device}'
+        qg0, ql0 = btrain.initial_position(self, obs, num_chains, initialisation, seed=seed, device=dev)
+        out = ctx.train_nuts(qg0, ql0[lo:hi].contiguous(), num_warmup=num_warmup, num_samples=num_samples,
+                             max_tree_depth=max_tree_depth, seed=seed, group=group, sn_offset=lo, progress=progress)
+        sl = out['samples_l']
+        if group is not None and world > 1:
+            from .distributed import gather_rows
+            sl = gather_rows(sl, N, group)           # device tensors: NCCL on GPUs
+        samples = btrain.constrain(self, out['samples_g'].cpu().numpy(), sl.cpu().numpy())
+        stats = out['stats'].cpu().numpy()
+        samples['potential_energy'] = stats[:, num_warmup:, 3]
+        extras = {'stats': stats, 'info': out['info'], 'passes': out['passes'], 'launches': ctx.launches()}
+        if outputdir is not None and rank == 0:
+            extras['yaml'], _ = btrain.postprocess_training(self, samples, outputdir, mode)
+        return samples, extras
+
     def prepare(self, obs, weights, band_inds=None, rv_mode=None, **fix):
         """Upload model + data set; returns the native context ready for ``logp_grad`` / ``nuts``.
         ``obs`` (10, N_obs, N) and ``weights`` (N, 300, n_b) use the reference layouts; the band

@@ -144,3 +144,60 @@ def test_two_rank_sharding_over_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0 and 'ok' in o, o
+
+
+def test_training_transforms_roundtrip_and_match_oracle():
+    """Host side of the training path: CorrCholesky forward/inverse, unconstrain -> constrain round
+    trip, and agreement with the oracle's (torch) restatement of numpyro's transform."""
+    import torch
+    from bayesn_b200 import SEDmodel, train as btrain
+    from oracle.ref_model import RefSED
+    m = SEDmodel(load_model='T21_model')
+    d = btrain.dims(m)
+    ne = d['n_eps']
+    rng = np.random.RandomState(3)
+    y = 0.4 * rng.randn(d['n_corr'])
+    Lo = btrain.corr_cholesky(y, ne)
+    assert np.allclose((Lo ** 2).sum(axis=1), 1.0) and np.allclose(np.triu(Lo, 1), 0.0)
+    Lo_t, _ = RefSED.corr_cholesky(torch.as_tensor(y), ne)
+    assert np.allclose(Lo, Lo_t.numpy(), atol=1e-14)
+    assert np.allclose(btrain.corr_cholesky_inverse(Lo), y, atol=1e-9)
+    obs = np.zeros((10, 4, 5))
+    obs[5], obs[7] = 0.03, 35.5
+    init = btrain.initial_values(m, obs, 'T21_model', rng)
+    qg, ql = btrain.unconstrain(m, init, 5, rng)
+    assert qg.shape == (d['G'],) and ql.shape == (5, d['Dl'])
+    c = btrain.constrain(m, qg[None, None], ql[:, None, None])
+    assert np.allclose(c['W0'][0, 0], init['W0']) and np.allclose(c['sigmaepsilon_tform'][0, 0], init['sigmaepsilon_tform'])
+    assert np.allclose(c['L_Omega'][0, 0], np.eye(ne), atol=1e-6) and np.isclose(c['RV'][0, 0], 3.0)
+    assert np.isclose(c['tauA_tform'][0, 0], init['tauA_tform']) and np.allclose(c['AV'][0, 0], init['AV'])
+    assert c['eps'].shape == (1, 1, ne, 5) and c['theta'].shape == (1, 1, 5)
+    # same constrained values as the oracle's unpacking of the same vector
+    g, _ = RefSED('T21_model', bands=['g_PS1']).train_unpack(torch.as_tensor(qg))
+    assert np.allclose(g['L_Sigma'].numpy(), c['sigmaepsilon'][0, 0][:, None] * c['L_Omega'][0, 0], atol=1e-12)
+    assert np.isclose(float(g['sigma0']), c['sigma0'][0, 0]) and np.isclose(float(g['tauA']), c['tauA'][0, 0])
+
+
+def test_training_postprocess_sign_and_scale(tmp_path):
+    """Reference postprocess :2186-2242: chains whose W1 has the opposite sign are flipped together
+    with theta, theta is rescaled to unit spread and bayesn.yaml carries the posterior means."""
+    import yaml
+    from bayesn_b200 import SEDmodel, train as btrain
+    m = SEDmodel(load_model='T21_model')
+    L, T = len(m.l_knots), len(m.tau_knots)
+    ne = (L - 2) * T
+    rng = np.random.RandomState(0)
+    C, S, N = 2, 6, 5
+    W1 = np.repeat(m.W1.flatten(order='F')[None, None], C, 0).repeat(S, 1)
+    W1[1] *= -1
+    theta = 2.0 * rng.randn(C, S, N)
+    samples = {'W0': np.repeat(m.W0.flatten(order='F')[None, None], C, 0).repeat(S, 1), 'W1': W1, 'theta': theta.copy(),
+               'sigmaepsilon': np.full((C, S, ne), 0.1), 'L_Omega': np.tile(np.eye(ne), (C, S, 1, 1)),
+               'sigma0': np.full((C, S), 0.1), 'tauA': np.full((C, S), 0.3), 'RV': np.full((C, S), 2.6)}
+    ydat, out = btrain.postprocess_training(m, samples, str(tmp_path))
+    assert np.allclose(np.std(out['theta'], axis=2), 1.0)
+    assert np.all(np.sign(out['W1'][1, 0]) == np.sign(out['W1'][0, 0]))
+    assert 'RV' not in ydat and np.isclose(ydat['TAUA'], 0.3)
+    back = yaml.safe_load(open(tmp_path / 'bayesn.yaml'))
+    assert np.allclose(back['W0'], m.W0) and np.allclose(back['L_SIGMA_EPSILON'], 0.1 * np.eye(ne))
+    assert (tmp_path / 'chains.pkl').exists() and (tmp_path / 'initial_chains.pkl').exists()
