@@ -400,6 +400,7 @@ int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_
     nd.adapt_step = cfg->adapt_step_size; nd.adapt_mass = cfg->adapt_mass_matrix;
     nd.regularize = cfg->regularize_mass_matrix;
     nd.seed_lo = (unsigned)(cfg->seed & 0xffffffffu); nd.seed_hi = (unsigned)(cfg->seed >> 32);
+    nd.unit_offset = (unsigned)cfg->unit_offset;
     std::vector<int> ends = adaptation_window_ends(cfg->num_warmup);
     if (ends.size() > 24) return fail(ctx, -1, "too many adaptation windows");
     nd.n_windows = (int)ends.size();
@@ -408,7 +409,7 @@ int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_
     return dispatch(ctx, /*stage=*/cfg->num_chains >= 2, call);
 }
 
-int bayesn_init_to_median(bayesn_ctx* ctx, int n_chains, uint64_t seed, float* q, void* stream) {
+int bayesn_init_to_median(bayesn_ctx* ctx, int n_chains, uint64_t seed, uint64_t unit_offset, float* q, void* stream) {
     if (!ctx) return -1;
     if (!ctx->have_model || !ctx->have_data) return fail(ctx, -1, "set_model and bind_dataset first");
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
@@ -416,6 +417,7 @@ int bayesn_init_to_median(bayesn_ctx* ctx, int n_chains, uint64_t seed, float* q
     A.N = ctx->D.N; A.C = n_chains; A.D = ctx->M.D; A.n_eps = ctx->M.n_eps; A.rv_mode = ctx->M.rv_mode;
     A.tauA = 1.f / ctx->M.inv_tauA; A.sdD = 1.f / sqrtf(ctx->M.inv_sd2); A.muhat = ctx->D.muhat;
     A.seed_lo = (unsigned)(seed & 0xffffffffu); A.seed_hi = (unsigned)(seed >> 32); A.q = q;
+    A.unit_offset = (unsigned)unit_offset;
     const long long total = (long long)A.N * A.C * A.D;
     init_median_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A);
     ctx->launches++;

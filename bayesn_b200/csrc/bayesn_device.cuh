@@ -66,6 +66,7 @@ struct NutsDev {
     float target_accept, init_step;
     int adapt_step, adapt_mass, regularize;
     unsigned seed_lo, seed_hi;
+    unsigned unit_offset;   // index of this launch's first (SN, chain) unit in the whole job: keys the random streams
     int n_windows;
     int win_end[24];
 };

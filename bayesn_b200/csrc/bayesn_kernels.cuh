@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
     const int nvec = nuts_num_vectors(cfg.max_depth);
     VecIO<VPL> io{work + unit * (size_t)nvec * 32 * VPL, lane};
     const uint2 key = make_uint2(cfg.seed_lo, cfg.seed_hi);
+    const uint32_t gunit = (uint32_t)unit + cfg.unit_offset;      // random streams do not depend on the sharding
     bool own[VPL];
 #pragma unroll
     for (int s = 0; s < VPL; ++s) own[s] = (lane + 32 * s) < D;
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
     auto begin_transition = [&]() {
         rk = 0;
         // momentum refresh r ~ N(0, M)
-        uint4 ra = philox4x32(make_uint4((uint32_t)it, 0x40000000u, (uint32_t)lane, (uint32_t)unit), key);
+        uint4 ra = philox4x32(make_uint4((uint32_t)it, 0x40000000u, (uint32_t)lane, gunit), key);
         float n0 = sqrtf(-2.f * logf(u01(ra.x) + 5.9604644775390625e-8f));
         float n1 = sqrtf(-2.f * logf(u01(ra.z) + 5.9604644775390625e-8f));
         float sn0, cs0, sn1, cs1;
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
         turning = false; diverging = false;
     };
     auto begin_doubling = [&]() {
-        uint4 rd = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, (uint32_t)unit), key);
+        uint4 rd = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, gunit), key);
         going_right = (rd.x >> 31) != 0;
         u_main = u01(rd.y);
         if (going_right) { io.ld(V_ZR, z); io.ld(V_RR, r); io.ld(V_GR, g); }
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
             for (int s = 0; s < VPL; ++s) ok = ok && isfinite(g[s]);
             ok = __all_sync(FULL, ok);
             if (!ok && init_tries < 100) {
-                uint4 ra = philox4x32(make_uint4((uint32_t)init_tries, 0x20000000u, (uint32_t)lane, (uint32_t)unit), key);
+                uint4 ra = philox4x32(make_uint4((uint32_t)init_tries, 0x20000000u, (uint32_t)lane, gunit), key);
                 float uu[4] = {u01(ra.x), u01(ra.y), u01(ra.z), u01(ra.w)};
 #pragma unroll
                 for (int s = 0; s < VPL; ++s) z[s] = own[s] ? (4.f * uu[s & 3] - 2.f) : 0.f;
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
             } else {
 #pragma unroll
                 for (int s = 0; s < VPL; ++s) rsum[s] += r[s];
-                uint4 rl = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, (uint32_t)unit), key);
+                uint4 rl = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, gunit), key);
                 const float tp = 1.f / (1.f + expf(-(leaf_w - w_sub)));   // uniform transition kernel
                 if (u01(rl.x) < tp) {
                     io.st(V_SZP, z); io.st(V_SGP, g);
@@ -478,7 +479,7 @@ struct InitArgs {
     int N, C, D, n_eps, rv_mode;
     float tauA, sdD;
     const float* muhat;
-    unsigned seed_lo, seed_hi;
+    unsigned seed_lo, seed_hi, unit_offset;
     float* q;
 };
 
@@ -506,7 +507,7 @@ __global__ void init_median_kernel(InitArgs A) {
     const int kind = (i < A.n_eps) ? 0 : (i - A.n_eps + 1);   // 0 eps, 1 theta, 2 AV, 3 tmax, 4 Ds, 5 RV
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-        uint4 ra = philox4x32(make_uint4((uint32_t)b, (uint32_t)i, 0x80000000u, (uint32_t)unit), key);
+        uint4 ra = philox4x32(make_uint4((uint32_t)b, (uint32_t)i, 0x80000000u, (uint32_t)unit + A.unit_offset), key);
         float u[4] = {u01(ra.x), u01(ra.y), u01(ra.z), u01(ra.w)};
         float n0 = sqrtf(-2.f * logf(u[0] + 5.9604644775390625e-8f));
         float n1 = sqrtf(-2.f * logf(u[2] + 5.9604644775390625e-8f));

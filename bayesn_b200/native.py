@@ -37,7 +37,7 @@ class NutsCfg(C.Structure):
     _fields_ = [('num_warmup', C.c_int32), ('num_samples', C.c_int32), ('num_chains', C.c_int32),
                 ('max_tree_depth', C.c_int32), ('target_accept', C.c_float), ('init_step_size', C.c_float),
                 ('adapt_step_size', C.c_int32), ('adapt_mass_matrix', C.c_int32),
-                ('regularize_mass_matrix', C.c_int32), ('seed', C.c_uint64)]
+                ('regularize_mass_matrix', C.c_int32), ('seed', C.c_uint64), ('unit_offset', C.c_uint64)]
 
 
 EXPORTS = ['bayesn_abi_version', 'bayesn_ctx_create', 'bayesn_ctx_destroy', 'bayesn_last_error',
@@ -75,7 +75,7 @@ def load_library():
     lib.bayesn_nuts_workspace_bytes.restype = C.c_size_t
     lib.bayesn_nuts_fit.argtypes = [C.c_void_p, C.POINTER(NutsCfg)] + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]
     lib.bayesn_launch_count.argtypes = [C.c_void_p]
-    lib.bayesn_init_to_median.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.bayesn_init_to_median.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.bayesn_ffma_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.bayesn_launch_count.restype = C.c_longlong
     lib.bayesn_train_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
@@ -170,13 +170,14 @@ class Context:
         import torch
         return torch.cuda.current_stream().cuda_stream
 
-    def init_to_median(self, n_chains, seed=0, out=None):
+    def init_to_median(self, n_chains, seed=0, out=None, sn_offset=0):
         """Initial unconstrained positions (N, C, D) for the bound data set (device kernel)."""
         import torch
         if out is None:
             out = torch.empty((self.N, n_chains, self.D), dtype=torch.float32, device=f'cuda:{self.device}')
         self._check(self.lib.bayesn_init_to_median(self.h, int(n_chains), int(seed) & 0xFFFFFFFFFFFFFFFF,
-                                                   out.data_ptr(), self._stream()), 'bayesn_init_to_median')
+                                                   int(sn_offset) * int(n_chains), out.data_ptr(), self._stream()),
+                    'bayesn_init_to_median')
         return out
 
     def ffma_peak_tflops(self):
@@ -198,7 +199,7 @@ class Context:
 
     def nuts(self, q_init, num_warmup=250, num_samples=250, max_tree_depth=10, target_accept=0.8,
              init_step_size=1.0, adapt_step_size=True, adapt_mass_matrix=True, regularize_mass_matrix=True, seed=0,
-             out=None):
+             out=None, sn_offset=0):
         """Run the device NUTS for every (SN, chain).  Returns dict of CUDA tensors."""
         import torch
         assert q_init.is_cuda and q_init.dtype == torch.float32 and q_init.is_contiguous()
@@ -206,7 +207,7 @@ class Context:
         assert N == self.N and D == self.D
         cfg = NutsCfg(int(num_warmup), int(num_samples), int(Cn), int(max_tree_depth), float(target_accept),
                       float(init_step_size), int(adapt_step_size), int(adapt_mass_matrix),
-                      int(regularize_mass_matrix), int(seed) & 0xFFFFFFFFFFFFFFFF)
+                      int(regularize_mass_matrix), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sn_offset) * int(Cn))
         wb = int(self.lib.bayesn_nuts_workspace_bytes(self.h, C.byref(cfg)))
         dev = q_init.device
         if out is None:
@@ -285,7 +286,7 @@ class Context:
         dev = qg0.device
         cfg = NutsCfg(int(num_warmup), int(num_samples), int(Cn), int(max_tree_depth), float(target_accept),
                       float(init_step_size), int(adapt_step_size), int(adapt_mass_matrix),
-                      int(regularize_mass_matrix), int(seed) & 0xFFFFFFFFFFFFFFFF)
+                      int(regularize_mass_matrix), int(seed) & 0xFFFFFFFFFFFFFFFF, 0)
         out = dict(samples_g=torch.zeros((Cn, num_samples, G), dtype=torch.float32, device=dev),
                    samples_l=torch.zeros((N, Cn, num_samples, Dl), dtype=torch.float32, device=dev),
                    stats=torch.zeros((Cn, num_warmup + num_samples, 5), dtype=torch.float32, device=dev))

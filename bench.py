@@ -201,6 +201,10 @@ def run_ours(args):
     e2e_value = world * n_sne * e2e_steps / float(t.item())
 
     extra = {}
+    if not args.no_train:
+        tr = train_leg(args, dev, rank, world)       # every rank takes part (SNe sharded, all-reduce per leapfrog)
+        if rank == 0:
+            extra['training'] = tr
     if rank == 0:
         # ---- roofline of the dominant kernel (the persistent NUTS kernel) -------------------------
         L, T = len(model.l_knots), len(model.tau_knots)
@@ -243,6 +247,71 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def train_leg(args, dev, rank, world):
+    """Config C4: M20 population training, 500 simulated SNe x 84 obs (CSP/RC bands),
+    4 chains, train_model_globalRV sampled by the device-resident sharded NUTS; SNe are sharded over the
+    ranks (strong scaling) and the per-leapfrog sums are all-reduced with NCCL.  Shortened run
+    (warm-up + draws stated in the output); the unit is one leapfrog step of all 4 chains."""
+    import torch
+    import torch.distributed as dist
+    from bayesn_b200 import SEDmodel, train as btrain
+    from bayesn_b200.distributed import shard_bounds
+    n_total, C, W, S = args.train_n, 4, args.train_warmup, args.train_samples
+    m = SEDmodel(load_model='M20_model', device=dev)
+    obs, weights, band_inds = btrain.simulate_training_set(m, n_total, seed=20241019)
+    lo, hi = shard_bounds(n_total, rank, world)
+    ctx = m.prepare_training(obs[:, :, lo:hi], weights[lo:hi], band_inds)
+    qg0, ql0 = btrain.initial_position(m, obs, C, 'M20_model', seed=1, device=dev)
+    group = dist.group.WORLD if world > 1 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = ctx.train_nuts(qg0, ql0[lo:hi].contiguous(), num_warmup=W, num_samples=S, max_tree_depth=10, seed=2, group=group,
+                         sn_offset=lo)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    st = out['stats'].cpu().numpy()
+    res = {'workload': f'C4: M20_model train_model_globalRV, {n_total} simulated SNe x {obs.shape[1]} obs sharded over {world} '
+                       f'GPU(s), {C} chains x ({W}+{S}) (nominal 500+500; shortened), max_tree_depth 10, NUTS step_size 0.1',
+           'seconds': dt, 'passes': out['passes'], 'us_per_leapfrog_pass': dt / out['passes'] * 1e6,
+           'leapfrog_passes_per_s': out['passes'] / dt, 'sn_evals_per_s': out['passes'] * n_total * C / dt,
+           'gpu_launches': 3 * out['passes'] + 2,        # SN + reduction + control kernel per pass (CUDA-graph replays included) 'allreduce_doubles_per_pass': (C * ctx.train_dims()[2]) if world > 1 else 0,
+           'mean_accept_sampling': float(st[:, W:, 0].mean()), 'divergences': float(out['info'][:, 5].sum()),
+           'finished': out['finished']}
+    if rank == 0 and not args.no_train_cpu:
+        from oracle.ref_model import RefSED
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+        bands = ['B_CSP', 'V_CSP', 'r_CSP', 'i_CSP', 'Y_RC', 'J_RC1', 'H_RC']
+        ref = RefSED('M20_model', bands=bands)
+        from bayesn_b200 import datafiles
+        fd = datafiles.load_yaml(os.path.join(datafiles.FILTER_DIR, 'filters.yaml'))
+        all_names = ['NULL_BAND'] + list(fd['filters'].keys())
+        remap = np.array([ref.band_dict[all_names[i]] for i in band_inds])
+        o = np.array(obs)
+        o[4] = remap[o[4].astype(int)]
+        w = np.zeros((n_total, 300, len(ref.band_dict)))
+        w[:, :, remap] = weights
+        qg = qg0[0].cpu().numpy().astype(np.float64)
+        ql = ql0[:, 0].cpu().numpy().astype(np.float64)
+        ref.train_logp_grad(qg, ql, o, w)
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 6.0:
+            ref.train_logp_grad(qg, ql, o, w)
+            n += 1
+        cdt = time.perf_counter() - t0
+        res['cpu_baseline'] = {'value': n / cdt / 1.0, 'unit': 'joint log p + gradient evaluations/s (one chain)',
+                               'cores': torch.get_num_threads(), 'kind': 'port',
+                               'sample': f'{n} evaluations of the float64 oracle train_logp_grad over {n_total} SNe',
+                               'sn_evals_per_s': n * n_total / cdt}
+        res['speedup_vs_cpu_port_sn_evals'] = res['sn_evals_per_s'] / res['cpu_baseline']['sn_evals_per_s']
+    return res
+
+
 def micro_logp(model, ctx_fit, args, dev, F, peak):
     """Config C2: fused log p + gradient over N simulated SNe x 40 obs, one evaluation each."""
     import torch
@@ -273,8 +342,8 @@ def oracle_evals_per_s(obs, weights, band_inds_names, rows, seconds, threads=Non
     """Time the float64 oracle's batched log p + gradient (torch autograd) on the host cores."""
     import torch
     from oracle.ref_model import RefSED
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores this process may use (torchrun pins OMP_NUM_THREADS=1 by default)
+    torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
     ref = RefSED(MODEL, bands=BANDS)
     # oracle band order = YAML order; remap the product's compact band indices
     names = band_inds_names
@@ -324,6 +393,7 @@ def run_reference(args):
     # inputs: the same simulate_light_curve recipe, produced by the oracle itself on the CPU
     from oracle.ref_model import RefSED
     import torch
+    torch.set_num_threads(len(os.sched_getaffinity(0)))      # torchrun pins OMP_NUM_THREADS=1 by default
     ref = RefSED(MODEL, bands=BANDS)
     rows = 256
     np.random.seed(20241019)
@@ -378,6 +448,11 @@ def main():
     ap.add_argument('--no-micro', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--write-consts', action='store_true')
+    ap.add_argument('--no-train', action='store_true')
+    ap.add_argument('--no-train-cpu', action='store_true')
+    ap.add_argument('--train-n', type=int, default=500)
+    ap.add_argument('--train-warmup', type=int, default=40)
+    ap.add_argument('--train-samples', type=int, default=20)
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

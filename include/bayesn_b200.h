@@ -98,6 +98,9 @@ typedef struct {
     float target_accept, init_step_size;
     int32_t adapt_step_size, adapt_mass_matrix, regularize_mass_matrix;
     uint64_t seed;
+    uint64_t unit_offset;   /* index of this data set's first (SN, chain) unit in the whole job (first SN *
+                             * num_chains): random streams are keyed by the global unit, so sharding
+                             * SNe over GPUs reproduces the single-GPU draws bit for bit */
 } bayesn_nuts_cfg;
 
 int bayesn_ctx_create(int device, bayesn_ctx** out);
@@ -188,7 +191,7 @@ int bayesn_train_nuts_status(bayesn_ctx* ctx, float* out, void* stream);
 
 /* numpyro init_to_median(num_samples=15) (reference bayesn/bayesn_model.py:1757, :2110): initial
  * unconstrained positions q [N][n_chains][D] (device, out) for the bound data set. */
-int bayesn_init_to_median(bayesn_ctx* ctx, int n_chains, uint64_t seed, float* q, void* stream);
+int bayesn_init_to_median(bayesn_ctx* ctx, int n_chains, uint64_t seed, uint64_t unit_offset, float* q, void* stream);
 
 /* FP32 FMA peak of this device in TFLOP/s, measured with an FFMA-only kernel: the roofline
  * denominator for the SIMT kernels (no reference counterpart; measurement aid). */
