@@ -9,6 +9,7 @@
 #include "bayesn_kernels.cuh"
 #include "bayesn_train.cuh"
 #include "bayesn_train_nuts.cuh"
+#include "bayesn_tiles.cuh"
 
 using namespace bayesn;
 
@@ -620,6 +621,45 @@ int bayesn_train_nuts_status(bayesn_ctx* ctx, float* out, void* stream) {
         done += h[c].phase == 2;
     }
     return done == C ? 1 : 0;
+}
+
+
+static int tiles_dev(bayesn_ctx* ctx, const bayesn_tiles_desc* d, TilesDev& T) {
+    if (!ctx || !d) return -1;
+    if (d->N <= 0 || d->n_b <= 0 || d->n_b > 32 || d->n_bw < 300 * 51 + 2) return fail(ctx, -1, "bad tile description");
+    T.N = d->N; T.n_b = d->n_b; T.n_bw = d->n_bw;
+    T.master = d->master; T.z = d->z; T.ebv = d->ebv; T.fold = d->fold; T.bscale = d->bscale; T.used = d->used;
+    T.model_wave = d->model_wave; T.band_spacing = d->band_spacing; T.RV_MW = d->RV_MW;
+    for (int i = 0; i < 9; ++i) { T.xk[i] = d->f99_xk[i]; T.yk[i] = d->f99_yk[i]; T.mk[i] = d->f99_mk[i]; }
+    return 0;
+}
+
+int bayesn_tiles_support(bayesn_ctx* ctx, const bayesn_tiles_desc* d, int32_t* support, int32_t* total_width,
+                         void* stream) {
+    TilesDev T{};
+    if (int rc = tiles_dev(ctx, d, T)) return rc;
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long units = (long long)T.N * T.n_b;
+    tiles_support_kernel<<<(unsigned)((units + 3) / 4), 128, 0, st>>>(T, reinterpret_cast<int4*>(support));
+    tiles_offsets_kernel<<<(T.N + 255) / 256, 256, 0, st>>>(T.N, T.n_b, reinterpret_cast<int4*>(support), total_width);
+    ctx->launches += 2;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+int bayesn_tiles_fill(bayesn_ctx* ctx, const bayesn_tiles_desc* d, const int32_t* support, int wt_stride,
+                      float* weights, void* stream) {
+    TilesDev T{};
+    if (int rc = tiles_dev(ctx, d, T)) return rc;
+    if (wt_stride <= 0 || wt_stride % 4) return fail(ctx, -1, "wt_stride must be a positive multiple of 4");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    const long long units = (long long)T.N * T.n_b;
+    tiles_fill_kernel<<<(unsigned)((units + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+        T, reinterpret_cast<const int4*>(support), wt_stride, weights);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
 }
 
 }  // extern "C"

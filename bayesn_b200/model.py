@@ -146,9 +146,11 @@ class SEDmodel(object):
         if band_inds is None:
             band_inds = np.arange(weights.shape[2])
         ctx = self._context(native.RV_FIXED)
+        builder = packing.DeviceTileBuilder(ctx, self.filters, band_inds, self.RV_MW) if weights is None else None
         packed = packing.pack_dataset(obs, weights, self.zps[band_inds], self.offsets[band_inds], self.M0,
                                       math.sqrt(25.0 + self.sigma0 ** 2), self.tauA, self.n_eps,
-                                      device=f'cuda:{ctx.device}', train=True, sigma_pec=self.sigma_pec)
+                                      device=f'cuda:{ctx.device}', train=True, sigma_pec=self.sigma_pec,
+                                      builder=builder)
         ctx.bind_dataset(packed)
         return ctx
 
@@ -201,9 +203,12 @@ class SEDmodel(object):
         if band_inds is None:
             band_inds = np.arange(weights.shape[2])
         ctx = self._context(rv_mode, **fix)
+        # weights=None: the per-SN band weights (reference _calculate_band_weights :499-554) are built
+        # on the device straight into the packed tiles, from obs[-5] (z) and obs[-2] (E(B-V)_MW)
+        builder = packing.DeviceTileBuilder(ctx, self.filters, band_inds, self.RV_MW) if weights is None else None
         packed = packing.pack_dataset(obs, weights, self.zps[band_inds], self.offsets[band_inds], self.M0,
                                       math.sqrt(25.0 + self.sigma0 ** 2), self.tauA, self.n_eps,
-                                      device=f'cuda:{ctx.device}')
+                                      device=f'cuda:{ctx.device}', builder=builder)
         ctx.bind_dataset(packed)
         return ctx
 

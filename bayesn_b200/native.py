@@ -33,6 +33,14 @@ class DatasetDesc(C.Structure):
                 ('muhat', C.c_void_p), ('lconst', C.c_void_p), ('muhat_err2', C.c_void_p)]
 
 
+class TilesDesc(C.Structure):
+    _fields_ = [('N', C.c_int32), ('n_b', C.c_int32), ('n_bw', C.c_int32),
+                ('master', C.c_void_p), ('z', C.c_void_p), ('ebv', C.c_void_p), ('fold', C.c_void_p),
+                ('bscale', C.c_void_p), ('used', C.c_void_p), ('model_wave', C.c_void_p),
+                ('band_spacing', C.c_double), ('RV_MW', C.c_double),
+                ('f99_xk', C.c_double * 9), ('f99_yk', C.c_double * 9), ('f99_mk', C.c_double * 9)]
+
+
 class NutsCfg(C.Structure):
     _fields_ = [('num_warmup', C.c_int32), ('num_samples', C.c_int32), ('num_chains', C.c_int32),
                 ('max_tree_depth', C.c_int32), ('target_accept', C.c_float), ('init_step_size', C.c_float),
@@ -45,7 +53,7 @@ EXPORTS = ['bayesn_abi_version', 'bayesn_ctx_create', 'bayesn_ctx_destroy', 'bay
            'bayesn_flux_batch', 'bayesn_nuts_workspace_bytes', 'bayesn_nuts_fit', 'bayesn_launch_count',
            'bayesn_init_to_median', 'bayesn_ffma_peak', 'bayesn_train_dims', 'bayesn_train_begin',
            'bayesn_train_finish', 'bayesn_train_nuts_init', 'bayesn_train_nuts_sn', 'bayesn_train_nuts_ctl',
-           'bayesn_train_nuts_status']
+           'bayesn_train_nuts_status', 'bayesn_tiles_support', 'bayesn_tiles_fill']
 
 _lib = None
 
@@ -78,6 +86,8 @@ def load_library():
     lib.bayesn_init_to_median.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.bayesn_ffma_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.bayesn_launch_count.restype = C.c_longlong
+    lib.bayesn_tiles_support.argtypes = [C.c_void_p, C.POINTER(TilesDesc), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bayesn_tiles_fill.argtypes = [C.c_void_p, C.POINTER(TilesDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.bayesn_train_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
     lib.bayesn_train_begin.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
     lib.bayesn_train_finish.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
@@ -224,6 +234,26 @@ class Context:
                                              out['stats'].data_ptr(), out['chain_info'].data_ptr(), ws.data_ptr(),
                                              ws.numel() * 4, self._stream()), 'bayesn_nuts_fit')
         return out
+
+    # ------------------------------------------------------------------ band-weight tiles on the device
+    def tiles_desc(self, N, n_b, dev, builder):
+        d = TilesDesc()
+        d.N, d.n_b, d.n_bw = int(N), int(n_b), int(dev['master'].shape[1])
+        for k in ('master', 'z', 'ebv', 'fold', 'bscale', 'used', 'model_wave'):
+            setattr(d, k, dev[k].data_ptr())
+        d.band_spacing, d.RV_MW = builder.band_spacing, builder.RV_MW
+        for i in range(9):
+            d.f99_xk[i], d.f99_yk[i], d.f99_mk[i] = float(builder.xk[i]), float(builder.yk[i]), float(builder.mk[i])
+        self._keep['tiles'] = dev
+        return d
+
+    def tiles_support(self, desc, support, total):
+        self._check(self.lib.bayesn_tiles_support(self.h, C.byref(desc), support.data_ptr(), total.data_ptr(),
+                                                  self._stream()), 'bayesn_tiles_support')
+
+    def tiles_fill(self, desc, support, wt_stride, weights):
+        self._check(self.lib.bayesn_tiles_fill(self.h, C.byref(desc), support.data_ptr(), int(wt_stride),
+                                               weights.data_ptr(), self._stream()), 'bayesn_tiles_fill')
 
     # ------------------------------------------------------------------ training
     def train_dims(self):

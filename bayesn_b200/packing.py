@@ -13,51 +13,12 @@ def band_log10_scale(zps, offsets):
     return 0.4 * (27.5 - np.asarray(offsets, dtype=np.float64)) - np.asarray(zps, dtype=np.float64) / 2.5
 
 
-def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, device='cuda', chunk=8192, train=False,
-                 sigma_pec=150 / 3e5):
-    """Returns a dict of torch tensors on ``device``.
-
-    * valid (mask != 0) observations are moved to the front of each SN; ``n_valid`` counts them;
-    * the band scale 10^(0.4(27.5-offset) - zp/2.5 - 0.4(M0 + muhat)) is folded into the weight
-      tile in float64 before rounding to float32, so the kernel never forms 10^27-sized factors;
-    * ``support`` is the exact non-zero extent of each (SN, band) row and the offset of that row
-      in the SN's compact weight tile (only bands the SN was observed in are stored);
-    * ``lconst`` collects every parameter-independent term of the log joint density.
-
-    ``train=True`` packs a training set (``train_model_globalRV``, reference :1153-1182): ``obs[1]``
-    / ``obs[2]`` are magnitudes and their errors, the Ds prior width and tau_A are sampled (their
-    terms are evaluated on the device) and ``muhat_err2`` carries (5/(z ln10))^2 (z_err^2 + sigma_pec^2).
-    """
+def _tiles_on_host(weights, used, fold, bscale, M0, device, chunk):
+    """Compact float32 weight tiles from the reference-layout (N, 300, n_b) float64 array."""
     import torch
-    obs = np.asarray(obs, dtype=np.float64)
-    N_obs, N = obs.shape[1], obs.shape[2]
-    n_b = weights.shape[2]
-    assert weights.shape[0] == N and weights.shape[1] == NBINS
-    t, y, sig = obs[0].T, obs[1].T, obs[2].T
-    band = np.rint(obs[-6].T).astype(np.int32)
-    mask = obs[-1].T != 0
-    muhat = np.ascontiguousarray(obs[-3, 0, :])
-    if np.any(mask & ((band < 0) | (band >= n_b))):
-        raise ValueError('band index out of range of the weights array')
-    bscale = band_log10_scale(zps, offsets)
-    assert bscale.shape[0] == n_b
-    # the kernels carry the distance as Ds - float32(muhat): fold exactly that rounded muhat into the
-    # weights, otherwise every flux of the SN is off by the rounding (2e-6 mag, which the
-    # magnitude-space training gradient amplifies by n_obs / sigma^2)
-    muhat_f32 = muhat.astype(np.float32).astype(np.float64)
-    if train:
-        # magnitudes relative to the SN's mean magnitude (see eval_logp_grad, TRAIN branch)
-        nval = np.maximum(mask.sum(axis=1), 1)
-        ybar = (np.where(mask, y, 0.0).sum(axis=1) / nval).astype(np.float32).astype(np.float64)
-        y = y - ybar[:, None]
-        fold = muhat_f32 - (ybar - 27.5)
-    else:
-        fold = muhat_f32
+    N, n_b = used.shape
     # exact non-zero extent of every (SN, band) weight row after rounding to float32; bands without
     # a valid observation of that SN (always the NULL band 0) get an empty row
-    used = np.zeros((N, n_b), dtype=bool)
-    rows = np.repeat(np.arange(N), N_obs)
-    used[rows[mask.ravel()], band.ravel()[mask.ravel()]] = True
     sup_h = np.zeros((N, n_b, 4), dtype=np.int32)
     tiles = []
     bins = np.arange(NBINS)[None, None, :]
@@ -90,7 +51,99 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
     for tile in tiles:
         wt[s0:s0 + tile.shape[0], :tile.shape[1]] = torch.from_numpy(tile).to(device)
         s0 += tile.shape[0]
-    del tiles
+    return sup_h, wt, wt_store, wt_stride
+
+
+class DeviceTileBuilder:
+    """Everything the device band-weight builder needs from the host model (reference
+    ``_calculate_band_weights`` :499-554): the master curves of the bands in play, the model grid
+    and the Milky Way F99 spline at R_V = 3.1."""
+
+    def __init__(self, ctx, filters, band_inds, RV_MW=3.1):
+        from .static import F99_XK, f99_yk, inv_kd
+        self.ctx = ctx
+        self.master = np.ascontiguousarray(filters.master[np.asarray(band_inds)], dtype=np.float64)
+        self.model_wave = np.ascontiguousarray(filters.grid.model_wave, dtype=np.float64)
+        self.band_spacing = float(filters.grid.band_spacing)
+        self.RV_MW = float(RV_MW)
+        yk, _ = f99_yk(np.float64(RV_MW))
+        self.xk, self.yk, self.mk = F99_XK.copy(), np.asarray(yk), inv_kd(F99_XK) @ yk
+
+
+def _tiles_on_device(builder, obs, used, fold, bscale, device):
+    """Compact tiles straight from (z, E(B-V)) on the GPU: no (N, 300, n_b) array anywhere."""
+    import torch
+    N, n_b = used.shape
+    f64 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
+    bits = (used.astype(np.uint64) << np.arange(n_b, dtype=np.uint64)[None, :]).sum(axis=1).astype(np.uint32)
+    dev = dict(master=f64(builder.master), z=f64(obs[-5, 0, :]), ebv=f64(obs[-2, 0, :]), fold=f64(fold),
+               bscale=f64(bscale), used=torch.as_tensor(bits.view(np.int32), device=device),
+               model_wave=f64(builder.model_wave))
+    sup = torch.zeros((N, n_b, 4), dtype=torch.int32, device=device)
+    total = torch.zeros(N, dtype=torch.int32, device=device)
+    desc = builder.ctx.tiles_desc(N, n_b, dev, builder)
+    builder.ctx.tiles_support(desc, sup, total)
+    wt_stride = max(4, -(-int(total.max().item()) // 4) * 4)
+    wt_store = torch.zeros(N * wt_stride + OVERRUN + 32, dtype=torch.float32, device=device)
+    wt = wt_store[:N * wt_stride].view(N, wt_stride)
+    builder.ctx.tiles_fill(desc, sup, wt_stride, wt)
+    torch.cuda.synchronize()
+    return sup.cpu().numpy(), wt, wt_store, wt_stride
+
+
+def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, device='cuda', chunk=8192, train=False,
+                 sigma_pec=150 / 3e5, builder=None):
+    """Returns a dict of torch tensors on ``device``.
+
+    * valid (mask != 0) observations are moved to the front of each SN; ``n_valid`` counts them;
+    * the band scale 10^(0.4(27.5-offset) - zp/2.5 - 0.4(M0 + muhat)) is folded into the weight
+      tile in float64 before rounding to float32, so the kernel never forms 10^27-sized factors;
+    * ``support`` is the exact non-zero extent of each (SN, band) row and the offset of that row
+      in the SN's compact weight tile (only bands the SN was observed in are stored);
+    * ``lconst`` collects every parameter-independent term of the log joint density.
+
+    ``weights=None`` with a :class:`DeviceTileBuilder` builds the tiles on the GPU from the redshifts
+    and Milky Way reddenings in ``obs`` (``_calculate_band_weights`` + packing in one kernel pair).
+
+    ``train=True`` packs a training set (``train_model_globalRV``, reference :1153-1182): ``obs[1]``
+    / ``obs[2]`` are magnitudes and their errors, the Ds prior width and tau_A are sampled (their
+    terms are evaluated on the device) and ``muhat_err2`` carries (5/(z ln10))^2 (z_err^2 + sigma_pec^2).
+    """
+    import torch
+    obs = np.asarray(obs, dtype=np.float64)
+    N_obs, N = obs.shape[1], obs.shape[2]
+    n_b = len(zps)
+    assert weights is None or (weights.shape[0] == N and weights.shape[1] == NBINS and weights.shape[2] == n_b)
+    assert weights is not None or builder is not None
+    t, y, sig = obs[0].T, obs[1].T, obs[2].T
+    band = np.rint(obs[-6].T).astype(np.int32)
+    mask = obs[-1].T != 0
+    muhat = np.ascontiguousarray(obs[-3, 0, :])
+    if np.any(mask & ((band < 0) | (band >= n_b))):
+        raise ValueError('band index out of range of the weights array')
+    bscale = band_log10_scale(zps, offsets)
+    assert bscale.shape[0] == n_b
+    # the kernels carry the distance as Ds - float32(muhat): fold exactly that rounded muhat into the
+    # weights, otherwise every flux of the SN is off by the rounding (2e-6 mag, which the
+    # magnitude-space training gradient amplifies by n_obs / sigma^2)
+    muhat_f32 = muhat.astype(np.float32).astype(np.float64)
+    if train:
+        # magnitudes relative to the SN's mean magnitude (see eval_logp_grad, TRAIN branch)
+        nval = np.maximum(mask.sum(axis=1), 1)
+        ybar = (np.where(mask, y, 0.0).sum(axis=1) / nval).astype(np.float32).astype(np.float64)
+        y = y - ybar[:, None]
+        fold = muhat_f32 - (ybar - 27.5)
+    else:
+        fold = muhat_f32
+    if weights is None:
+        fold = fold + M0              # the device builder takes the whole per-SN exponent
+    used = np.zeros((N, n_b), dtype=bool)
+    rows = np.repeat(np.arange(N), N_obs)
+    used[rows[mask.ravel()], band.ravel()[mask.ravel()]] = True
+    if weights is None:
+        sup_h, wt, wt_store, wt_stride = _tiles_on_device(builder, obs, used, fold, bscale, device)
+    else:
+        sup_h, wt, wt_store, wt_stride = _tiles_on_host(weights, used, fold, bscale, M0, device, chunk)
     # valid observations first, widest band support first: the kernel processes observations in
     # pairs (one per half-warp) and a pair costs as many rounds as its wider member
     band_c = np.clip(band, 0, n_b - 1)
@@ -116,7 +169,8 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
         lconst += -half_l2pi * (1 + n_eps) - math.log(tauA) - math.log(Ds_prior_sd) - half_l2pi
         muhat_err2 = None
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
-    return dict(N=N, N_obs=N_obs, n_b=n_b, wt_stride=wt_stride, obs4=to(obs4), n_valid=to(n_valid), weights=wt, support=to(sup_h),
+    return dict(N=N, N_obs=N_obs, n_b=n_b, wt_stride=wt_stride, obs4=to(obs4), n_valid=to(n_valid), weights=wt,
+                support=to(np.ascontiguousarray(sup_h)),
                 muhat=to(muhat.astype(np.float32)), lconst=to(lconst.astype(np.float32)),
                 muhat64=muhat, order=order, _weights_storage=wt_store,
                 muhat_err2=None if muhat_err2 is None else to(muhat_err2.astype(np.float32)))

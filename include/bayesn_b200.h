@@ -189,6 +189,36 @@ int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream);
 int bayesn_train_nuts_ctl(bayesn_ctx* ctx, const double* red, void* stream);
 int bayesn_train_nuts_status(bayesn_ctx* ctx, float* out, void* stream);
 
+/* Per-SN band-weight tiles built on the device: SEDmodel._calculate_band_weights
+ * (bayesn/bayesn_model.py:499-554: redshifted linear interpolation of the x51-oversampled band master
+ * curves onto the 300 model bins, normalisation, Fitzpatrick99 Milky Way dust at R_V = 3.1, 1/(1+z))
+ * followed by the scale folding / float32 rounding / support compaction of bayesn_dataset_desc.weights
+ * - without ever materialising the (N, 300, n_b) float64 array.  All pointers are DEVICE pointers.
+ *   master [n_b][n_bw]  band_interpolate_weights rows of the bands in play (column 0 = NULL band)
+ *   z, ebv, fold [N]    redshift, Milky Way E(B-V), and M0 + float32(muhat_s) (training: minus
+ *                       (ybar_s - 27.5)); the log10 scale of (s, k) is bscale[k] - 0.4 fold[s]
+ *   used [N]            bit k set <=> SN s has a valid observation in band k (other rows stay empty)
+ *   f99_xk/yk/mk        knots (1/micron), knot values and second derivatives of the F99 k(lambda-V) spline at R_V,MW
+ * bayesn_tiles_support fills support [N][n_b][4] = {first, last, offset, 0} and total_width [N]; the
+ * caller allocates weights [N][wt_stride] (+ BAYESN_OVERRUN floats), wt_stride = max total_width
+ * rounded up to a multiple of 4 and zero-initialised, and calls bayesn_tiles_fill. */
+typedef struct {
+    int32_t N, n_b, n_bw;
+    const double* master;
+    const double* z;
+    const double* ebv;
+    const double* fold;
+    const double* bscale;
+    const uint32_t* used;
+    const double* model_wave;
+    double band_spacing, RV_MW;
+    double f99_xk[9], f99_yk[9], f99_mk[9];
+} bayesn_tiles_desc;
+int bayesn_tiles_support(bayesn_ctx* ctx, const bayesn_tiles_desc* desc, int32_t* support, int32_t* total_width,
+                         void* stream);
+int bayesn_tiles_fill(bayesn_ctx* ctx, const bayesn_tiles_desc* desc, const int32_t* support, int wt_stride,
+                      float* weights, void* stream);
+
 /* numpyro init_to_median(num_samples=15) (reference bayesn/bayesn_model.py:1757, :2110): initial
  * unconstrained positions q [N][n_chains][D] (device, out) for the bound data set. */
 int bayesn_init_to_median(bayesn_ctx* ctx, int n_chains, uint64_t seed, uint64_t unit_offset, float* q, void* stream);

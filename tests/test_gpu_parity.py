@@ -277,3 +277,38 @@ def test_c1_posterior_parity_with_cpu_oracle_sampler():
     # and the fits recover the simulated truth
     zsc = (samples['theta'].reshape(-1, 10).mean(axis=0) - d['true_theta']) / samples['theta'].reshape(-1, 10).std(axis=0)
     assert np.all(np.abs(zsc) < 4)
+
+
+@pytest.mark.parametrize('model,bands,train', [
+    ('W22_model', C2_BANDS, False),
+    ('W22_model', ['u_LSST', 'g_LSST', 'r_LSST', 'i_LSST', 'z_LSST', 'y_LSST'], False),
+    ('M20_model', ['B_CSP', 'V_CSP', 'r_CSP', 'i_CSP', 'Y_RC', 'J_RC1', 'H_RC'], True),
+])
+def test_device_tile_builder_matches_host_band_weights(model, bands, train):
+    """The device band-weight builder (reference _calculate_band_weights :499-554 + packing) against
+    the host float64 path: identical supports and offsets, float32 tiles equal to the last bit but
+    for libm rounding (<= 1 ulp on a handful of elements), and the same log p."""
+    from bayesn_b200 import SEDmodel, packing
+    N = 300
+    case = make_case(model, bands, np.arange(-8, 40, 6.0), N=N, seed=21, mag=train, mask_some=True, ebv_mw=0.0)
+    rng = np.random.RandomState(2)
+    ebv = rng.uniform(0.0, 0.15, N)
+    case['obs'][8] = ebv[None, :]
+    m, bi = product_model(case)
+    w_host = m._calculate_band_weights(case['z'], ebv, bi)
+    prep = m.prepare_training if train else m.prepare
+    c_host = prep(case['obs'], w_host, bi)
+    c_dev = prep(case['obs'], None, bi)
+    ph, pd = c_host._keep['data'], c_dev._keep['data']
+    assert torch.equal(ph['support'], pd['support'])
+    assert ph['wt_stride'] == pd['wt_stride'] and torch.equal(ph['obs4'], pd['obs4'])
+    a, b = ph['weights'], pd['weights']
+    diff = (a - b).abs()
+    ulp = torch.abs(a) * 2.0 ** -23
+    assert bool((diff <= ulp).all())
+    assert float((diff > 0).float().mean()) < 1e-3          # bit-identical almost everywhere
+    if not train:
+        q = c_host.init_to_median(2, seed=1)
+        lp_h, g_h = c_host.logp_grad(q)
+        lp_d, g_d = c_dev.logp_grad(q)
+        assert torch.allclose(lp_h, lp_d, rtol=2e-6) and torch.allclose(g_h, g_d, rtol=1e-4, atol=1e-3)
