@@ -506,7 +506,12 @@ class SEDmodel(object):
         band_inds = np.r_[0, np.unique(glob)]
         band_indices = np.searchsorted(band_inds, glob)[:, None].repeat(N, axis=1).astype(int)
         mask = np.ones_like(band_indices)
-        band_weights = self._calculate_band_weights(z, ebv_mw, band_inds)
+        if N > 1 and np.all(z == z[0]) and np.all(ebv_mw == ebv_mw[0]):
+            # one object drawn N times (get_flux_from_chains): its band weights are computed once
+            band_weights = np.broadcast_to(self._calculate_band_weights(z[:1], ebv_mw[:1], band_inds),
+                                           (N, 300, len(band_inds)))
+        else:
+            band_weights = self._calculate_band_weights(z, ebv_mw, band_inds)
         tt = np.repeat(t[..., None], N, axis=1) - tmax[None, :]
         hsiao_interp = np.array([HSIAO_PHASE0_INDEX + np.floor(tt), HSIAO_PHASE0_INDEX + np.ceil(tt),
                                  np.remainder(tt, 1)])

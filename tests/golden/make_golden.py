@@ -75,7 +75,25 @@ def golden_posterior():
     print('done', res['seconds'], res['evals'])
 
 
+def golden_train():
+    """Training log density (train_model_globalRV, unconstrained) and gradient at a seeded point."""
+    from tests.test_gpu_train import training_point
+    case = make_case('T21_model', ['g_PS1', 'r_PS1', 'i_PS1', 'z_PS1'], np.arange(-8, 40, 4.0), N=6, seed=31, mag=True,
+                     mask_some=True)
+    ref = case['ref']
+    qg, ql = training_point(ref, case, 1, 8)
+    qg32, ql32 = qg[0].astype(np.float32), ql[:, 0].astype(np.float32)
+    lp, gg, gl = ref.train_logp_grad(qg32.astype(np.float64), ql32.astype(np.float64), case['obs'], case['weights'])
+    np.savez_compressed(os.path.join(HERE, 'train_T21_griz.npz'), obs=case['obs'], weights=case['weights'], z=case['z'],
+                        ebv=case['ebv'], qg=qg32, ql=ql32, logp=lp, grad_g=gg, grad_l=gl,
+                        band_names=np.array(case['band_names']))
+    print('train', lp)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'train':
+        golden_train()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'posterior':
         golden_posterior()
     else:

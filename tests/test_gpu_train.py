@@ -161,3 +161,21 @@ def test_train_nuts_adapts_and_conserves_energy():
     assert st[:, 60:, 2].sum() <= 3
     out2 = ctx.train_nuts(qg32, ql32, use_graph=False, passes_per_graph=16, **kw)
     assert torch.equal(out['samples_g'], out2['samples_g']) and torch.equal(out['samples_l'], out2['samples_l'])
+
+
+def test_train_kernel_against_committed_golden():
+    """Same inputs as tests/test_oracle.py::test_training_oracle_gradient_finite_difference_and_golden."""
+    import os
+    from bayesn_b200 import SEDmodel
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'train_T21_griz.npz'))
+    m = SEDmodel(load_model='T21_model')
+    bi = np.array([m.band_dict[str(n)] for n in d['band_names']])
+    ctx = m.prepare_training(d['obs'], None, bi)              # band weights rebuilt on the device from z, E(B-V)
+    qg = torch.tensor(d['qg'][None], dtype=torch.float32, device='cuda').contiguous()
+    ql = torch.tensor(d['ql'][:, None], dtype=torch.float32, device='cuda').contiguous()
+    lp, gg, gl = ctx.train_logp_grad(qg, ql)
+    torch.cuda.synchronize()
+    assert abs(float(lp[0]) - float(d['logp'])) / abs(float(d['logp'])) < LOGP_TOL
+    gg, gl = gg[0].cpu().numpy().astype(np.float64), gl[:, 0].cpu().numpy().astype(np.float64)
+    assert np.max(np.abs(gg - d['grad_g'])) / np.max(np.abs(d['grad_g'])) < GRAD_TOL
+    assert np.max(np.max(np.abs(gl - d['grad_l']), axis=1) / np.max(np.abs(d['grad_l']), axis=1)) < GRAD_TOL

@@ -202,3 +202,51 @@ def test_summary_statistics():
     assert 250 < ess < 700          # theory: 8000 (1-0.9)/(1+0.9) = 421
     tab = summary.summary_table({'a': x, 'b': np.stack([x, ar], axis=-1)})
     assert list(tab.index) == ['a', 'b[0]', 'b[1]'] and 'r_hat' in tab.columns
+
+
+def test_training_oracle_gradient_finite_difference_and_golden():
+    """train_model_globalRV (reference :1115-1182) in the unconstrained space: the autograd gradient
+    of the restatement against central differences, and the committed fixture."""
+    import torch
+    from tests.common import ref_model
+    d = np.load(os.path.join(HERE, 'golden', 'train_T21_griz.npz'))
+    ref = ref_model('T21_model', [str(b) for b in d['band_names'][1:]])
+    qg, ql = d['qg'].astype(np.float64), d['ql'].astype(np.float64)
+    lp, gg, gl = ref.train_logp_grad(qg, ql, d['obs'], d['weights'])
+    assert abs(lp - float(d['logp'])) < 1e-9 * abs(lp)
+    assert np.allclose(gg, d['grad_g'], rtol=1e-9, atol=1e-9) and np.allclose(gl, d['grad_l'], rtol=1e-9, atol=1e-9)
+
+    def f(a, b):
+        with torch.no_grad():
+            return float(ref.train_logp(torch.as_tensor(a), torch.as_tensor(b), d['obs'], d['weights']))
+    dims = ref.train_dims()
+    G = dims['G']
+    for i in [0, 40, 75, 100, 140, 300, G - 3, G - 2, G - 1]:       # W0, W1, sigma_eps, L_Omega, sigma0, RV, tauA
+        h = 1e-6
+        a, b = qg.copy(), qg.copy()
+        a[i] += h
+        b[i] -= h
+        fd = (f(a, ql) - f(b, ql)) / (2 * h)
+        assert abs(fd - gg[i]) < 1e-5 * max(1.0, abs(gg[i])), (i, fd, gg[i])
+    for (s, j) in [(0, 0), (2, dims['n_eps']), (3, dims['n_eps'] + 1), (5, dims['n_eps'] + 2)]:
+        h = 1e-6
+        a, b = ql.copy(), ql.copy()
+        a[s, j] += h
+        b[s, j] -= h
+        fd = (f(qg, a) - f(qg, b)) / (2 * h)
+        assert abs(fd - gl[s, j]) < 1e-5 * max(1.0, abs(gl[s, j])), (s, j, fd, gl[s, j])
+
+
+def test_corr_cholesky_is_a_correlation_factor_with_numpyro_logdet():
+    """CorrCholeskyTransform restatement: unit-norm rows, lower triangular, positive diagonal, and
+    its log|det J| equals the log-determinant of the Jacobian d(strict lower triangle)/dy."""
+    import torch
+    from oracle.ref_model import RefSED
+    n = 5
+    y = torch.tensor(np.random.RandomState(1).randn(n * (n - 1) // 2) * 0.6, dtype=torch.float64)
+    L, ld = RefSED.corr_cholesky(y, n)
+    assert torch.allclose((L ** 2).sum(dim=1), torch.ones(n, dtype=torch.float64))
+    assert torch.all(torch.diagonal(L) > 0) and torch.allclose(torch.triu(L, 1), torch.zeros(n, n, dtype=torch.float64))
+    ii, jj = torch.tril_indices(n, n, -1)
+    J = torch.autograd.functional.jacobian(lambda v: RefSED.corr_cholesky(v, n)[0][ii, jj], y)
+    assert abs(float(torch.linalg.slogdet(J)[1]) - float(ld)) < 1e-10
