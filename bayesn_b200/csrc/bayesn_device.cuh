@@ -120,35 +120,35 @@ __device__ __forceinline__ float treduce16(float (&v)[16], int lane) {
     return v[0];
 }
 
-// The same within each 16-lane half of the warp (the two halves work on two different
-// observations): 15 shuffles; on return lane hl = lane & 15 holds its half's total of value hl.
+// The same for two interleaved groups of 16 lanes (even lanes / odd lanes work on two different
+// observations): 15 shuffles; on return lane l holds the total of value (l >> 1) of its group.
 __device__ __forceinline__ float treduce16h(float (&v)[16], int lane) {
-    bool up = lane & 8;
+    bool up = lane & 16;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         float send = up ? v[i] : v[i + 8];
         float keep = up ? v[i + 8] : v[i];
-        v[i] = keep + __shfl_xor_sync(FULL, send, 8);
+        v[i] = keep + __shfl_xor_sync(FULL, send, 16);
     }
-    up = lane & 4;
+    up = lane & 8;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float send = up ? v[i] : v[i + 4];
         float keep = up ? v[i + 4] : v[i];
-        v[i] = keep + __shfl_xor_sync(FULL, send, 4);
+        v[i] = keep + __shfl_xor_sync(FULL, send, 8);
     }
-    up = lane & 2;
+    up = lane & 4;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         float send = up ? v[i] : v[i + 2];
         float keep = up ? v[i + 2] : v[i];
-        v[i] = keep + __shfl_xor_sync(FULL, send, 2);
+        v[i] = keep + __shfl_xor_sync(FULL, send, 4);
     }
-    up = lane & 1;
+    up = lane & 2;
     {
         float send = up ? v[0] : v[1];
         float keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(FULL, send, 1);
+        v[0] = keep + __shfl_xor_sync(FULL, send, 2);
     }
     return v[0];
 }
@@ -507,20 +507,24 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     }
     __syncwarp();
 
-    // ---- band-pass integrals: half-warp per observation, 16 lanes over wavelength bins ---------
+    // ---- band-pass integrals: two observations per pass, 16 lanes over wavelength bins each ---------
+    // The lanes of the two observations are INTERLEAVED (even lanes: first, odd lanes: second): when both
+    // are in the same band - the common case after sorting - neighbouring lanes read the same J_l row
+    // and weight, which the shared-memory pipe serves as one broadcast, halving its traffic (the LSU
+    // pipe, not the FMA pipe, is the busiest unit of this loop).
     // log L is accumulated in double: far from the mode |log L| reaches 1e6 while NUTS needs energy
     // differences to ~1e-2, which float32 partial sums cannot hold (ulp(7.5e5) = 0.06)
     double logL = 0.0;
     float gDs = 0.f, gAV = 0.f, gT = 0.f, gRV = 0.f;
     const float* wtile = STAGE ? c.wt_s : c.wt_g;
-    const int hl = lane & 15, hb = lane & 16;
+    const int hl = lane >> 1, hb = lane & 1;
     // lane hl = 4 + l ends every reduction holding Q_l; it also keeps row l of W for the d/dtmax term
     float wrow[TP];
 #pragma unroll
     for (int m = 0; m < TP; ++m) wrow[m] = (hl >= 4 && hl < 4 + LP) ? c.Ws[(hl - 4) * TP + m] : 0.f;
     float gTW = 0.f;
     for (int p = 0; p < npair; ++p) {
-        float* rc = c.rec + (2 * p + (lane >> 4)) * REC;
+        float* rc = c.rec + (2 * p + hb) * REC;
         float u[LP4];
         {
             const float4* up = reinterpret_cast<const float4*>(rc);
@@ -536,7 +540,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         const float yo = scal.z, iso = scal.w;
         const int4 sp = c.sup[pk >> 16];
         int nr = (sp.y - sp.x + 15) >> 4;
-        nr = max(nr, __shfl_xor_sync(FULL, nr, 16));
+        nr = max(nr, __shfl_xor_sync(FULL, nr, 1));
         // running pointers: one add per array per round instead of rebuilding addresses
         const int b_first = sp.x + hl;
         const float* p0 = hs + (pk & 0xff) * BP + b_first;
@@ -580,8 +584,8 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         }
         const float val = treduce16h(acc, lane);
         const float F = __shfl_sync(FULL, val, hb);
-        const float FA = __shfl_sync(FULL, val, hb | 1);
-        const float FT = __shfl_sync(FULL, val, hb | 2);
+        const float FA = __shfl_sync(FULL, val, hb | 2);
+        const float FT = __shfl_sync(FULL, val, hb | 4);
         const float Sv = c.sc[0];
         const float flux = Sv * F;
         float chi, r;                      // r = d log L / d flux
@@ -602,7 +606,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         gDs = fmaf(-KAPPA * r, flux, gDs);
         gAV = fmaf(-KAPPA * coef, FA, gAV);
         gT = fmaf((pk & 256) ? coef : 0.f, FT, gT);
-        if (DRV) gRV = fmaf(-KAPPA * AV * coef, __shfl_sync(FULL, val, hb | 3), gRV);
+        if (DRV) gRV = fmaf(-KAPPA * AV * coef, __shfl_sync(FULL, val, hb | 6), gRV);
         // d logL / d(sum_m W[l][m] Jt[m]) for this observation, overwriting u (no longer needed),
         // and its product with (W J_t'(t))[l] for the gradient through the time spline
         const float dU = -KAPPA * coef * val;
@@ -616,11 +620,11 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         if (hl >= 4 && hl < 4 + LP) rc[hl - 4] = dU;
     }
     // the two halves hold the sums over their own observations
-    logL += __shfl_xor_sync(FULL, logL, 16);
-    gDs += __shfl_xor_sync(FULL, gDs, 16);
-    gAV += __shfl_xor_sync(FULL, gAV, 16);
-    gT += __shfl_xor_sync(FULL, gT, 16);
-    if (DRV) gRV += __shfl_xor_sync(FULL, gRV, 16);
+    logL += __shfl_xor_sync(FULL, logL, 1);
+    gDs += __shfl_xor_sync(FULL, gDs, 1);
+    gAV += __shfl_xor_sync(FULL, gAV, 1);
+    gT += __shfl_xor_sync(FULL, gT, 1);
+    if (DRV) gRV += __shfl_xor_sync(FULL, gRV, 1);
     __syncwarp();
 
     gT += wsum(gTW);
