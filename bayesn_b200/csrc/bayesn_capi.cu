@@ -108,6 +108,7 @@ int train_prepare(bayesn_ctx* ctx, int C) {
     rc |= train_alloc(ctx, &T.scr, (size_t)C * ne * ne);
     rc |= train_alloc(ctx, &T.lpg, (size_t)C);
     rc |= train_alloc(ctx, &T.part, (size_t)ctx->D.N * C * T.PR);
+    rc |= train_alloc(ctx, &T.rpart, (size_t)((ctx->D.N + TRAIN_RCHUNK - 1) / TRAIN_RCHUNK) * C * T.R);
     if (rc) return rc;
     ctx->train_C = C;
     ctx->train_N = ctx->D.N;
@@ -187,6 +188,21 @@ int launch_train_sn(bayesn_ctx* ctx, const float* ql, float* grad_l, cudaStream_
     const unsigned grid = (unsigned)((units + WPB - 1) / WPB);
     kern<<<grid, WPB * 32, bytes, st>>>(ctx->M, ctx->D, ctx->T, ntile, ql, grad_l);
     ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// two-stage deterministic reduction of the per-SN rows (bayesn_train.cuh T3)
+int launch_train_reduce(bayesn_ctx* ctx, const float* lat, size_t chain_stride, size_t sn_stride, double* red,
+                        cudaStream_t st) {
+    const TrainDev& T = ctx->T;
+    const int nchunk = (ctx->D.N + TRAIN_RCHUNK - 1) / TRAIN_RCHUNK;
+    const size_t smem = (size_t)TRAIN_RCHUNK * (T.PR + ctx->M.n_eps + 2) * sizeof(float);
+    CU_CHECK(ctx, cudaFuncSetAttribute(train_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    train_reduce_kernel<<<dim3(nchunk, T.C), 256, smem, st>>>(ctx->M, T, ctx->D.N, ctx->LP, ctx->TP, lat, chain_stride,
+                                                              sn_stride, T.rpart);
+    train_reduce_final_kernel<<<dim3((T.R + 255) / 256, T.C), 256, 0, st>>>(T, nchunk, T.rpart, red);
+    ctx->launches += 2;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
 }
@@ -503,16 +519,13 @@ int bayesn_train_begin(bayesn_ctx* ctx, int n_chains, const float* qg, const flo
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
     if (int rc = train_prepare(ctx, n_chains)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    train_globals_kernel<<<n_chains, 128, 0, st>>>(ctx->M, ctx->T, ctx->LP, ctx->TP, qg);
+    const size_t msm = (size_t)ctx->M.n_eps * ctx->M.n_eps * sizeof(float);
+    train_globals_kernel<<<n_chains, 128, msm, st>>>(ctx->M, ctx->T, ctx->LP, ctx->TP, qg);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     TrainSnCall call{ctx, ql, grad_l, st};
     if (int rc = dispatch(ctx, /*stage=*/n_chains >= 2, call)) return rc;
-    dim3 grid((ctx->T.R + 7) / 8, n_chains);
-    train_reduce_kernel<<<grid, 256, 0, st>>>(ctx->M, ctx->T, ctx->D.N, ctx->LP, ctx->TP, ql, (size_t)ctx->T.Dl,
-                                              (size_t)n_chains * ctx->T.Dl, red);
-    ctx->launches++;
-    CU_CHECK(ctx, cudaGetLastError());
+    if (int rc = launch_train_reduce(ctx, ql, (size_t)ctx->T.Dl, (size_t)n_chains * ctx->T.Dl, red, st)) return rc;
     return 0;
 }
 
@@ -521,7 +534,7 @@ int bayesn_train_finish(bayesn_ctx* ctx, int n_chains, const float* qg, const do
     if (!ctx) return -1;
     if (!ctx->have_model || ctx->train_C != n_chains) return fail(ctx, -1, "bayesn_train_begin first");
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
-    train_finish_kernel<<<n_chains, 128, 0, (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->LP, ctx->TP, qg, red, logp,
+    train_finish_kernel<<<n_chains, 128, (size_t)ctx->M.n_eps * ctx->M.n_eps * sizeof(float), (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->LP, ctx->TP, qg, red, logp,
                                                                      grad_g);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
@@ -574,7 +587,7 @@ int bayesn_train_nuts_init(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, int sn_o
     rc |= alloc(&TN.work_g, (size_t)C * nvec * ctx->T.G);
     rc |= alloc(&TN.gtmp, (size_t)C * ctx->T.G);
     if (rc) return rc;
-    train_nuts_init_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(ctx->M, ctx->T, TN, ctx->D, ctx->LP, ctx->TP, qg0, ql0);
+    train_nuts_init_kernel<<<C, 256, (size_t)ctx->M.n_eps * ctx->M.n_eps * sizeof(float), (cudaStream_t)stream>>>(ctx->M, ctx->T, TN, ctx->D, ctx->LP, ctx->TP, qg0, ql0);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     ctx->have_tn = true;
@@ -587,20 +600,16 @@ int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     TrainNutsSnCall call{ctx, st};
     if (int rc = dispatch(ctx, /*stage=*/ctx->T.C >= 2, call)) return rc;
-    dim3 grid((ctx->T.R + 7) / 8, ctx->T.C);
-    // the reduction needs theta_s and eps_tform_s of the point just evaluated: the current positions
     const size_t vec = (size_t)32 * ctx->TN.VPL, nvec = train_nuts_num_vectors(ctx->TN.cfg.max_depth);
-    train_reduce_kernel<<<grid, 256, 0, st>>>(ctx->M, ctx->T, ctx->D.N, ctx->LP, ctx->TP, ctx->TN.work_l + TV_CZ * vec,
-                                              nvec * vec, (size_t)ctx->T.C * nvec * vec, red);
-    ctx->launches++;
-    CU_CHECK(ctx, cudaGetLastError());
+    if (int rc = launch_train_reduce(ctx, ctx->TN.work_l + TV_CZ * vec, nvec * vec, (size_t)ctx->T.C * nvec * vec, red, st))
+        return rc;
     return 0;
 }
 
 int bayesn_train_nuts_ctl(bayesn_ctx* ctx, const double* red, void* stream) {
     if (!ctx) return -1;
     if (!ctx->have_tn) return fail(ctx, -1, "bayesn_train_nuts_init first");
-    train_nuts_ctl_kernel<<<ctx->T.C, 256, 0, (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->TN, ctx->LP, ctx->TP, red);
+    train_nuts_ctl_kernel<<<ctx->T.C, 256, (size_t)ctx->M.n_eps * ctx->M.n_eps * sizeof(float), (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->TN, ctx->LP, ctx->TP, red);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -662,4 +671,7 @@ int bayesn_tiles_fill(bayesn_ctx* ctx, const bayesn_tiles_desc* d, const int32_t
     return 0;
 }
 
+#ifdef CTL_TIMING
+int bayesn_debug_ctl_times(long long* out) { return cudaMemcpyFromSymbol(out, bayesn::g_ctl_t, sizeof(long long) * 16) == cudaSuccess ? 0 : -1; }
+#endif
 }  // extern "C"

@@ -34,6 +34,7 @@ struct TrainDev {
     float* scr;     // [C][ne*ne] scratch of the reverse sweep
     double* lpg;    // [C] log prior + log|det J| of the global sites
     float* part;    // [N][C][PR] per-SN contributions
+    double* rpart;  // [ceil(N/32)][C][R] chunk partial sums of the reduction
 };
 
 // Per-SN rows and the reduced buffer end with TRAIN_NX sampler partial sums (used by the NUTS
@@ -92,8 +93,9 @@ struct TrainShared {
     float yk[9], dyk[9];
 };
 
+// `mat`: n_eps^2 floats of shared memory (scratch of the row scans)
 __device__ __forceinline__ void train_globals_dev(const ModelDev& M, const TrainDev& Tr, int LP, int TP, int c,
-                                                  const float* __restrict__ qg, TrainShared& S) {
+                                                  const float* __restrict__ qg, TrainShared& S, float* mat) {
     double* sh = S.sh;
     float* s_sig = S.sig;
     float* s_yk = S.yk;
@@ -129,14 +131,14 @@ __device__ __forceinline__ void train_globals_dev(const ModelDev& M, const Train
     __syncthreads();
     // rows of L_Omega by signed stick breaking; L_Sigma = diag(sigma_epsilon) L_Omega.  Row i:
     // t_j = tanh(y_ij), c_j = prod_{k<=j} (1 - t_k^2), L[i][j] = t_j sqrt(c_{j-1}), L[i][i] = sqrt(c_{i-1}).
-    // Three sweeps: element-parallel transcendental work, a per-row running sum of log(1 - t^2),
-    // element-parallel assembly - instead of one thread walking a row through tanh / log / sqrt.
+    // Three sweeps: element-parallel transcendental work, a per-row running sum of log(1 - t^2) in
+    // shared memory, element-parallel assembly - instead of one thread walking a row through tanh /
+    // log / sqrt and global memory.
     float* Ls = Tr.Ls + (size_t)c * ne * ne;
     float* LsT = Tr.LsT + (size_t)c * ne * ne;
     float* Lo = Tr.Lo + (size_t)c * ne * ne;
     float* tm = Tr.tm + (size_t)c * ne * ne;
     float* cum = Tr.cum + (size_t)c * ne * ne;
-    float* clog = Tr.clog + (size_t)c * ne * ne;
     for (int e = tid; e < Tr.n_corr; e += blockDim.x) {
         int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)e)) * 0.5f);
         while (i * (i - 1) / 2 > e) --i;
@@ -145,20 +147,26 @@ __device__ __forceinline__ void train_globals_dev(const ModelDev& M, const Train
         const double yv = qg[oY + e];
         const double l1m = 2.0 * (0.6931471805599453 - fabs(yv) - log1p(exp(-2.0 * fabs(yv))));   // log(1 - tanh^2)
         tm[i * ne + j] = (float)tanh(yv);
-        clog[i * ne + j] = (float)l1m;
+        mat[i * ne + j] = (float)l1m;
         lp += l1m;                                   // tanh log-det
     }
     __syncthreads();
-    for (int i = tid >> 5; i < ne; i += blockDim.x >> 5) warp_row_cumsum(clog + i * ne, i, tid & 31, false);
+    for (int i = tid; i < ne; i += blockDim.x) {
+        float run = 0.f;
+        for (int j = 0; j < i; ++j) {
+            run += mat[i * ne + j];
+            mat[i * ne + j] = run;
+        }
+    }
     __syncthreads();
     for (int e = tid; e < ne * ne; e += blockDim.x) {
         const int i = e / ne, j = e - i * ne;
         float lo = 0.f, t = 0.f, cj = 1.f;
         if (j <= i) {
-            const float clp = (j > 0) ? clog[i * ne + j - 1] : 0.f;       // log c_{j-1}
+            const float clp = (j > 0) ? mat[i * ne + j - 1] : 0.f;        // log c_{j-1}
             if (j < i) {
                 t = tm[e];
-                const float cl = clog[e];
+                const float cl = mat[e];
                 cj = expf(cl);
                 lo = t * expf(0.5f * clp);
                 // stick-breaking log-det (columns 0..i-2) + LKJCholesky(eta = 1) on the diagonal element
@@ -227,7 +235,8 @@ __device__ __forceinline__ void train_globals_dev(const ModelDev& M, const Train
 __global__ void __launch_bounds__(128) train_globals_kernel(ModelDev M, TrainDev Tr, int LP, int TP,
                                                             const float* __restrict__ qg_all) {
     __shared__ TrainShared S;
-    train_globals_dev(M, Tr, LP, TP, blockIdx.x, qg_all + (size_t)blockIdx.x * Tr.G, S);
+    extern __shared__ __align__(16) float tmat[];
+    train_globals_dev(M, Tr, LP, TP, blockIdx.x, qg_all + (size_t)blockIdx.x * Tr.G, S, tmat);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -274,49 +283,74 @@ __global__ void __launch_bounds__(WPB * 32) train_sn_kernel(ModelDev M, DataDev 
 
 // ------------------------------------------------------------------------------------------
 // (T3) reduction over the SNe of this rank.  red[c] = [log p, d/dsigma0, d/dRV, d/dtauA,
-//      dW0 (padded [LP][TP]), dW1, dL_Sigma (row-major, lower triangle)], all double.
-// ------------------------------------------------------------------------------------------
+//      dW0 (padded [LP][TP]), dW1, dL_Sigma (row-major, lower triangle), sampler partial sums],
+//      all double.  dL_Sigma = sum_s vec(dW_s) eps_tform_s^T is a small GEMM (n_eps x N x n_eps):
+//      stage 1 tiles it - one CTA per (chunk of 32 SNe, chain) stages the chunk's rows and latents
+//      in shared memory once and produces every output's partial sum; stage 2 adds the chunk
+//      partials in a fixed order (deterministic: ranks and replays must agree bit for bit).
 //      The latents (theta_s, eps_tform_s) of SN s / chain c are read at lat + c * chain_stride +
 //      s * sn_stride (the caller's ql array, or the sampler's current-position vectors).
+// ------------------------------------------------------------------------------------------
+constexpr int TRAIN_RCHUNK = 32;
+
 __global__ void __launch_bounds__(256) train_reduce_kernel(ModelDev M, TrainDev Tr, int N, int LP, int TP,
                                                            const float* __restrict__ lat, size_t chain_stride,
-                                                           size_t sn_stride, double* __restrict__ red) {
-    const int c = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // one warp per output, lanes over SNe
-    const int ne = M.n_eps, L = M.L, C = Tr.C, PR = Tr.PR, LPTP = Tr.LPTP;
-    if (r >= Tr.R) return;
-    const size_t stride = (size_t)C * PR;
-    const float* base = Tr.part + (size_t)c * PR;
-    double acc = 0.0;
-    if (r == 0) {
-        const int off = LPTP + 3 + ((LPTP + 3) & 1);
-        for (int s = lane; s < N; s += 32) acc += *reinterpret_cast<const double*>(base + s * stride + off);
-    } else if (r < 4) {
-        for (int s = lane; s < N; s += 32) acc += base[s * stride + LPTP + (r - 1)];
-    } else if (r < 4 + LPTP) {
-        const int p = r - 4;
-        for (int s = lane; s < N; s += 32) acc += base[s * stride + p];
-    } else if (r < 4 + 2 * LPTP) {
-        const int p = r - 4 - LPTP;
-        const float* th = lat + (size_t)c * chain_stride + ne;       // theta_s
-        for (int s = lane; s < N; s += 32) acc += (double)base[s * stride + p] * th[(size_t)s * sn_stride];
-    } else if (r >= train_red_base(LPTP, ne)) {
-        const int x = train_part_base(LPTP) + (r - train_red_base(LPTP, ne));
-        for (int s = lane; s < N; s += 32) acc += base[s * stride + x];
-    } else {
-        const int e = r - 4 - 2 * LPTP;
-        const int i = e / ne, j = e - i * ne;
-        if (j <= i) {
-            // vec_F index i = (l-1) + (L-2) m  ->  position of dW[l][m] in the padded layout
-            const int m = i / (L - 2), l = 1 + (i - m * (L - 2));
-            const int p = l * TP + m;
-            const float* ev = lat + (size_t)c * chain_stride + j;    // eps_tform_s[j]
-            for (int s = lane; s < N; s += 32) acc += (double)base[s * stride + p] * ev[(size_t)s * sn_stride];
-        }
+                                                           size_t sn_stride, double* __restrict__ rpart) {
+    extern __shared__ __align__(16) float rsm[];
+    const int chunk = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    const int ne = M.n_eps, L = M.L, C = Tr.C, PR = Tr.PR, LPTP = Tr.LPTP, R = Tr.R;
+    const int s0 = chunk * TRAIN_RCHUNK;
+    const int ns = min(TRAIN_RCHUNK, N - s0);
+    const int ES = ne + 2;                                  // eps_tform, theta (+ pad)
+    float* A = rsm;                                         // [32][PR]   per-SN rows
+    float* E = rsm + TRAIN_RCHUNK * PR;                     // [32][ES]   latents
+    for (int e = tid; e < ns * PR; e += blockDim.x) {
+        const int s = e / PR, x = e - s * PR;
+        A[e] = Tr.part[((size_t)(s0 + s) * C + c) * PR + x];
     }
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-    if (lane == 0) red[(size_t)c * Tr.R + r] = acc;
+    for (int e = tid; e < ns * (ne + 1); e += blockDim.x) {
+        const int s = e / (ne + 1), x = e - s * (ne + 1);
+        E[s * ES + x] = lat[(size_t)c * chain_stride + (size_t)(s0 + s) * sn_stride + x];
+    }
+    __syncthreads();
+    const int off_lp = LPTP + 3 + ((LPTP + 3) & 1);
+    const int rbase = train_red_base(LPTP, ne), pbase = train_part_base(LPTP);
+    double* out = rpart + ((size_t)chunk * C + c) * R;
+    for (int r = tid; r < R; r += blockDim.x) {
+        double acc = 0.0;
+        if (r == 0) {
+            for (int s = 0; s < ns; ++s) acc += *reinterpret_cast<const double*>(A + s * PR + off_lp);
+        } else if (r < 4) {
+            for (int s = 0; s < ns; ++s) acc += A[s * PR + LPTP + (r - 1)];
+        } else if (r < 4 + LPTP) {
+            for (int s = 0; s < ns; ++s) acc += A[s * PR + (r - 4)];
+        } else if (r < 4 + 2 * LPTP) {
+            const int p = r - 4 - LPTP;
+            for (int s = 0; s < ns; ++s) acc += (double)A[s * PR + p] * E[s * ES + ne];
+        } else if (r >= rbase) {
+            const int x = pbase + (r - rbase);
+            for (int s = 0; s < ns; ++s) acc += A[s * PR + x];
+        } else {
+            const int e = r - 4 - 2 * LPTP;
+            const int i = e / ne, j = e - i * ne;
+            if (j <= i) {
+                // vec_F index i = (l-1) + (L-2) m  ->  position of dW[l][m] in the padded layout
+                const int m = i / (L - 2), l = 1 + (i - m * (L - 2));
+                const int p = l * TP + m;
+                for (int s = 0; s < ns; ++s) acc += (double)A[s * PR + p] * E[s * ES + j];
+            }
+        }
+        out[r] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) train_reduce_final_kernel(TrainDev Tr, int nchunk, const double* __restrict__ rpart,
+                                                                 double* __restrict__ red) {
+    const int c = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= Tr.R) return;
+    double acc = 0.0;
+    for (int k = 0; k < nchunk; ++k) acc += rpart[((size_t)k * Tr.C + c) * Tr.R + r];
+    red[(size_t)c * Tr.R + r] = acc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -325,7 +359,7 @@ __global__ void __launch_bounds__(256) train_reduce_kernel(ModelDev M, TrainDev 
 // gg = sign * d log p / d qg (sign = -1 gives the gradient of the potential energy)
 __device__ __forceinline__ void train_finish_dev(const ModelDev& M, const TrainDev& Tr, int LP, int TP, int c,
                                                  const float* __restrict__ qg, const double* __restrict__ red,
-                                                 float* __restrict__ gg, float sign) {
+                                                 float* __restrict__ gg, float sign, float* mat) {
     const int tid = threadIdx.x;
     const int L = M.L, T = M.T, ne = M.n_eps, LPTP = Tr.LPTP;
     const int oW1 = L * T, oSe = 2 * L * T, oY = oSe + ne, oSc = oY + Tr.n_corr;
@@ -339,7 +373,7 @@ __device__ __forceinline__ void train_finish_dev(const ModelDev& M, const TrainD
     const float* Lo = Tr.Lo + (size_t)c * ne * ne;
     const float* tm = Tr.tm + (size_t)c * ne * ne;
     const float* cum = Tr.cum + (size_t)c * ne * ne;
-    float* scr = Tr.scr + (size_t)c * ne * ne;
+    float* scr = mat;                                  // shared memory
     // Reverse sweep of the stick breaking.  With gL_ij = sigma_i G[i][j] (d/dL_Omega[i][j]) and
     // A_j the weight of log c_j in the density, d/dc_j obeys dc_j = a_j / c_j + (1 - t_{j+1}^2) dc_{j+1},
     // a_j = A_j + sqrt(c_j)/2 * (j == i-1 ? gL_ii : gL_{i,j+1} t_{j+1}); multiplying by c_j turns it
@@ -357,19 +391,19 @@ __device__ __forceinline__ void train_finish_dev(const ModelDev& M, const TrainD
         scr[e] = a;
     }
     __syncthreads();
-    for (int i = tid >> 5; i < ne; i += blockDim.x >> 5) {     // one warp per row
-        const int lane = tid & 31;
-        // d/dsigma_i = sum_j G[i][j] L_Omega[i][j], and the suffix sums of row i
+    for (int i = tid; i < ne; i += blockDim.x) {
+        // d/dsigma_i = sum_j G[i][j] L_Omega[i][j], and the suffix sums of row i (shared memory)
         double dse = 0.0;
-        for (int j = lane; j <= i; j += 32) dse += Gm[i * ne + j] * (double)Lo[i * ne + j];
-        for (int o = 16; o; o >>= 1) dse += __shfl_xor_sync(FULL, dse, o);
-        warp_row_cumsum(scr + i * ne, i, lane, true);
-        if (lane == 0) {
-            const double se = Tr.sig[(size_t)c * ne + i];
-            const double u = qg[oSe + i];
-            const double sgm = 1.0 / (1.0 + exp(-u));
-            gg[oSe + i] = sign * (float)(dse * (1.0 + se * se) * HALF_PI * sgm * (1.0 - sgm) + (1.0 - 2.0 * sgm));
+        for (int j = 0; j <= i; ++j) dse += Gm[i * ne + j] * (double)Lo[i * ne + j];
+        float run = 0.f;
+        for (int j = i - 1; j >= 0; --j) {
+            run += scr[i * ne + j];
+            scr[i * ne + j] = run;
         }
+        const double se = Tr.sig[(size_t)c * ne + i];
+        const double u = qg[oSe + i];
+        const double sgm = 1.0 / (1.0 + exp(-u));
+        gg[oSe + i] = sign * (float)(dse * (1.0 + se * se) * HALF_PI * sgm * (1.0 - sgm) + (1.0 - 2.0 * sgm));
     }
     __syncthreads();
     for (int e = tid; e < Tr.n_corr; e += blockDim.x) {
@@ -400,8 +434,9 @@ __global__ void __launch_bounds__(128) train_finish_kernel(ModelDev M, TrainDev 
                                                            double* __restrict__ logp, float* __restrict__ grad_g) {
     const int c = blockIdx.x;
     const double* red = red_all + (size_t)c * Tr.R;
+    extern __shared__ __align__(16) float tmat[];
     if (threadIdx.x == 0) logp[c] = red[0] + Tr.lpg[c];
-    train_finish_dev(M, Tr, LP, TP, c, qg_all + (size_t)c * Tr.G, red, grad_g + (size_t)c * Tr.G, 1.f);
+    train_finish_dev(M, Tr, LP, TP, c, qg_all + (size_t)c * Tr.G, red, grad_g + (size_t)c * Tr.G, 1.f, tmat);
 }
 
 }  // namespace bayesn

@@ -24,6 +24,13 @@
 
 namespace bayesn {
 
+#ifdef CTL_TIMING
+__device__ long long g_ctl_t[16];
+#define CTL_T(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_ctl_t[k] = clock64(); } while (0)
+#else
+#define CTL_T(k)
+#endif
+
 enum { TV_ZL = 0, TV_RL, TV_GL, TV_ZR, TV_RR, TV_GR, TV_ZP, TV_GP, TV_RSUM, TV_SZP, TV_SGP, TV_WMEAN, TV_WM2,
        TV_CZ, TV_CR, TV_CG, TV_RSUB, TV_IM, TV_CKPT };
 __host__ __device__ inline int train_nuts_num_vectors(int max_depth) { return TV_CKPT + 2 * max_depth; }
@@ -275,9 +282,11 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
     __shared__ TrainShared S;
     __shared__ float shsum[8 * TRAIN_NX];
     __shared__ TrainCtl sctl;
+    extern __shared__ __align__(16) float tmat[];      // n_eps^2 floats: scratch of the stick-breaking row scans
     const int c = blockIdx.x, tid = threadIdx.x;
     const int G = Tr.G;
     const NutsDev& cfg = Nt.cfg;
+    CTL_T(0);
     if (tid == 0) sctl = Nt.ctl[c];
     __syncthreads();
     if (sctl.phase == 2) {
@@ -293,8 +302,10 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
     const uint32_t gkey = 0x7fff0000u + (uint32_t)c;          // stream id of the global slice of chain c
 
     // ---- 1. finish the evaluation made at CZ: gradient of the potential wrt the unconstrained globals
-    train_finish_dev(M, Tr, LP, TP, c, W.v(TV_CZ), red, gnew, -1.f);
+    CTL_T(1);
+    train_finish_dev(M, Tr, LP, TP, c, W.v(TV_CZ), red, gnew, -1.f, tmat);
     __syncthreads();
+    CTL_T(2);
     const double pe_new = -(red[0] + Tr.lpg[c]);
     const float eps = sctl.eps_dir;
     const int leaf = sctl.leaf;
@@ -334,7 +345,9 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
             }
         }
     }
+    CTL_T(3);
     block_sums<TRAIN_NX>(pv, shsum, tot);
+    CTL_T(4);
 
     // ---- 3. scalar decisions (thread 0), mirrored from nuts_kernel ------------------------------------
     if (tid == 0) {
@@ -470,6 +483,7 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
     }
     __syncthreads();
 
+    CTL_T(5);
     // ---- 4. apply the vector actions to the global slice (same order as the SN kernel) --------------------
     const int act = sctl.act;
     const int wf_n = sctl.wf_act;
@@ -533,6 +547,7 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
         gcopy(W, TV_CZ, gr ? TV_ZR : TV_ZL); gcopy(W, TV_CR, gr ? TV_RR : TV_RL); gcopy(W, TV_CG, gr ? TV_GR : TV_GL);
     }
     __syncthreads();
+    CTL_T(6);
     // ---- 5. first half of the next leapfrog of the global slice, then the constrained tables ------------
     {
         const float e2 = sctl.eps_dir;
@@ -544,7 +559,9 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
         }
     }
     __syncthreads();
-    train_globals_dev(M, Tr, LP, TP, c, W.v(TV_CZ), S);
+    CTL_T(7);
+    train_globals_dev(M, Tr, LP, TP, c, W.v(TV_CZ), S, tmat);
+    CTL_T(8);
     if (tid == 0) Nt.ctl[c] = sctl;
 }
 
@@ -552,6 +569,7 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
 __global__ void train_nuts_init_kernel(ModelDev M, TrainDev Tr, TrainNutsDev Nt, DataDev Dd, int LP, int TP,
                                        const float* __restrict__ qg0, const float* __restrict__ ql0) {
     __shared__ TrainShared S;
+    extern __shared__ __align__(16) float tmat[];
     const int c = blockIdx.x, tid = threadIdx.x;
     const int G = Tr.G, Dl = Tr.Dl, C = Tr.C, VPL = Nt.VPL;
     const int nvec = train_nuts_num_vectors(Nt.cfg.max_depth);
@@ -572,7 +590,7 @@ __global__ void train_nuts_init_kernel(ModelDev M, TrainDev Tr, TrainNutsDev Nt,
         }
     }
     __syncthreads();
-    train_globals_dev(M, Tr, LP, TP, c, W.v(TV_CZ), S);
+    train_globals_dev(M, Tr, LP, TP, c, W.v(TV_CZ), S, tmat);
     if (tid == 0) {
         TrainCtl s{};
         s.act = ACT_INIT;
