@@ -26,6 +26,7 @@ struct bayesn_ctx {
     std::vector<void*> train_owned;
     int train_C = 0, train_N = 0;
     TrainNutsDev TN{};          // training sampler state
+    XchgDev X{};                // peer-memory exchange of the training sums (world 1 = off)
     std::vector<void*> tn_owned;
     bool have_tn = false;
 };
@@ -201,7 +202,7 @@ int launch_train_reduce(bayesn_ctx* ctx, const float* lat, size_t chain_stride, 
     CU_CHECK(ctx, cudaFuncSetAttribute(train_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     train_reduce_kernel<<<dim3(nchunk, T.C), 256, smem, st>>>(ctx->M, T, ctx->D.N, ctx->LP, ctx->TP, lat, chain_stride,
                                                               sn_stride, T.rpart);
-    train_reduce_final_kernel<<<dim3((T.R + 255) / 256, T.C), 256, 0, st>>>(T, nchunk, T.rpart, red);
+    train_reduce_final_kernel<<<dim3((T.R + 255) / 256, T.C), 256, 0, st>>>(T, nchunk, T.rpart, red, ctx->X);
     ctx->launches += 2;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -529,13 +530,13 @@ int bayesn_train_begin(bayesn_ctx* ctx, int n_chains, const float* qg, const flo
     return 0;
 }
 
-int bayesn_train_finish(bayesn_ctx* ctx, int n_chains, const float* qg, const double* red, double* logp,
+int bayesn_train_finish(bayesn_ctx* ctx, int n_chains, const float* qg, double* red, double* logp,
                         float* grad_g, void* stream) {
     if (!ctx) return -1;
     if (!ctx->have_model || ctx->train_C != n_chains) return fail(ctx, -1, "bayesn_train_begin first");
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
     train_finish_kernel<<<n_chains, 128, (size_t)ctx->M.n_eps * ctx->M.n_eps * sizeof(float), (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->LP, ctx->TP, qg, red, logp,
-                                                                     grad_g);
+                                                                     grad_g, ctx->X);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -606,10 +607,10 @@ int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream) {
     return 0;
 }
 
-int bayesn_train_nuts_ctl(bayesn_ctx* ctx, const double* red, void* stream) {
+int bayesn_train_nuts_ctl(bayesn_ctx* ctx, double* red, void* stream) {
     if (!ctx) return -1;
     if (!ctx->have_tn) return fail(ctx, -1, "bayesn_train_nuts_init first");
-    train_nuts_ctl_kernel<<<ctx->T.C, 256, (size_t)ctx->M.n_eps * ctx->M.n_eps * sizeof(float), (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->TN, ctx->LP, ctx->TP, red);
+    train_nuts_ctl_kernel<<<ctx->T.C, 256, (size_t)ctx->M.n_eps * ctx->M.n_eps * sizeof(float), (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->TN, ctx->LP, ctx->TP, red, ctx->X);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -668,6 +669,28 @@ int bayesn_tiles_fill(bayesn_ctx* ctx, const bayesn_tiles_desc* d, const int32_t
         T, reinterpret_cast<const int4*>(support), wt_stride, weights);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+
+int bayesn_train_set_exchange(bayesn_ctx* ctx, int world, int rank, const uint64_t* peer_bufs, const uint64_t* peer_flags,
+                              void* scratch) {
+    if (!ctx) return -1;
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(ctx, -1, "exchange supports 1..8 ranks");
+    XchgDev X{};
+    X.world = world; X.rank = rank;
+    if (world > 1) {
+        if (!peer_bufs || !peer_flags || !scratch) return fail(ctx, -1, "exchange needs peer buffers, flags and scratch");
+        for (int p = 0; p < world; ++p) {
+            X.peer_buf[p] = reinterpret_cast<double*>(peer_bufs[p]);
+            X.peer_flag[p] = reinterpret_cast<unsigned*>(peer_flags[p]);
+        }
+        X.my_buf = X.peer_buf[rank];
+        X.my_flag = X.peer_flag[rank];
+        unsigned* sc = static_cast<unsigned*>(scratch);      // [4] zero-initialised device words: seq, done, err
+        X.seq = sc; X.done = sc + 1; X.err = sc + 2;
+    }
+    ctx->X = X;
     return 0;
 }
 

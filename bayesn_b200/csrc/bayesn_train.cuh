@@ -344,13 +344,76 @@ __global__ void __launch_bounds__(256) train_reduce_kernel(ModelDev M, TrainDev 
     }
 }
 
+// Exchange of the reduced sums between the ranks that hold different SN shards, fused into the
+// second reduction stage: every rank STORES its sums straight into a slot of every peer's buffer
+// over NVLink (peer-mapped symmetric memory), the last CTA to finish publishes a sequence number
+// to every peer, and the consumer (the control kernel / train_finish) waits for all ranks'
+// numbers and adds the slots in rank order - the same bits on every rank, no NCCL launch, one
+// NVLink store latency instead of a collective.  Buffers are double-buffered by pass parity.
+struct XchgDev {
+    int world, rank;
+    double* peer_buf[8];          // peer p's buffer: [2][world][C][R] doubles
+    unsigned* peer_flag[8];       // peer p's flags:  [2][world]
+    double* my_buf;
+    unsigned* my_flag;
+    unsigned* seq;                // this rank's pass counter (device)
+    unsigned* done;               // CTA completion counter of the publishing kernel
+    unsigned* err;                // set if a wait timed out
+};
+
 __global__ void __launch_bounds__(256) train_reduce_final_kernel(TrainDev Tr, int nchunk, const double* __restrict__ rpart,
-                                                                 double* __restrict__ red) {
+                                                                 double* __restrict__ red, XchgDev X) {
     const int c = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= Tr.R) return;
-    double acc = 0.0;
-    for (int k = 0; k < nchunk; ++k) acc += rpart[((size_t)k * Tr.C + c) * Tr.R + r];
-    red[(size_t)c * Tr.R + r] = acc;
+    const unsigned next = X.world > 1 ? *X.seq + 1u : 0u;
+    if (r < Tr.R) {
+        double acc = 0.0;
+        for (int k = 0; k < nchunk; ++k) acc += rpart[((size_t)k * Tr.C + c) * Tr.R + r];
+        if (X.world > 1) {
+            const size_t slot = (((size_t)(next & 1u) * X.world + X.rank) * Tr.C + c) * Tr.R + r;
+            for (int p = 0; p < X.world; ++p) X.peer_buf[p][slot] = acc;
+        } else {
+            red[(size_t)c * Tr.R + r] = acc;
+        }
+    }
+    if (X.world > 1) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned total = gridDim.x * gridDim.y;
+            if (atomicAdd(X.done, 1u) == total - 1) {
+                *X.done = 0u;
+                __threadfence_system();
+                for (int p = 0; p < X.world; ++p) {
+                    unsigned* f = X.peer_flag[p] + (next & 1u) * X.world + X.rank;
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(next) : "memory");
+                }
+                *X.seq = next;
+            }
+        }
+    }
+}
+
+// consumer side: wait for every rank's sums of the current pass, add them in rank order into red[c]
+__device__ __forceinline__ void xchg_gather(const XchgDev& X, const TrainDev& Tr, int c, double* __restrict__ red) {
+    if (X.world <= 1) return;
+    const unsigned cur = *X.seq;
+    if ((int)threadIdx.x < X.world) {
+        const unsigned* f = X.my_flag + (cur & 1u) * X.world + threadIdx.x;
+        const long long t0 = clock64();
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (clock64() - t0 > 4000000000LL) { *X.err = 1u; break; }      // ~2 s: never hang the GPU
+        } while (v != cur);
+    }
+    __syncthreads();
+    const double* src = X.my_buf + ((size_t)(cur & 1u) * X.world * Tr.C + c) * Tr.R;
+    for (int r = threadIdx.x; r < Tr.R; r += blockDim.x) {
+        double acc = 0.0;
+        for (int p = 0; p < X.world; ++p) acc += __ldcg(src + (size_t)p * Tr.C * Tr.R + r);   // L2: peers wrote it
+        red[(size_t)c * Tr.R + r] = acc;
+    }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -429,10 +492,10 @@ __device__ __forceinline__ void train_finish_dev(const ModelDev& M, const TrainD
 }
 
 __global__ void __launch_bounds__(128) train_finish_kernel(ModelDev M, TrainDev Tr, int LP, int TP,
-                                                           const float* __restrict__ qg_all,
-                                                           const double* __restrict__ red_all,
-                                                           double* __restrict__ logp, float* __restrict__ grad_g) {
+                                                           const float* __restrict__ qg_all, double* __restrict__ red_all,
+                                                           double* __restrict__ logp, float* __restrict__ grad_g, XchgDev X) {
     const int c = blockIdx.x;
+    xchg_gather(X, Tr, c, red_all);
     const double* red = red_all + (size_t)c * Tr.R;
     extern __shared__ __align__(16) float tmat[];
     if (threadIdx.x == 0) logp[c] = red[0] + Tr.lpg[c];

@@ -278,7 +278,7 @@ __device__ __forceinline__ void block_sums(float (&v)[NV], float* sh /* [8][NV] 
 }
 
 __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDev Tr, TrainNutsDev Nt, int LP, int TP,
-                                                             const double* __restrict__ red_all) {
+                                                             double* __restrict__ red_all, XchgDev X) {
     __shared__ TrainShared S;
     __shared__ float shsum[8 * TRAIN_NX];
     __shared__ TrainCtl sctl;
@@ -293,6 +293,8 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
         if (tid == 0) Nt.ctl[c].act = ACT_DONE;
         return;
     }
+    // sums of the other ranks' SN shards (fused peer-memory exchange; no-op on one GPU / with NCCL)
+    xchg_gather(X, Tr, c, red_all);
     const double* red = red_all + (size_t)c * Tr.R;
     const double* rx = red + train_red_base(Tr.LPTP, M.n_eps);
     const int nvec = train_nuts_num_vectors(cfg.max_depth);

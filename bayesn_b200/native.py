@@ -53,7 +53,7 @@ EXPORTS = ['bayesn_abi_version', 'bayesn_ctx_create', 'bayesn_ctx_destroy', 'bay
            'bayesn_flux_batch', 'bayesn_nuts_workspace_bytes', 'bayesn_nuts_fit', 'bayesn_launch_count',
            'bayesn_init_to_median', 'bayesn_ffma_peak', 'bayesn_train_dims', 'bayesn_train_begin',
            'bayesn_train_finish', 'bayesn_train_nuts_init', 'bayesn_train_nuts_sn', 'bayesn_train_nuts_ctl',
-           'bayesn_train_nuts_status', 'bayesn_tiles_support', 'bayesn_tiles_fill']
+           'bayesn_train_nuts_status', 'bayesn_tiles_support', 'bayesn_tiles_fill', 'bayesn_train_set_exchange']
 
 _lib = None
 
@@ -95,6 +95,8 @@ def load_library():
     lib.bayesn_train_nuts_sn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bayesn_train_nuts_ctl.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bayesn_train_nuts_status.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
+    lib.bayesn_train_set_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                              C.c_void_p]
     _lib = lib
     return lib
 
@@ -256,6 +258,46 @@ class Context:
                                                weights.data_ptr(), self._stream()), 'bayesn_tiles_fill')
 
     # ------------------------------------------------------------------ training
+    def enable_train_exchange(self, group, n_chains):
+        """Switch the exchange of the per-leapfrog training sums from the caller's NCCL all-reduce to
+        the fused peer-memory exchange: a symmetric (peer-mapped over NVLink) buffer per rank, filled
+        by every rank's reduction kernel with plain stores and consumed by the control kernel."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world == 1:
+            self.disable_train_exchange()
+            return
+        R = self.train_dims()[2]
+        dev = torch.device(f'cuda:{self.device}')
+        n_data = 2 * world * n_chains * R
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        buf = symm.empty(n_data + 16, dtype=torch.float64, device=dev)       # data + 2 * world uint32 flags
+        hdl = symm.rendezvous(buf, group)
+        buf.zero_()
+        scratch = torch.zeros(4, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier(group)
+        off = int(getattr(hdl, 'offset', 0) or 0)
+        bases = [int(p) + off for p in hdl.buffer_ptrs]
+        pb = (C.c_uint64 * world)(*bases)
+        pf = (C.c_uint64 * world)(*[b + 8 * n_data for b in bases])
+        self._check(self.lib.bayesn_train_set_exchange(self.h, world, rank, pb, pf, scratch.data_ptr()),
+                    'bayesn_train_set_exchange')
+        self._keep['xchg'] = (buf, hdl, scratch, n_chains)
+
+    def disable_train_exchange(self):
+        self._check(self.lib.bayesn_train_set_exchange(self.h, 1, 0, None, None, None), 'bayesn_train_set_exchange')
+        self._keep.pop('xchg', None)
+
+    def train_exchange_error(self):
+        x = self._keep.get('xchg')
+        return bool(x[2][2].item()) if x else False
+
     def train_dims(self):
         """(G, Dl, R): unconstrained global / per-SN latent dimensions and the length of the
         per-chain reduction buffer."""
@@ -299,7 +341,7 @@ class Context:
     def train_nuts(self, qg0, ql0, num_warmup=500, num_samples=500, max_tree_depth=10, target_accept=0.8,
                    init_step_size=0.1, adapt_step_size=True, adapt_mass_matrix=True, regularize_mass_matrix=False,
                    seed=0, group=None, sn_offset=0, passes_per_graph=32, use_graph=True, max_passes=None,
-                   progress=None):
+                   progress=None, exchange='nccl'):
         """Device-resident NUTS over the joint training posterior (numpyro call at reference
         :1767-1770, :1913-1919).  ``qg0`` (C, G), ``ql0`` (N, C, Dl) float32 CUDA tensors.  One pass =
         one leapfrog of every chain = SN kernel + reduction -> [all-reduce over ``group``] -> control
@@ -328,11 +370,16 @@ class Context:
                                                     self._stream()), 'bayesn_train_nuts_init')
         if group is not None:
             import torch.distributed as dist
+        peer = group is not None and exchange == 'peer' and dist.get_world_size(group) > 1
+        if peer:
+            self.enable_train_exchange(group, Cn)        # fused NVLink peer-memory exchange instead of NCCL
+        else:
+            self.disable_train_exchange()
 
         def one_pass():
             st = self._stream()
             self._check(self.lib.bayesn_train_nuts_sn(self.h, red.data_ptr(), st), 'bayesn_train_nuts_sn')
-            if group is not None:
+            if group is not None and not peer:
                 dist.all_reduce(red, op=dist.ReduceOp.SUM, group=group)
             self._check(self.lib.bayesn_train_nuts_ctl(self.h, red.data_ptr(), st), 'bayesn_train_nuts_ctl')
 
@@ -361,6 +408,9 @@ class Context:
                 for _ in range(passes_per_graph):
                     one_pass()
         done = False
+        import time as _time
+        torch.cuda.synchronize()
+        t_loop, p_loop = _time.perf_counter(), passes
         while not done:
             if graph is not None:
                 graph.replay()
@@ -374,6 +424,8 @@ class Context:
                 progress(passes, np.ctypeslib.as_array(status).reshape(Cn, 8).copy())
             if max_passes is not None and passes >= max_passes:
                 break
+        torch.cuda.synchronize()
+        out['loop_seconds'], out['loop_passes'] = _time.perf_counter() - t_loop, passes - p_loop
         # flush: the latent slices apply the last transition's actions (final draw) in one more SN pass
         self._check(self.lib.bayesn_train_nuts_sn(self.h, red.data_ptr(), self._stream()), 'bayesn_train_nuts_sn')
         torch.cuda.synchronize()
@@ -381,6 +433,11 @@ class Context:
         out['info'] = np.ctypeslib.as_array(status).reshape(Cn, 8).copy()
         out['passes'] = passes
         out['finished'] = bool(done)
+        if peer:
+            if self.train_exchange_error():
+                raise RuntimeError('peer-memory exchange timed out waiting for a rank')
+            dist.barrier(group)
+            self.disable_train_exchange()
         return out
 
     def flux_batch(self, M0, theta, AV, W0, W1, eps, Ds, RV, band_indices, mask, J_t, hsiao_interp, weights,

@@ -164,7 +164,7 @@ int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_
 int bayesn_train_dims(bayesn_ctx* ctx, int* G, int* Dl, int* R);
 int bayesn_train_begin(bayesn_ctx* ctx, int n_chains, const float* qg, const float* ql, float* grad_l, double* red,
                        void* stream);
-int bayesn_train_finish(bayesn_ctx* ctx, int n_chains, const float* qg, const double* red, double* logp,
+int bayesn_train_finish(bayesn_ctx* ctx, int n_chains, const float* qg, double* red, double* logp,
                         float* grad_g, void* stream);
 
 /* Device-resident NUTS over the joint training posterior (all globals + the latents of every SN),
@@ -186,7 +186,20 @@ int bayesn_train_finish(bayesn_ctx* ctx, int n_chains, const float* qg, const do
 int bayesn_train_nuts_init(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, int sn_offset, const float* qg0,
                            const float* ql0, float* samples_g, float* samples_l, float* stats, void* stream);
 int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream);
-int bayesn_train_nuts_ctl(bayesn_ctx* ctx, const double* red, void* stream);
+int bayesn_train_nuts_ctl(bayesn_ctx* ctx, double* red, void* stream);
+
+/* Fused exchange of the per-leapfrog training sums over NVLink peer memory, replacing the caller's
+ * all-reduce between bayesn_train_nuts_sn and bayesn_train_nuts_ctl (and between bayesn_train_begin
+ * and a consumer): the second reduction stage stores this rank's sums into a slot of EVERY peer's
+ * buffer and publishes a pass number; the control kernel waits for all ranks' numbers and adds the
+ * slots in rank order (bit-identical on every rank).
+ *   peer_bufs[p]  device address, valid in THIS process, of rank p's buffer of 2 * world * C * R doubles
+ *   peer_flags[p] same for rank p's 2 * world uint32 flags (zero-initialised)
+ *   scratch       4 zero-initialised uint32 words in this rank's own memory (pass counter, CTA counter, error)
+ * The buffers must be peer-mapped symmetric memory (e.g. torch.distributed._symmetric_memory); all
+ * ranks must issue the same sequence of passes.  world = 1 switches the exchange off. */
+int bayesn_train_set_exchange(bayesn_ctx* ctx, int world, int rank, const uint64_t* peer_bufs,
+                              const uint64_t* peer_flags, void* scratch);
 int bayesn_train_nuts_status(bayesn_ctx* ctx, float* out, void* stream);
 
 /* Per-SN band-weight tiles built on the device: SEDmodel._calculate_band_weights

@@ -34,12 +34,13 @@ Nt = 24
 obs_t, w_t, bi_t = btrain.simulate_training_set(mt, Nt, seed=5, bands=('g_PS1', 'r_PS1', 'i_PS1', 'z_PS1'))
 kw = dict(num_chains=2, num_warmup=0, num_samples=6, max_tree_depth=5, initialisation='T21_model', seed=3)
 group = dist.group.WORLD
-def run(group):
+def run(group, exchange='nccl'):
     lo, hi = shard_bounds(Nt, rank, world) if group is not None else (0, Nt)
     c = mt.prepare_training(obs_t[:, :, lo:hi], w_t[lo:hi], bi_t)
     qg0, ql0 = btrain.initial_position(mt, obs_t, 2, 'T21_model', seed=3, device=f'cuda:{local}')
     o = c.train_nuts(qg0, ql0[lo:hi].contiguous(), num_warmup=0, num_samples=6, max_tree_depth=5, init_step_size=0.004,
-                     adapt_step_size=False, adapt_mass_matrix=False, seed=3, group=group, sn_offset=lo, passes_per_graph=8)
+                     adapt_step_size=False, adapt_mass_matrix=False, seed=3, group=group, sn_offset=lo, passes_per_graph=8,
+                     exchange=exchange)
     return o
 o_sh = run(group)
 o_1 = run(None)
@@ -59,4 +60,26 @@ if rank == 0:
     print(f'train: sharded({world} ranks) vs single GPU: same tree sizes (first 3) {ok_steps}, max |d globals| {dz:.2e}, max |d latents| {dl:.2e}, ranks agree {same}')
     print('n_steps sharded', st_sh[:, :, 1].astype(int).tolist(), 'single', st_1[:, :, 1].astype(int).tolist())
     assert ok_steps and same and dz < 5e-3 and dl < 5e-3
+# ---- (3) fused peer-memory exchange instead of NCCL: same bits
+o_peer = run(group, 'peer')
+torch.cuda.synchronize()
+same_peer = bool(torch.equal(o_peer['samples_g'], o_sh['samples_g'])) and bool(torch.equal(o_peer['samples_l'], o_sh['samples_l']))
+if rank == 0:
+    print(f'train: peer-memory exchange == NCCL all-reduce bit for bit: {same_peer}')
+assert same_peer
+# ---- (4) timing at C4 scale: NCCL vs peer exchange
+import time
+mm = SEDmodel(load_model='M20_model', device=f'cuda:{local}')
+Nb = int(os.environ.get('TRAIN_N', 500))
+obs_b, w_b, bi_b = btrain.simulate_training_set(mm, Nb, seed=20241019)
+lo, hi = shard_bounds(Nb, rank, world)
+cb = mm.prepare_training(obs_b[:, :, lo:hi], None, bi_b)
+qg0, ql0 = btrain.initial_position(mm, obs_b, 4, 'M20_model', seed=1, device=f'cuda:{local}')
+for ex in ('nccl', 'peer'):
+    dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    o = cb.train_nuts(qg0, ql0[lo:hi].contiguous(), num_warmup=30, num_samples=10, max_tree_depth=10, seed=2, group=group,
+                      sn_offset=lo, exchange=ex)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    if rank == 0:
+        print(f'train C4 x{world} GPUs N={Nb} exchange={ex}: {dt:.2f} s, {o["passes"]} passes, {dt / o["passes"] * 1e6:.1f} us/pass incl. setup, {o["loop_seconds"] / o["loop_passes"] * 1e6:.1f} us/pass in the replay loop, accept {o["stats"][:, 30:, 0].mean().item():.3f}')
 dist.destroy_process_group()
