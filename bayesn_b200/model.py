@@ -176,7 +176,7 @@ class SEDmodel(object):
             import torch.distributed as dist
             rank, world = dist.get_rank(group), dist.get_world_size(group)
         lo, hi = shard_bounds(N, rank, world)
-        ctx = self.prepare_training(obs[:, :, lo:hi], weights[lo:hi], band_inds)
+        ctx = self.prepare_training(obs[:, :, lo:hi], None if weights is None else weights[lo:hi], band_inds)
         dev = f'cuda:{ctx.device}'
         qg0, ql0 = btrain.initial_position(self, obs, num_chains, initialisation, seed=seed, device=dev)
         out = ctx.train_nuts(qg0, ql0[lo:hi].contiguous(), num_warmup=num_warmup, num_samples=num_samples,

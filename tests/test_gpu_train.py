@@ -179,3 +179,26 @@ def test_train_kernel_against_committed_golden():
     gg, gl = gg[0].cpu().numpy().astype(np.float64), gl[:, 0].cpu().numpy().astype(np.float64)
     assert np.max(np.abs(gg - d['grad_g'])) / np.max(np.abs(d['grad_g'])) < GRAD_TOL
     assert np.max(np.max(np.abs(gl - d['grad_l']), axis=1) / np.max(np.abs(d['grad_l']), axis=1)) < GRAD_TOL
+
+
+def test_training_recovers_the_generating_model():
+    """End to end: SNe simulated from T21 (simulate_light_curve, mag=True), SEDmodel.train with the
+    device-resident sampler (4 chains), posterior of the global parameters against the truth."""
+    from bayesn_b200 import SEDmodel, train as btrain, summary
+    m = SEDmodel(load_model='T21_model')
+    obs, w, bi = btrain.simulate_training_set(m, 100, seed=11, bands=('g_PS1', 'r_PS1', 'i_PS1', 'z_PS1'),
+                                              t=np.arange(-8, 40, 3.0), yerr=0.02)
+    W, S = 150, 100
+    samples, ex = m.train(obs, None, bi, num_chains=4, num_warmup=W, num_samples=S, initialisation='T21_model', seed=5)
+    st = ex['stats']
+    assert ex['info'][:, 5].sum() <= 4                       # divergences
+    assert 0.6 < st[:, W:, 0].mean() < 0.98
+    for k, truth in (('tauA', m.tauA), ('sigma0', m.sigma0), ('RV', m.RV)):
+        x = samples[k]
+        assert abs(x.mean() - truth) < 4 * x.std() + 1e-3, (k, x.mean(), x.std(), truth)
+        assert summary.split_rhat(x) < 1.3, k
+    W0 = samples['W0']
+    z = (W0.mean(axis=(0, 1)) - m.W0.flatten(order='F')) / W0.std(axis=(0, 1))
+    assert np.sqrt((z ** 2).mean()) < 2.5 and np.abs(z).max() < 5, z
+    assert samples['theta'].shape == (4, S, 100) and samples['eps'].shape == (4, S, m.n_eps, 100)
+    assert samples['L_Omega'].shape == (4, S, m.n_eps, m.n_eps)
