@@ -339,8 +339,8 @@ def micro_logp(model, ctx_fit, args, dev, F, peak):
     ach = F * evals_s / 1e12
     return {'n_sne': n, 'n_chains': 1, 'ms_per_launch': ms, 'evals_per_s': evals_s,
             'roofline': {'bound': 'fp32_fma', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak},
-            'note': f'inputs ({n} weight tiles, {n * 9 * 304 * 4 / 1e6:.0f} MB) exceed nothing: re-read from L2/HBM '
-                    f'each launch'}
+            'note': f'inputs: {n} compact weight tiles ({ctx._keep["data"]["weights"].numel() * 4 / 1e6:.0f} MB) + observations, '
+                    f're-read from L2/HBM each launch; no L2 flush (a launch is 0.24 ms of compute-bound work)'}
 
 
 def oracle_evals_per_s(obs, weights, band_inds_names, rows, seconds, threads=None):
