@@ -1,0 +1,171 @@
+"""``run`` / ``parse_yaml_input`` / ``process_dataset`` of the reference's ``SEDmodel``
+(``bayesn/bayesn_model.py:1735-1924``, ``:1656-1733``, ``:2370-2730``) for the SNANA **text**
+branch: a directory ``<version_photometry>/`` holding ``<name>.LIST`` and one SNANA text file per
+object.  Modes ``fitting`` (``fit_method: mcmc``) and ``training_globalRV``; same YAML keys and
+defaults, same output files (``chains.pkl``, ``input.yaml``, ``<prefix>.FITRES.TEXT``; training:
+``bayesn.yaml``, ``initial_chains.pkl``).  Out of scope here: SNANA FITS input, ``data_table``
+input, SNANA cluster conventions (``jobsplit`` directory search), the VI and dust modes, LCPLOT.
+"""
+import os
+import time
+
+import numpy as np
+
+from . import snana
+
+C_KMS = 299792.458
+
+
+def parse_yaml_input(model, args, cmd_args=None):
+    """Defaults of reference :1684-1709 (the keys this driver understands)."""
+    args = dict(args)
+    if cmd_args is not None:
+        for k, v in (vars(cmd_args) if not isinstance(cmd_args, dict) else cmd_args).items():
+            if k in ('input', 'filters') or v is None:
+                continue
+            if k == 'map' and isinstance(v, str):
+                fm = np.loadtxt(v, dtype=str)
+                v = {row[0]: row[1] for row in np.atleast_2d(fm)}
+            args[k] = v
+    args.pop('CONFIG', None)
+    args.pop('config', None)
+    for k, d in (('num_chains', 4), ('num_warmup', 500), ('num_samples', 500), ('fit_method', 'mcmc'),
+                 ('chain_method', 'parallel'), ('initialisation', 'median'), ('map', {}), ('drop_bands', []),
+                 ('outputdir', os.getcwd()), ('outfile_prefix', 'output'), ('sim_prescale', 1),
+                 ('save_fit_errors', False), ('error_floor', 0.0)):
+        args[k] = args.get(k, d)
+    args['l_knots'] = args.get('l_knots', model.l_knots.tolist())
+    args['tau_knots'] = args.get('tau_knots', model.tau_knots.tolist())
+    args['fit_method'] = str(args['fit_method']).lower()
+    if args['fit_method'] not in ('vi', 'mcmc'):
+        raise ValueError(f'Requested fitting method {args["fit_method"]}, must be one of "mcmc" or "vi"')
+    if args['fit_method'] == 'vi':
+        raise NotImplementedError('the VI path is outside the scope of this implementation; use fit_method: mcmc')
+    if 'mode' not in args:
+        raise ValueError("input needs a 'mode'")
+    os.makedirs(args['outputdir'], exist_ok=True)
+    return args
+
+
+def process_dataset(model, args):
+    """SNANA text directory -> reference-layout arrays.  Returns dict(obs (10, N_obs, N) with
+    FLUXCAL (fitting) or MAG (training) in rows 1-2, band_inds, sn_names, peak_mjds, fitres columns).
+    Same per-object steps as reference :2577-2689: rest-frame phases from PEAKMJD, filter mapping,
+    bands outside the model's wavelength coverage dropped, phase cut to the tau-knot range, error floor,
+    zero padding with mask 0, non-positive fluxes masked for training (:2714-2718)."""
+    if 'version_photometry' not in args:
+        raise ValueError('Please pass version_photometry (a directory containing <name>.LIST and SNANA text files)')
+    data_dir = args['version_photometry']
+    name = os.path.split(os.path.normpath(data_dir))[-1]
+    sn_files = np.atleast_1d(np.loadtxt(os.path.join(data_dir, f'{name}.LIST'), dtype=str))
+    training = 'training' in args['mode'].lower()
+    fmap = dict(args.get('map', {}))
+    used = [0]
+    lcs, names, peaks, cols = [], [], [], {k: [] for k in ('zHEL', 'zHELERR', 'zHD', 'zHDERR', 'MWEBV', 'HOST_LOGMASS')}
+    for fn in sn_files:
+        meta, lc = snana.read_snana_ascii(os.path.join(data_dir, str(fn)))
+        peak = meta['PEAKMJD'] if 'PEAKMJD' in meta else meta['SEARCH_PEAKMJD']
+        zhel = float(meta['REDSHIFT_HELIO'])
+        zcmb = float(meta.get('REDSHIFT_FINAL', meta.get('REDSHIFT_CMB', zhel)))
+        zhel_err = float(meta.get('REDSHIFT_HELIO_ERR', 5e-4))
+        vpec = float(meta.get('VPEC', 0.0))
+        zpec = np.sqrt((1 + vpec / C_KMS) / (1 - vpec / C_KMS)) - 1
+        zhd = (1 + zcmb) / (1 + zpec) - 1
+        band_col = lc['BAND'] if 'BAND' in lc else lc['FLT']
+        flt = np.array([fmap.get(str(b), str(b)) for b in band_col])
+        if 'FLUXCAL' in lc:
+            flux, ferr = lc['FLUXCAL'].astype(float), lc['FLUXCALERR'].astype(float)
+        else:
+            flux = 10 ** ((27.5 - lc['MAG']) / 2.5)
+            ferr = (np.log(10) / 2.5) * flux * lc['MAGERR']
+        ferr = np.maximum(ferr, args.get('error_floor', 0.0) * (np.log(10) / 2.5) * flux)
+        t = (lc['MJD'] - peak) / (1 + zhel)
+        keep = np.isfinite(flux) & np.isfinite(ferr) & (t > model.tau_knots.min()) & (t < model.tau_knots.max())
+        for f in np.unique(flt):
+            if f not in model.band_dict:
+                raise KeyError(f'Filter {f} not present in BayeSN, check your filter mapping')
+            lo, hi = model.band_lim_dict[f]
+            if zhel > lo / model.l_knots[0] - 1 or zhel < hi / model.l_knots[-1] - 1 or f in args.get('drop_bands', []):
+                keep &= flt != f
+        gl = np.array([model.band_dict[f] for f in flt])
+        glk = gl[keep]
+        _, first = np.unique(glk, return_index=True)
+        for g in glk[np.sort(first)]:                          # order of first appearance, like pandas .unique()
+            if g not in used:
+                used.append(int(g))
+        lcs.append(dict(t=t[keep], flux=flux[keep], ferr=ferr[keep], gl=gl[keep], z=zhel, zerr=zhel_err,
+                        mu=float(model.cosmo.distmod(np.array([zhd]))[0]), ebv=float(meta.get('MWEBV', 0.0)),
+                        mass=float(meta.get('HOSTGAL_LOGMASS', -9.0))))
+        names.append(str(meta.get('SNID', fn)))
+        peaks.append(float(peak))
+        for k, v in (('zHEL', zhel), ('zHELERR', zhel_err), ('zHD', zcmb), ('zHDERR', float(meta.get('REDSHIFT_FINAL_ERR', 5e-4))),
+                     ('MWEBV', float(meta.get('MWEBV', 0.0))), ('HOST_LOGMASS', float(meta.get('HOSTGAL_LOGMASS', -9.0)))):
+            cols[k].append(v)
+    band_inds = np.array(used)                                  # NULL band + bands in order of first use
+    local = {g: i for i, g in enumerate(used)}
+    N, n_obs = len(lcs), max(max(len(l['t']) for l in lcs), 1)
+    obs = np.zeros((10, n_obs, N))
+    obs[2] = 1 / np.sqrt(2 * np.pi)                              # padded sigma (:2703-2704)
+    for i, l in enumerate(lcs):
+        n = len(l['t'])
+        flux, ferr = l['flux'], l['ferr']
+        obs[0, :n, i] = l['t']
+        if training:
+            good = flux > 0
+            with np.errstate(divide='ignore', invalid='ignore'):
+                obs[1, :n, i] = np.where(good, 27.5 - 2.5 * np.log10(np.where(good, flux, 1.0)), 0.0)
+                obs[2, :n, i] = np.where(good, (2.5 / np.log(10)) * ferr / np.where(good, flux, 1.0), 1 / np.sqrt(2 * np.pi))
+            obs[9, :n, i] = good
+            obs[0, :n, i] = np.where(good, l['t'], 0.0)
+        else:
+            obs[1, :n, i], obs[2, :n, i] = flux, ferr
+            obs[9, :n, i] = 1
+        obs[4, :n, i] = np.where(obs[9, :n, i] != 0, [local[g] for g in l['gl']], 0)
+        obs[3, :, i], obs[5, :, i], obs[6, :, i], obs[7, :, i], obs[8, :, i] = l['mass'], l['z'], l['zerr'], l['mu'], l['ebv']
+    return dict(obs=obs, band_inds=band_inds, sn_names=names, peak_mjds=np.array(peaks),
+                fitres={k: np.array(v) for k, v in cols.items()})
+
+
+def run(model, args, cmd_args=None):
+    """Reference ``SEDmodel.run`` for ``mode: fitting`` (per-object NUTS fits of every SN in the data
+    set, :1809-1849) and ``mode: training_globalRV`` (:1766-1770, :1913-1924).  Returns the samples
+    dict (reference site names; (chains, draws, ..., N) for fits)."""
+    import yaml
+    from . import outputs
+    args = parse_yaml_input(model, args, cmd_args)
+    mode = args['mode'].lower()
+    ds = process_dataset(model, args)
+    model.data, model.sn_list, model.peak_mjds = ds['obs'], ds['sn_names'], ds['peak_mjds']
+    model.used_band_inds = ds['band_inds']
+    if model.verbose:
+        print(f'Current mode: {args["mode"]}\nRunning...')
+    start = time.time()
+    if mode == 'fitting':
+        cons, raw = model.fit_batch(ds['obs'], None, ds['band_inds'], num_chains=args['num_chains'],
+                                    num_warmup=args['num_warmup'], num_samples=args['num_samples'], max_tree_depth=10,
+                                    seed=0, return_device=True)
+        cols, dropped = outputs.postprocess_fits(model, cons, ds['obs'], sn_names=ds['sn_names'], outputdir=args['outputdir'],
+                                                 outfile_prefix=args['outfile_prefix'], save_chains=True,
+                                                 extra_columns={k: v for k, v in ds['fitres'].items() if k not in ('zHEL', 'MWEBV')})
+        samples = {}
+        for k, v in cons.items():
+            v = v.cpu().numpy().astype(np.float64)
+            samples[k] = (v.transpose(1, 2, 3, 0) if k == 'eps' else v.transpose(1, 2, 0, 3)) if v.ndim == 4 else v.transpose(1, 2, 0)
+        if 'tmax' in samples:
+            samples['peak_MJD'] = ds['peak_mjds'][None, None, :] + samples['tmax'] * (1 + ds['obs'][5, 0, :][None, None, :])
+    elif mode == 'training_globalrv':
+        init = args['initialisation']
+        if init in ('median', 'sample'):
+            raise NotImplementedError("training starts from a reference model: set 'initialisation' to a model name "
+                                      "(e.g. M20_model) or a BAYESN.YAML path")
+        samples, _ = model.train(ds['obs'], None, ds['band_inds'], num_chains=args['num_chains'],
+                                 num_warmup=args['num_warmup'], num_samples=args['num_samples'], initialisation=init,
+                                 outputdir=args['outputdir'], mode=args['mode'])
+    else:
+        raise ValueError("Invalid mode, this implementation runs 'training_globalRV' and 'fitting'")
+    model.end_time = time.time()
+    if model.verbose:
+        print(f'Total inference runtime: {model.end_time - start} seconds')
+    with open(os.path.join(args['outputdir'], 'input.yaml'), 'w') as fh:
+        yaml.safe_dump({k: (v if isinstance(v, (int, float, str, bool, list, dict, type(None))) else str(v)) for k, v in args.items()}, fh)
+    return samples

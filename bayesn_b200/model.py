@@ -140,6 +140,17 @@ class SEDmodel(object):
     def param_dim(self, rv_mode=native.RV_FIXED):
         return self.n_eps + (4 if rv_mode == native.RV_FIXED else 5)
 
+    def run(self, args, cmd_args=None):
+        """Reference :1735-1924 for the SNANA text branch, modes ``fitting`` and ``training_globalRV``
+        (``bayesn_b200/driver.py``)."""
+        from . import driver
+        return driver.run(self, args, cmd_args)
+
+    def process_dataset(self, args):
+        """Reference :2370-2730, SNANA text directory branch (``bayesn_b200/driver.py``)."""
+        from . import driver
+        return driver.process_dataset(self, args)
+
     def prepare_training(self, obs, weights, band_inds=None):
         """Upload a training set (``obs[1]``/``obs[2]`` in magnitudes, reference :2711-2730) and
         return the native context for ``train_logp_grad`` (``train_model_globalRV``, :1115-1182)."""

@@ -86,3 +86,22 @@ def write_snana_lcfile(output_dir, snname, mjd, flt, mag, magerr, tmax, z_helio,
             fh.write(f'OBS: {a:.5f} {b} {c:.5f} {d:.5f}\n')
         fh.write('END:\n')
     return path
+
+
+def write_snana_fluxfile(output_dir, snname, mjd, flt, fluxcal, fluxcalerr, peak_mjd, z_helio, z_final, z_err=5e-4,
+                         ebv_mw=0.0, filename=None, extra=None):
+    """SNANA text file with FLUXCAL photometry (the layout ``process_dataset`` reads, reference
+    :2577-2600: ``PEAKMJD``, ``REDSHIFT_HELIO``, ``REDSHIFT_FINAL``, columns MJD BAND FLUXCAL FLUXCALERR)."""
+    if filename is None:
+        filename = f'{snname}.DAT'
+    path = os.path.join(output_dir, filename)
+    with open(path, 'w') as fh:
+        fh.write(f'SNID: {snname}\nMWEBV: {ebv_mw}\nREDSHIFT_HELIO: {z_helio} +- {z_err}\n')
+        fh.write(f'REDSHIFT_FINAL: {z_final} +- {z_err}\nPEAKMJD: {peak_mjd}\n')
+        for k, v in (extra or {}).items():
+            fh.write(f'{k}: {v}\n')
+        fh.write(f'NOBS: {len(mjd)}\nNVAR: 4\nVARLIST: MJD BAND FLUXCAL FLUXCALERR\n')
+        for a, b, c, d in zip(mjd, flt, fluxcal, fluxcalerr):
+            fh.write(f'OBS: {a:.5f} {b} {c:.6f} {d:.6f}\n')
+        fh.write('END:\n')
+    return path

@@ -336,3 +336,44 @@ def test_batch_fit_postprocess_fitres_matches_host_summaries(tmp_path):
     txt = open(tmp_path / 't.FITRES.TEXT').read().splitlines()
     assert txt[5].startswith('VARNAMES: CID zHEL MWEBV MUHAT MU_LCFIT MUERR_LCFIT THETA THETAERR AV AVERR MEANRHAT MAXRHAT')
     assert sum(l.startswith('SN:') for l in txt) == 6
+
+
+def test_run_fitting_from_snana_text_directory(tmp_path):
+    """End to end like ``run_bayesn input.yaml`` with ``mode: fitting``: SNANA text files ->
+    process_dataset -> device band weights -> NUTS -> FITRES / chains.pkl / input.yaml; the fitted
+    distance moduli track the simulated ones."""
+    import pickle
+    from bayesn_b200 import SEDmodel, snana
+    m = SEDmodel(load_model='T21_model')
+    np.random.seed(3)
+    N = 6
+    z = np.random.uniform(0.02, 0.06, N)
+    tgrid = np.arange(-8, 36, 4.0)
+    flux, err, par = m.simulate_light_curve(tgrid, N, PS1, yerr=0.03, err_type='mag', z=z, mu='z', ebv_mw=0.01, mag=False)
+    d = tmp_path / 'SIMFIT'
+    d.mkdir()
+    bands = np.repeat(['g', 'r', 'i', 'z'], len(tgrid))
+    tt = np.tile(tgrid, 4)
+    files = []
+    for i in range(N):
+        snana.write_snana_fluxfile(str(d), f'{1000 + i}', 58000.0 + tt * (1 + z[i]), bands, flux[:, i], err[:, i], 58000.0,
+                                   z[i], z[i], ebv_mw=0.01)
+        files.append(f'{1000 + i}.DAT')
+    (d / 'SIMFIT.LIST').write_text('\n'.join(files) + '\n')
+    out = tmp_path / 'out'
+    args = dict(mode='fitting', version_photometry=str(d), outputdir=str(out), outfile_prefix='fit', num_warmup=150,
+                num_samples=100, map={'g': 'g_PS1', 'r': 'r_PS1', 'i': 'i_PS1', 'z': 'z_PS1'})
+    samples = m.run(args)
+    assert samples['theta'].shape == (4, 100, N) and samples['eps'].shape == (4, 100, 24, N)
+    assert samples['peak_MJD'].shape == (4, 100, N) and abs(samples['peak_MJD'].mean() - 58000.0) < 1.0
+    lines = (out / 'fit.FITRES.TEXT').read_text().splitlines()
+    rows = [l.split() for l in lines if l.startswith('SN:')]
+    head = [l for l in lines if l.startswith('VARNAMES:')][0].split()[1:]
+    assert len(rows) == N and rows[0][1] == '1000'
+    mu_fit = np.array([float(r[1 + head.index('MU_LCFIT')]) for r in rows])
+    mu_err = np.array([float(r[1 + head.index('MUERR_LCFIT')]) for r in rows])
+    truth = par['mu'] + par['del_M']
+    assert np.all(np.abs(mu_fit - truth) < 5 * mu_err + 0.05), (mu_fit, truth, mu_err)
+    assert (out / 'input.yaml').exists()
+    chains = pickle.load(open(out / 'chains.pkl', 'rb'))
+    assert chains['AV'].shape == (N, 4, 100)

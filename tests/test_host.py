@@ -201,3 +201,39 @@ def test_training_postprocess_sign_and_scale(tmp_path):
     back = yaml.safe_load(open(tmp_path / 'bayesn.yaml'))
     assert np.allclose(back['W0'], m.W0) and np.allclose(back['L_SIGMA_EPSILON'], 0.1 * np.eye(ne))
     assert (tmp_path / 'chains.pkl').exists() and (tmp_path / 'initial_chains.pkl').exists()
+
+
+def test_process_dataset_reads_snana_text_directory(tmp_path):
+    """Reference process_dataset, SNANA text branch (:2577-2730): phases, filter map, band drops,
+    padding, training magnitudes and masks."""
+    from bayesn_b200 import SEDmodel, snana
+    m = SEDmodel(load_model='T21_model')
+    d = tmp_path / 'SIMX'
+    d.mkdir()
+    rng = np.random.RandomState(0)
+    names = []
+    for i, (z, n) in enumerate([(0.03, 6), (0.05, 9)]):
+        mjd = 57000 + np.linspace(-5, 30, n) * (1 + z)
+        flt = np.array(['g', 'r', 'i'])[np.arange(n) % 3]
+        flux = rng.uniform(1e3, 1e4, n)
+        if i == 1:
+            flux[2] = -5.0                               # non-positive flux: masked in training
+            mjd[0] = 57000 - 30 * (1 + z)                # outside the tau-knot range: dropped
+        snana.write_snana_fluxfile(str(d), f'sn{i}', mjd, flt, flux, 0.05 * np.abs(flux), 57000.0, z, z + 0.001, ebv_mw=0.02 * i)
+        names.append(f'sn{i}.DAT')
+    (d / 'SIMX.LIST').write_text('\n'.join(names) + '\n')
+    args = dict(mode='fitting', version_photometry=str(d), map={'g': 'g_PS1', 'r': 'r_PS1', 'i': 'i_PS1'})
+    ds = m.process_dataset(args)
+    obs = ds['obs']
+    assert obs.shape == (10, 8, 2) and ds['sn_names'] == ['sn0', 'sn1']
+    assert list(ds['band_inds']) == [0, m.band_dict['g_PS1'], m.band_dict['r_PS1'], m.band_dict['i_PS1']]
+    assert obs[9, :, 0].sum() == 6 and obs[9, :, 1].sum() == 8
+    assert np.allclose(obs[0, :6, 0], np.linspace(-5, 30, 6)) and np.all(obs[4, :6, 0] == [1, 2, 3, 1, 2, 3])
+    assert np.isclose(obs[7, 0, 1], m.cosmo.distmod(np.array([0.051]))[0]) and obs[8, 0, 1] == 0.02
+    assert np.allclose(obs[2, 6:, 0], 1 / np.sqrt(2 * np.pi)) and np.all(obs[1, 6:, 0] == 0)
+    tr = m.process_dataset(dict(args, mode='training_globalRV'))['obs']
+    assert tr[9, :, 1].sum() == 7                        # the negative flux is masked
+    k = int(np.argmin(tr[9, :8, 1]))
+    assert tr[1, k, 1] == 0 and tr[4, k, 1] == 0
+    good = tr[9, :, 0] != 0
+    assert np.allclose(tr[1, good, 0], 27.5 - 2.5 * np.log10(obs[1, good, 0]))
