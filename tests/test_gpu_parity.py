@@ -377,3 +377,26 @@ def test_run_fitting_from_snana_text_directory(tmp_path):
     assert (out / 'input.yaml').exists()
     chains = pickle.load(open(out / 'chains.pkl', 'rb'))
     assert chains['AV'].shape == (N, 4, 100)
+
+
+def test_get_flux_from_chains_shapes_and_values():
+    """Reference get_flux_from_chains (:3426-3524): (N_sne, num_samples, n_bands, len(t)) model photometry
+    of posterior draws; the first draw equals a direct get_flux_batch call at those parameters."""
+    samples, (z, ebv) = _fit_2016w()
+    from bayesn_b200 import SEDmodel
+    m = SEDmodel(load_model='T21_model')
+    t = np.arange(-5, 30, 5.0)
+    bands = ['g_PS1', 'r_PS1']
+    fg = m.get_flux_from_chains(t, bands, samples, z, ebv, mag=False, num_samples=8)
+    assert fg.shape == (1, 8, 2, len(t)) and np.all(np.isfinite(fg)) and np.all(fg > 0)
+    fm = m.get_flux_from_chains(t, bands, samples, z, ebv, mag=True, mean=True)
+    assert fm.shape == (1, 1, 2, len(t))
+    # first draw (chains flattened in Fortran order, as the reference does) through simulate_light_curve
+    fl = lambda k: samples[k][..., 0].flatten(order='F')[0]
+    eps = samples['eps'][..., 0]
+    eps = eps.reshape((eps.shape[0] * eps.shape[1], eps.shape[2]), order='F')[0].reshape((4, 6), order='F')
+    eps_full = np.zeros((1, 6, 6))
+    eps_full[0, 1:-1] = eps
+    lc, _, _ = m.simulate_light_curve(t, 1, bands, theta=fl('theta'), AV=fl('AV'), mu=fl('mu'), tmax=fl('tmax'),
+                                      del_M=fl('delM'), eps=eps_full, z=z, ebv_mw=ebv, yerr=0, mag=False)
+    assert np.allclose(fg[0, 0], lc[:, 0].reshape(2, len(t)), rtol=1e-5)
