@@ -200,7 +200,7 @@ int launch_train_reduce(bayesn_ctx* ctx, const float* lat, size_t chain_stride, 
     const int nchunk = (ctx->D.N + TRAIN_RCHUNK - 1) / TRAIN_RCHUNK;
     const size_t smem = (size_t)TRAIN_RCHUNK * (T.PR + ctx->M.n_eps + 2) * sizeof(float);
     CU_CHECK(ctx, cudaFuncSetAttribute(train_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    train_reduce_kernel<<<dim3(nchunk, T.C), 256, smem, st>>>(ctx->M, T, ctx->D.N, ctx->LP, ctx->TP, lat, chain_stride,
+    train_reduce_kernel<<<dim3(nchunk, T.C, (T.R + 255) / 256), 256, smem, st>>>(ctx->M, T, ctx->D.N, ctx->LP, ctx->TP, lat, chain_stride,
                                                               sn_stride, T.rpart);
     train_reduce_final_kernel<<<dim3((T.R + 255) / 256, T.C), 256, 0, st>>>(T, nchunk, T.rpart, red, ctx->X);
     ctx->launches += 2;

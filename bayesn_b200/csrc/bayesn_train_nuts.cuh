@@ -254,24 +254,26 @@ __device__ __forceinline__ void gcopy(const GVec& W, int dst, int src) {
 }
 
 // block-wide sums of NV per-thread partials (NV <= 32); every thread gets all totals in out[]
+// only the values whose bit is set in `need` are reduced (the others come back as 0)
 template <int NV>
-__device__ __forceinline__ void block_sums(float (&v)[NV], float* sh /* [8][NV] */, float (&out)[NV]) {
+__device__ __forceinline__ void block_sums(float (&v)[NV], float* sh /* [8][NV] */, float (&out)[NV],
+                                           unsigned need = 0xffffffffu) {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        float x = v[k];
-        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
-        v[k] = x;
+        if ((need >> k) & 1u) {
+            float x = v[k];
+            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+            if (l == 0) sh[w * NV + k] = x;
+        }
     }
-    __syncthreads();
-    if (l == 0)
-        for (int k = 0; k < NV; ++k) sh[w * NV + k] = v[k];
     __syncthreads();
     const int nw = blockDim.x >> 5;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         float t = 0.f;
-        for (int i = 0; i < nw; ++i) t += sh[i * NV + k];
+        if ((need >> k) & 1u)
+            for (int i = 0; i < nw; ++i) t += sh[i * NV + k];
         out[k] = t;
     }
     __syncthreads();
@@ -348,7 +350,15 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
         }
     }
     CTL_T(3);
-    block_sums<TRAIN_NX>(pv, shsum, tot);
+    {
+        // kinetic energy always; the checkpoint pairs idx_min..idx_max and the whole-tree pair only when this leaf uses them
+        unsigned need = 1u;
+        if (running) {
+            for (int k = idx_min; k <= idx_max; ++k) need |= 3u << (2 + 2 * k);
+            if (leaf + 1 == sctl.n_max) need |= 3u << (TRAIN_NX - 2);
+        }
+        block_sums<TRAIN_NX>(pv, shsum, tot, need);
+    }
     CTL_T(4);
 
     // ---- 3. scalar decisions (thread 0), mirrored from nuts_kernel ------------------------------------
