@@ -610,7 +610,10 @@ int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream) {
 int bayesn_train_nuts_ctl(bayesn_ctx* ctx, double* red, void* stream) {
     if (!ctx) return -1;
     if (!ctx->have_tn) return fail(ctx, -1, "bayesn_train_nuts_init first");
-    train_nuts_ctl_kernel<<<ctx->T.C, 256, (size_t)ctx->M.n_eps * ctx->M.n_eps * sizeof(float), (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->TN, ctx->LP, ctx->TP, red, ctx->X);
+    const size_t csm = (size_t)ctx->T.R * sizeof(double) +
+                       ((size_t)ctx->M.n_eps * ctx->M.n_eps + ctx->T.G) * sizeof(float);
+    CU_CHECK(ctx, cudaFuncSetAttribute(train_nuts_ctl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+    train_nuts_ctl_kernel<<<ctx->T.C, 256, csm, (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->TN, ctx->LP, ctx->TP, red, ctx->X);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;

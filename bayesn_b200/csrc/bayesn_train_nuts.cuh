@@ -284,7 +284,13 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
     __shared__ TrainShared S;
     __shared__ float shsum[8 * TRAIN_NX];
     __shared__ TrainCtl sctl;
-    extern __shared__ __align__(16) float tmat[];      // n_eps^2 floats: scratch of the stick-breaking row scans
+    // dynamic shared memory: [R doubles: this chain's reduced sums | n_eps^2 floats: scratch of the
+    // stick-breaking row scans | G floats: the unconstrained global position].  Staging the sums and the
+    // position once turns the ~25 dependent global-memory phases of this kernel into shared-memory ones.
+    extern __shared__ __align__(16) unsigned char ctl_smem[];
+    double* red_s = reinterpret_cast<double*>(ctl_smem);
+    float* tmat = reinterpret_cast<float*>(red_s + Tr.R);
+    float* qg_s = tmat + M.n_eps * M.n_eps;
     const int c = blockIdx.x, tid = threadIdx.x;
     const int G = Tr.G;
     const NutsDev& cfg = Nt.cfg;
@@ -297,17 +303,20 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
     }
     // sums of the other ranks' SN shards (fused peer-memory exchange; no-op on one GPU / with NCCL)
     xchg_gather(X, Tr, c, red_all);
-    const double* red = red_all + (size_t)c * Tr.R;
-    const double* rx = red + train_red_base(Tr.LPTP, M.n_eps);
     const int nvec = train_nuts_num_vectors(cfg.max_depth);
     GVec W{Nt.work_g + (size_t)c * nvec * G, G};
+    for (int r = tid; r < Tr.R; r += blockDim.x) red_s[r] = red_all[(size_t)c * Tr.R + r];
+    for (int i = tid; i < G; i += blockDim.x) qg_s[i] = W.v(TV_CZ)[i];
+    __syncthreads();
+    const double* red = red_s;
+    const double* rx = red + train_red_base(Tr.LPTP, M.n_eps);
     float* gnew = Nt.gtmp + (size_t)c * G;
     const uint2 key = make_uint2(cfg.seed_lo, cfg.seed_hi);
     const uint32_t gkey = 0x7fff0000u + (uint32_t)c;          // stream id of the global slice of chain c
 
     // ---- 1. finish the evaluation made at CZ: gradient of the potential wrt the unconstrained globals
     CTL_T(1);
-    train_finish_dev(M, Tr, LP, TP, c, W.v(TV_CZ), red, gnew, -1.f, tmat);
+    train_finish_dev(M, Tr, LP, TP, c, qg_s, red, gnew, -1.f, tmat);
     __syncthreads();
     CTL_T(2);
     const double pe_new = -(red[0] + Tr.lpg[c]);
@@ -567,12 +576,14 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
         for (int i = tid; i < G; i += blockDim.x) {
             const float ri = fmaf(-0.5f * e2, cg[i], cr[i]);
             cr[i] = ri;
-            cz[i] = fmaf(e2 * imv[i], ri, cz[i]);
+            const float zi = fmaf(e2 * imv[i], ri, cz[i]);
+            cz[i] = zi;
+            qg_s[i] = zi;
         }
     }
     __syncthreads();
     CTL_T(7);
-    train_globals_dev(M, Tr, LP, TP, c, W.v(TV_CZ), S, tmat);
+    train_globals_dev(M, Tr, LP, TP, c, qg_s, S, tmat);
     CTL_T(8);
     if (tid == 0) Nt.ctl[c] = sctl;
 }
