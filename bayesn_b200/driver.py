@@ -3,8 +3,9 @@
 branch: a directory ``<version_photometry>/`` holding ``<name>.LIST`` and one SNANA text file per
 object.  Modes ``fitting`` (``fit_method: mcmc``) and ``training_globalRV``; same YAML keys and
 defaults, same output files (``chains.pkl``, ``input.yaml``, ``<prefix>.FITRES.TEXT``; training:
-``bayesn.yaml``, ``initial_chains.pkl``).  Out of scope here: SNANA FITS input, ``data_table``
-input, SNANA cluster conventions (``jobsplit`` directory search), the VI and dust modes, LCPLOT.
+``bayesn.yaml``, ``initial_chains.pkl``; fitting also ``<prefix>.LCPLOT``).  Out of scope here: SNANA
+FITS input, ``data_table`` input, SNANA cluster conventions (``jobsplit`` directory search), the VI
+and dust modes.
 """
 import os
 import time
@@ -94,6 +95,7 @@ def process_dataset(model, args):
             if g not in used:
                 used.append(int(g))
         lcs.append(dict(t=t[keep], flux=flux[keep], ferr=ferr[keep], gl=gl[keep], z=zhel, zerr=zhel_err,
+                        mjd=lc['MJD'][keep], flt=flt[keep],
                         mu=float(model.cosmo.distmod(np.array([zhd]))[0]), ebv=float(meta.get('MWEBV', 0.0)),
                         mass=float(meta.get('HOSTGAL_LOGMASS', -9.0))))
         names.append(str(meta.get('SNID', fn)))
@@ -122,8 +124,33 @@ def process_dataset(model, args):
             obs[9, :n, i] = 1
         obs[4, :n, i] = np.where(obs[9, :n, i] != 0, [local[g] for g in l['gl']], 0)
         obs[3, :, i], obs[5, :, i], obs[6, :, i], obs[7, :, i], obs[8, :, i] = l['mass'], l['z'], l['zerr'], l['mu'], l['ebv']
-    return dict(obs=obs, band_inds=band_inds, sn_names=names, peak_mjds=np.array(peaks),
+    lcplot = [dict(CID=names[i], MJD=l['mjd'], FLUXCAL=l['flux'], FLUXCALERR=l['ferr'], FLT=l['flt']) for i, l in enumerate(lcs)]
+    return dict(obs=obs, band_inds=band_inds, sn_names=names, peak_mjds=np.array(peaks), lcplot=lcplot,
                 fitres={k: np.array(v) for k, v in cols.items()})
+
+
+def write_lcplot(model, path, ds, samples, save_fit_errors=False):
+    """``<prefix>.LCPLOT`` (reference :2256-2293): the photometry that was fitted (DATA_FLAG 1) followed
+    by the model light curve of every SN on a 2-day rest-frame grid in its own bands (DATA_FLAG 0):
+    the curve at the posterior mean, or mean / std over the draws with ``save_fit_errors``."""
+    import pandas as pd
+    t = np.arange(model.tau_knots[0], model.tau_knots[-1], 2)
+    z_hel, ebv = ds['obs'][5, 0, :], ds['obs'][8, 0, :]
+    bands = [list(pd.unique(l['FLT'])) for l in ds['lcplot']]
+    f = model.get_flux_from_chains(t, bands, samples, z_hel, ebv, num_samples=None, mag=False, mean=not save_fit_errors)
+    fm, fe = f.mean(axis=1), f.std(axis=1)
+    frames = []
+    for i, l in enumerate(ds['lcplot']):
+        d = pd.DataFrame({'CID': l['CID'], 'MJD': l['MJD'], 'FLUXCAL': l['FLUXCAL'], 'FLUXCALERR': l['FLUXCALERR'],
+                          'FLT': l['FLT'], 'DATA_FLAG': 1})
+        nb = len(bands[i])
+        fit = pd.DataFrame({'CID': l['CID'], 'MJD': (ds['peak_mjds'][i] + t * (1 + z_hel[i])).repeat(nb),
+                            'FLUXCAL': fm[i, :nb, :].flatten(order='F'), 'FLUXCALERR': fe[i, :nb, :].flatten(order='F'),
+                            'FLT': np.tile(bands[i], len(t)), 'DATA_FLAG': 0})
+        frames += [d, fit]
+    out = pd.concat(frames).sort_values(by=['CID', 'DATA_FLAG', 'MJD'])
+    out.to_csv(path, index=False)
+    return out
 
 
 def run(model, args, cmd_args=None):
@@ -151,6 +178,13 @@ def run(model, args, cmd_args=None):
         for k, v in cons.items():
             v = v.cpu().numpy().astype(np.float64)
             samples[k] = (v.transpose(1, 2, 3, 0) if k == 'eps' else v.transpose(1, 2, 0, 3)) if v.ndim == 4 else v.transpose(1, 2, 0)
+        muhat = ds['obs'][7, 0, :][None, None, :]
+        s0 = float(model.sigma0)
+        samples['mu'] = np.random.normal((samples['Ds'] * 25.0 + muhat * s0 ** 2) / (25.0 + s0 ** 2),
+                                         np.sqrt(s0 ** 2 * 25.0 / (25.0 + s0 ** 2)))        # reference :2250-2254
+        samples['delM'] = samples['Ds'] - samples['mu']
+        write_lcplot(model, os.path.join(args['outputdir'], f'{args["outfile_prefix"]}.LCPLOT'), ds, samples,
+                     args['save_fit_errors'])
         if 'tmax' in samples:
             samples['peak_MJD'] = ds['peak_mjds'][None, None, :] + samples['tmax'] * (1 + ds['obs'][5, 0, :][None, None, :])
     elif mode == 'training_globalrv':

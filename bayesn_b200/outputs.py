@@ -4,9 +4,8 @@ fitting branch): distance-modulus draws, per-SN summaries with split R-hat, ``FI
 
 The per-SN reductions run on the device on the (N, C, S, D) draw tensor that the NUTS kernel
 wrote, so that only ~10 floats per SN leave the GPU (100k SNe x 4 x 250 x 58 draws are 23 GB and
-never need to reach the host for a FITRES table).  LCPLOT is not produced here (it needs the
-data-ingest frame of ``process_dataset``, out of scope); ``SEDmodel.get_flux_from_chains`` gives
-the model light curves it is made of.
+never need to reach the host for a FITRES table).  ``<prefix>.LCPLOT`` is written by
+``bayesn_b200.driver.write_lcplot`` (it needs the photometry frame of ``process_dataset``).
 """
 import math
 import os

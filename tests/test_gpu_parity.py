@@ -375,6 +375,15 @@ def test_run_fitting_from_snana_text_directory(tmp_path):
     truth = par['mu'] + par['del_M']
     assert np.all(np.abs(mu_fit - truth) < 5 * mu_err + 0.05), (mu_fit, truth, mu_err)
     assert (out / 'input.yaml').exists()
+    import pandas as pd
+    lcp = pd.read_csv(out / 'fit.LCPLOT')
+    assert list(lcp.columns) == ['CID', 'MJD', 'FLUXCAL', 'FLUXCALERR', 'FLT', 'DATA_FLAG']
+    assert (lcp.DATA_FLAG == 1).sum() == N * len(tt) and (lcp.DATA_FLAG == 0).sum() == N * 4 * len(np.arange(-10, 40, 2))
+    one = lcp[(lcp.CID == 1000) & (lcp.FLT == 'r_PS1')]
+    # the model curve at the posterior mean passes through the data (3 % errors)
+    dat, fit = one[one.DATA_FLAG == 1], one[one.DATA_FLAG == 0]
+    interp = np.interp(dat.MJD.values, fit.MJD.values, fit.FLUXCAL.values)
+    assert np.median(np.abs(interp / dat.FLUXCAL.values - 1)) < 0.06
     chains = pickle.load(open(out / 'chains.pkl', 'rb'))
     assert chains['AV'].shape == (N, 4, 100)
 
