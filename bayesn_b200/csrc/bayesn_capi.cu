@@ -501,6 +501,24 @@ int bayesn_flux_batch(bayesn_ctx* ctx, int N, int N_obs, int n_b, int mag, float
 }
 
 
+int bayesn_spectra_batch(bayesn_ctx* ctx, int N, int N_obs, const float* theta, const float* AV, const float* W0,
+                         const float* W1, const float* eps, const float* RV, const float* J_t, const float* hsiao_interp,
+                         float* out, void* stream) {
+    if (!ctx) return -1;
+    if (!ctx->have_model) return fail(ctx, -1, "set_model first");
+    if (N <= 0 || N_obs <= 0) return 0;
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    FluxArgs A{};
+    A.N = N; A.N_obs = N_obs; A.L = ctx->M.L; A.T = ctx->M.T;
+    A.theta = theta; A.AV = AV; A.W0 = W0; A.W1 = W1; A.eps = eps; A.RV = RV; A.J_t = J_t; A.hsi = hsiao_interp;
+    A.Jl = ctx->M.Jl; A.hs = ctx->M.hs; A.Mf = ctx->M.Mf; A.LPs = jl_row_stride(ctx->LP); A.out = out;
+    const long long items = (long long)N * N_obs;
+    spectra_kernel<<<(unsigned)((items + 3) / 4), 128, 0, (cudaStream_t)stream>>>(A);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
 int bayesn_train_dims(bayesn_ctx* ctx, int* G, int* Dl, int* R) {
     if (!ctx || !ctx->have_model) return -1;
     const int ne = ctx->M.n_eps, L = ctx->M.L, T = ctx->M.T;

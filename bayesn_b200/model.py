@@ -3,8 +3,8 @@ for the hot path.  Same constructor, attributes, method names, argument meaning 
 layouts; the arithmetic runs in the sm_100a kernels behind ``libbayesn_b200.so``.
 
 What is kept from the reference API (file:line = ``bayesn/bayesn_model.py``):
-``SEDmodel(num_devices, load_model, filter_yaml, fiducial_cosmology)`` :199, ``get_spectra`` is
-not exposed (the kernels never materialise spectra), ``get_flux_batch`` :645, ``get_mag_batch``
+``SEDmodel(num_devices, load_model, filter_yaml, fiducial_cosmology)`` :199, ``get_spectra`` :556
+(the fit kernels never materialise spectra; this is a separate forward kernel), ``get_flux_batch`` :645, ``get_mag_batch``
 :711, ``fit`` :1994, ``fit_from_file`` :1926, ``simulate_light_curve`` :3103, ``sample_*``
 :3347-3424, ``get_flux_from_chains`` :3426, plus ``fit_batch`` (the vmapped per-object fit of
 ``run`` :1809-1849 as a plain method).  numpyro models are replaced by ``logp_grad`` (the
@@ -286,6 +286,19 @@ class SEDmodel(object):
         out = ctx.flux_batch(M0, theta, to(AV), to(W0), to(W1), to(eps), to(Ds), to(RV),
                              to(band_indices, torch.int32), to(np.asarray(mask) != 0, torch.uint8), to(J_t),
                              to(hsiao_interp), to(weights), bls, mag=mag)
+        return out.cpu().numpy().astype(np.float64)
+
+    def get_spectra(self, theta, AV, W0, W1, eps, RV, J_t, hsiao_interp):
+        """Reference :556-643: rest-frame, host-dust-extinguished SEDs (N, 300, N_obs) on the model grid."""
+        import torch
+        dev = f'cuda:{self._device_index()}'
+        ctx = self._ctxs.get(('fwd',))
+        if ctx is None:
+            ctx = self._ctxs[('fwd',)] = self._context(native.RV_FIXED)
+        to = lambda a: torch.as_tensor(np.array(a), device=dev).to(torch.float32)
+        theta = to(theta)
+        RV = np.broadcast_to(np.asarray(RV, dtype=np.float64), (theta.shape[0],))
+        out = ctx.spectra_batch(theta, to(AV), to(W0), to(W1), to(eps), to(RV), to(J_t), to(hsiao_interp))
         return out.cpu().numpy().astype(np.float64)
 
     def get_flux_batch(self, M0, theta, AV, W0, W1, eps, Ds, RV, band_indices, mask, J_t, hsiao_interp, weights):

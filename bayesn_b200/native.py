@@ -53,7 +53,7 @@ EXPORTS = ['bayesn_abi_version', 'bayesn_ctx_create', 'bayesn_ctx_destroy', 'bay
            'bayesn_flux_batch', 'bayesn_nuts_workspace_bytes', 'bayesn_nuts_fit', 'bayesn_launch_count',
            'bayesn_init_to_median', 'bayesn_ffma_peak', 'bayesn_train_dims', 'bayesn_train_begin',
            'bayesn_train_finish', 'bayesn_train_nuts_init', 'bayesn_train_nuts_sn', 'bayesn_train_nuts_ctl',
-           'bayesn_train_nuts_status', 'bayesn_tiles_support', 'bayesn_tiles_fill', 'bayesn_train_set_exchange']
+           'bayesn_train_nuts_status', 'bayesn_tiles_support', 'bayesn_tiles_fill', 'bayesn_train_set_exchange', 'bayesn_spectra_batch']
 
 _lib = None
 
@@ -86,6 +86,7 @@ def load_library():
     lib.bayesn_init_to_median.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.bayesn_ffma_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.bayesn_launch_count.restype = C.c_longlong
+    lib.bayesn_spectra_batch.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 10
     lib.bayesn_tiles_support.argtypes = [C.c_void_p, C.POINTER(TilesDesc), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bayesn_tiles_fill.argtypes = [C.c_void_p, C.POINTER(TilesDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.bayesn_train_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
@@ -438,6 +439,19 @@ class Context:
                 raise RuntimeError('peer-memory exchange timed out waiting for a rank')
             dist.barrier(group)
             self.disable_train_exchange()
+        return out
+
+    def spectra_batch(self, theta, AV, W0, W1, eps, RV, J_t, hsiao_interp):
+        """get_spectra with the reference's array layouts (CUDA tensors) -> (N, 300, N_obs)."""
+        import torch
+        f32 = lambda t: t.to(torch.float32).contiguous()
+        theta, AV, W0, W1, eps, RV, J_t, hsiao_interp = map(f32, (theta, AV, W0, W1, eps, RV, J_t, hsiao_interp))
+        N, N_obs = theta.shape[0], J_t.shape[2]
+        out = torch.empty((N, NBINS, N_obs), dtype=torch.float32, device=theta.device)
+        self._check(self.lib.bayesn_spectra_batch(self.h, N, N_obs, theta.data_ptr(), AV.data_ptr(), W0.data_ptr(),
+                                                  W1.data_ptr(), eps.data_ptr(), RV.data_ptr(), J_t.data_ptr(),
+                                                  hsiao_interp.data_ptr(), out.data_ptr(), self._stream()),
+                    'bayesn_spectra_batch')
         return out
 
     def flux_batch(self, M0, theta, AV, W0, W1, eps, Ds, RV, band_indices, mask, J_t, hsiao_interp, weights,

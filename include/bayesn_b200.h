@@ -136,6 +136,12 @@ int bayesn_flux_batch(bayesn_ctx* ctx, int N, int N_obs, int n_b, int mag, float
                       const float* hsiao_interp, const float* weights, const double* band_log10_scale, float* out,
                       void* stream);
 
+/* SEDmodel.get_spectra (bayesn/bayesn_model.py:556-643): host-dust-extinguished rest-frame SEDs on
+ * the 300-bin model grid, same argument meaning as bayesn_flux_batch; out [N][300][N_obs]. */
+int bayesn_spectra_batch(bayesn_ctx* ctx, int N, int N_obs, const float* theta, const float* AV, const float* W0,
+                         const float* W1, const float* eps, const float* RV, const float* J_t, const float* hsiao_interp,
+                         float* out, void* stream);
+
 /* Device-resident batched NUTS over every (SN, chain) of the bound data set: replaces the
  * numpyro MCMC(NUTS(fit_model_*)) runs at bayesn/bayesn_model.py:1830-1837 and :2128-2141.
  *   q_init  [N][C][D]           device, in   initial unconstrained positions

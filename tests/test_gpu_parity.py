@@ -107,6 +107,11 @@ def test_forward_flux_and_mag_parity():
     # weights columns follow the oracle's band order -> pass the matching global band indices
     f_gpu = m._forward(False, *args_np, band_inds=bi)
     m_gpu = m._forward(True, *args_np, band_inds=bi)
+    # get_spectra (reference :556-643): (N, 300, N_obs) host-dust-extinguished rest-frame SEDs
+    s_ref = ref.get_spectra(tt(p['theta']), tt(p['AV']), tt(ref.W0), tt(ref.W1), tt(p['eps']), tt(RV), J_t, hsi).numpy()
+    s_gpu = m.get_spectra(p['theta'], p['AV'], ref.W0, ref.W1, p['eps'], RV, J_t.numpy(), hsi.numpy())
+    assert s_gpu.shape == s_ref.shape == (N, 300, obs.shape[1])
+    assert np.max(np.abs(s_gpu - s_ref) / np.abs(s_ref)) < 1e-5
     sel = mask
     assert np.max(np.abs(f_gpu[sel] - f_ref[sel]) / np.abs(f_ref[sel])) < 1e-5
     assert np.max(np.abs(m_gpu[sel] - m_ref[sel])) < 2e-5
