@@ -358,10 +358,12 @@ class SEDmodel(object):
 
     def fit_batch(self, obs, weights, band_inds=None, num_chains=4, num_warmup=250, num_samples=250,
                   max_tree_depth=10, seed=0, RV=None, fix_tmax=False, fix_theta=False, theta_val=0.0, fix_AV=False,
-                  AV_val=0.0, init='median', return_device=False, q_init=None):
+                  AV_val=0.0, init='median', return_device=False, q_init=None, sn_offset=0):
         """Independent NUTS fits of N supernovae (the vmapped ``fit_vmap_mcmc`` of reference
         :1809-1849).  Returns (samples dict with arrays shaped (chains, draws, [dim,] N) like
-        the reference after :1839-1848, extras dict)."""
+        the reference after :1839-1848, extras dict).  ``sn_offset``: index of the first SN of
+        ``obs`` in the whole job when SNe are sharded over GPUs - the random streams are keyed by
+        the global SN index, so a shard reproduces the single-GPU draws bit for bit."""
         import torch
         rv_mode = self._rv_mode(RV)
         ctx = self.prepare(obs, weights, band_inds, rv_mode, fix_tmax=bool(fix_tmax), fix_theta=bool(fix_theta),
@@ -369,9 +371,9 @@ class SEDmodel(object):
         dev = f'cuda:{ctx.device}'
         muhat = np.asarray(obs)[-3, 0, :]
         if q_init is None:
-            q_init = self.init_to_median(muhat, num_chains, rv_mode, seed=seed, device=dev)
+            q_init = ctx.init_to_median(num_chains, seed=seed, sn_offset=sn_offset)      # device kernel
         out = ctx.nuts(q_init, num_warmup=num_warmup, num_samples=num_samples, max_tree_depth=max_tree_depth,
-                       seed=seed)
+                       seed=seed, sn_offset=sn_offset)
         torch.cuda.synchronize()
         cons = self.constrain(out['samples'], rv_mode)     # (N, C, S, ...)
         if return_device:
