@@ -1,8 +1,9 @@
 // bayesn_device.cuh - device code of the BayeSN hot path for sm_100a.
 //
-// One warp owns one (supernova, chain) pair.  The 32 lanes split the wavelength bins of the
-// band-pass integral; the per-observation sums (flux and the adjoint moments) are combined with
-// a transposed warp-shuffle reduction.  A CTA is 4 warps; the warps of a CTA that work on the
+// One warp owns one (supernova, chain) pair.  Observations are processed two at a time: 16 lanes
+// (even lanes / odd lanes) over the wavelength bins of each, only over the band's non-zero support;
+// the per-observation sums (flux and the adjoint moments) of both are combined with one transposed
+// warp-shuffle reduction.  A CTA is 4 warps; the warps of a CTA that work on the
 // same supernova share its band-weight tile, which is staged in shared memory with a 1-D TMA
 // bulk copy (cp.async.bulk + mbarrier) together with the wavelength-spline matrix J_l.
 //
@@ -258,7 +259,7 @@ __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b
     p.wDad = wtake(rvfree ? JROWS : 0);
     p.warpStride = w;
     // Lanes that have run past their band's support keep reading (and discard) up to OVERRUN bins
-    // beyond it while the other half-warp finishes a wider band: keep those reads inside the CTA's
+    // beyond it while the other observation of the pair finishes a wider band: keep those reads inside the CTA's
     // allocation (only the per-chain dust arrays of the sampled-RV fits sit at its very end).
     p.totalFloats = o + WPB * w + (rvfree ? OVERRUN : 0);
     const int jl_reach = p.oJl + (NB + OVERRUN) * jl_row_stride(LP);
@@ -469,7 +470,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     __syncwarp();
 
     // ---- per-observation setup, lanes over observations -------------------------------------
-    // Observations are processed in pairs (one per half-warp); an odd count is completed by a
+    // Observations are processed in pairs (16 interleaved lanes each); an odd count is completed by a
     // dummy copy of the last observation with 1/sigma = 0, which contributes exactly nothing.
     const int npair = (c.nobs + 1) >> 1;
     if (lane == 0) c.sc[0] = S;
