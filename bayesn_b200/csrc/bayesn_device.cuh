@@ -21,6 +21,16 @@
 
 #include "bayesn_b200.h"
 
+// -DBAYESN_BOUNDS_CHECK: device-side asserts on every address of the band-pass loop (lanes past the end
+// of a band's support deliberately keep reading - and discarding - up to BAYESN_OVERRUN elements; this
+// build proves those reads stay inside the allocations; compute-sanitizer is closed on the GPU pool)
+#ifdef BAYESN_BOUNDS_CHECK
+#include <assert.h>
+#define BAYESN_ASSERT(x) assert(x)
+#else
+#define BAYESN_ASSERT(x)
+#endif
+
 namespace bayesn {
 
 constexpr int NB = BAYESN_NBINS;
@@ -283,6 +293,7 @@ struct WarpCtx {
     const float *ad_g, *dad_g;      // dust basis a[b](RV) and da/dRV, [JROWS] each, global memory
     float sigma0, tauA, muerr2;
     float* part;                    // [LP*TP + 5]: dW, d/dsigma0, d/dRV, d/dtauA, log p (two floats of a double)
+    const float *smem_lo, *smem_hi, *wt_lo, *wt_hi, *hs_hi;   // allocation bounds (BAYESN_BOUNDS_CHECK builds)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -560,6 +571,10 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
                 const float4 v = pj[j];
                 jl[4 * j] = v.x; jl[4 * j + 1] = v.y; jl[4 * j + 2] = v.z; jl[4 * j + 3] = v.w;
             }
+            BAYESN_ASSERT((const float*)pj >= c.smem_lo && (const float*)(pj + LP4 / 4) <= c.smem_hi);
+            BAYESN_ASSERT(STAGE ? (pw >= c.smem_lo && pw < c.smem_hi) : (pw >= c.wt_lo && pw < c.wt_hi));
+            BAYESN_ASSERT(p0 >= hs && p0 + BP < c.hs_hi);
+            BAYESN_ASSERT(TRAIN || (pa >= c.smem_lo && pa < c.smem_hi));
             const float wl = STAGE ? *pw : __ldg(pw);
             const float h0 = __ldg(p0), h1 = __ldg(p0 + BP);
             const float a = TRAIN ? __ldg(pa) : *pa;
@@ -819,6 +834,11 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
     c.ad_g = c.dad_g = nullptr;
     c.part = nullptr;
     c.sigma0 = c.tauA = c.muerr2 = 0.f;
+    c.smem_lo = smem;
+    c.smem_hi = smem + P.totalFloats;
+    c.wt_lo = Dd.wt;
+    c.wt_hi = Dd.wt + (size_t)Dd.N * Dd.wt_stride + OVERRUN + 32;
+    c.hs_hi = M.hs + (NPH + 1) * BP + OVERRUN + 32;
     return active;
 }
 
