@@ -237,3 +237,22 @@ def test_process_dataset_reads_snana_text_directory(tmp_path):
     assert tr[1, k, 1] == 0 and tr[4, k, 1] == 0
     good = tr[9, :, 0] != 0
     assert np.allclose(tr[1, good, 0], 27.5 - 2.5 * np.log10(obs[1, good, 0]))
+
+
+def test_parse_yaml_input_defaults_and_errors(tmp_path):
+    """Reference parse_yaml_input :1656-1709: defaults, command-line overrides, fit_method validation."""
+    import argparse
+    from bayesn_b200 import SEDmodel, driver
+    m = SEDmodel(load_model='T21_model')
+    a = driver.parse_yaml_input(m, {'mode': 'fitting', 'outputdir': str(tmp_path / 'o')})
+    assert (a['num_chains'], a['num_warmup'], a['num_samples'], a['fit_method'], a['initialisation']) == (4, 500, 500, 'mcmc', 'median')
+    assert a['outfile_prefix'] == 'output' and a['l_knots'] == m.l_knots.tolist() and (tmp_path / 'o').is_dir()
+    cmd = argparse.Namespace(input='x.yaml', filters=None, num_warmup=100, num_samples=None)
+    a = driver.parse_yaml_input(m, {'mode': 'fitting', 'num_warmup': 250, 'outputdir': str(tmp_path)}, cmd)
+    assert a['num_warmup'] == 100 and a['num_samples'] == 500 and 'input' not in a
+    with pytest.raises(ValueError):
+        driver.parse_yaml_input(m, {'mode': 'fitting', 'fit_method': 'laplace', 'outputdir': str(tmp_path)})
+    with pytest.raises(NotImplementedError):
+        driver.parse_yaml_input(m, {'mode': 'fitting', 'fit_method': 'VI', 'outputdir': str(tmp_path)})
+    with pytest.raises(ValueError):
+        driver.process_dataset(m, {'mode': 'fitting'})
