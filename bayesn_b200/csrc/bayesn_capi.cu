@@ -119,7 +119,8 @@ int train_prepare(bayesn_ctx* ctx, int C) {
 struct Combo { int LP, TP, VPL; };
 const Combo kCombos[] = {{6, 6, 1}, {9, 6, 2}, {11, 6, 2}, {10, 9, 3}, {12, 10, 4}};
 
-int ntile_for(int C) { return (C % WPB == 0) ? 1 : (C == 1 ? WPB : 2); }
+// capacity (number of distinct SNe) of a CTA of WPB consecutive (SN, chain) units
+int ntile_for(int C) { return (C % WPB == 0) ? 1 : ((WPB % C == 0) ? WPB / C : (WPB + C - 1) / C + 1); }
 
 template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
 int launch_logp(bayesn_ctx* ctx, int C, const float* q, float* logp, float* grad, cudaStream_t st) {

@@ -36,7 +36,10 @@ namespace bayesn {
 constexpr int NB = BAYESN_NBINS;
 constexpr int BP = BAYESN_BPAD;
 constexpr int NPH = BAYESN_NPHASE;
-constexpr int WPB = 4;                          // warps (= (SN, chain) units) per CTA
+#ifndef BAYESN_WPB
+#define BAYESN_WPB 4
+#endif
+constexpr int WPB = BAYESN_WPB;                 // warps (= (SN, chain) units) per CTA
 constexpr float C2 = 1.3287712379549449f;       // 0.4 * log2(10)
 constexpr float KAPPA = 0.9210340371976184f;    // 0.4 * ln(10)
 constexpr float LN2 = 0.6931471805599453f;

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) spectra_kernel(FluxArgs A) {
 //     Stan-style windowed diagonal mass matrix.
 // ------------------------------------------------------------------------------------------
 #ifndef NUTS_MIN_CTAS
-#define NUTS_MIN_CTAS 4
+#define NUTS_MIN_CTAS (16 / BAYESN_WPB)
 #endif
 enum { V_ZL = 0, V_RL, V_GL, V_ZR, V_RR, V_GR, V_ZP, V_GP, V_RSUM, V_SZP, V_SGP, V_WMEAN, V_WM2, V_CKPT };
 __host__ __device__ inline int nuts_num_vectors(int max_depth) { return V_CKPT + 2 * max_depth; }
