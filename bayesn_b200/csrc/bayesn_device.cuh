@@ -134,10 +134,61 @@ __device__ __forceinline__ float treduce16(float (&v)[16], int lane) {
     return v[0];
 }
 
+// Packed FP32 arithmetic (Blackwell FFMA2 / FADD2: one issue slot for two IEEE fp32 operations on an
+// aligned register pair).  -DBAYESN_FFMA2=1 uses it for the two knot contractions of the band-pass loop
+// and the adds of the transposed reduction: 36 instead of 47 instructions per bin round and bit-identical
+// results (each half is an ordinary round-to-nearest FMA in the same order), but NOT faster on B200
+// (logp+grad 65.2 vs 67.5 M evals/s, NUTS unchanged; profiles/README.md): the loop is co-limited by the
+// shared-memory pipe (48 B of J_l row per bin and lane), not by issue slots alone.  Off by default.
+#ifndef BAYESN_FFMA2
+#define BAYESN_FFMA2 0
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // The same for two interleaved groups of 16 lanes (even lanes / odd lanes work on two different
 // observations): 15 shuffles; on return lane l holds the total of value (l >> 1) of its group.
 __device__ __forceinline__ float treduce16h(float (&v)[16], int lane) {
     bool up = lane & 16;
+#if BAYESN_FFMA2
+    // the adds of each exchange step are done two at a time (FADD2)
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        const float s0 = up ? v[i] : v[i + 8], s1 = up ? v[i + 1] : v[i + 9];
+        const float k0 = up ? v[i + 8] : v[i], k1 = up ? v[i + 9] : v[i + 1];
+        unpack2(fadd2(pack2(k0, k1), pack2(__shfl_xor_sync(FULL, s0, 16), __shfl_xor_sync(FULL, s1, 16))), v[i], v[i + 1]);
+    }
+    up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+        const float s0 = up ? v[i] : v[i + 4], s1 = up ? v[i + 1] : v[i + 5];
+        const float k0 = up ? v[i + 4] : v[i], k1 = up ? v[i + 5] : v[i + 1];
+        unpack2(fadd2(pack2(k0, k1), pack2(__shfl_xor_sync(FULL, s0, 8), __shfl_xor_sync(FULL, s1, 8))), v[i], v[i + 1]);
+    }
+    up = lane & 4;
+    {
+        const float s0 = up ? v[0] : v[2], s1 = up ? v[1] : v[3];
+        const float k0 = up ? v[2] : v[0], k1 = up ? v[3] : v[1];
+        unpack2(fadd2(pack2(k0, k1), pack2(__shfl_xor_sync(FULL, s0, 4), __shfl_xor_sync(FULL, s1, 4))), v[0], v[1]);
+    }
+#else
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         float send = up ? v[i] : v[i + 8];
@@ -158,6 +209,7 @@ __device__ __forceinline__ float treduce16h(float (&v)[16], int lane) {
         float keep = up ? v[i + 2] : v[i];
         v[i] = keep + __shfl_xor_sync(FULL, send, 4);
     }
+#endif
     up = lane & 2;
     {
         float send = up ? v[0] : v[1];
@@ -567,13 +619,29 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         float acc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#if BAYESN_FFMA2
+        // knot pairs (l, l+1) share one packed FMA: u and the J_l row arrive as aligned pairs from LDS.128,
+        // the even / odd halves are exactly the two FFMA chains of the scalar loop
+        f32x2 u2[LP4 / 2], q2[LP4 / 2];
+#pragma unroll
+        for (int k = 0; k < LP4 / 2; ++k) { u2[k] = pack2(u[2 * k], u[2 * k + 1]); q2[k] = pack2(0.f, 0.f); }
+#endif
         for (int it = 0; it < nr; ++it) {
+#if BAYESN_FFMA2
+            f32x2 jl2[LP4 / 2];
+#pragma unroll
+            for (int j = 0; j < LP4 / 4; ++j) {
+                const ulonglong2 v = reinterpret_cast<const ulonglong2*>(pj)[j];
+                jl2[2 * j] = v.x; jl2[2 * j + 1] = v.y;
+            }
+#else
             float jl[LP4];
 #pragma unroll
             for (int j = 0; j < LP4 / 4; ++j) {
                 const float4 v = pj[j];
                 jl[4 * j] = v.x; jl[4 * j + 1] = v.y; jl[4 * j + 2] = v.z; jl[4 * j + 3] = v.w;
             }
+#endif
             BAYESN_ASSERT((const float*)pj >= c.smem_lo && (const float*)(pj + LP4 / 4) <= c.smem_hi);
             BAYESN_ASSERT(STAGE ? (pw >= c.smem_lo && pw < c.smem_hi) : (pw >= c.wt_lo && pw < c.wt_hi));
             BAYESN_ASSERT(p0 >= hs && p0 + BP < c.hs_hi);
@@ -583,11 +651,20 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
             const float a = TRAIN ? __ldg(pa) : *pa;
             // two independent FFMA chains (4-cycle dependent-issue latency)
             float g0 = 0.f, g1 = 0.f;
+#if BAYESN_FFMA2
+            {
+                f32x2 g2 = pack2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < (LP + 1) / 2; ++k) g2 = ffma2(jl2[k], u2[k], g2);
+                unpack2(g2, g0, g1);
+            }
+#else
 #pragma unroll
             for (int l = 0; l < LP; l += 2) {
                 g0 = fmaf(jl[l], u[l], g0);
                 if (l + 1 < LP) g1 = fmaf(jl[l + 1], u[l + 1], g1);
             }
+#endif
             const float dh = h1 - h0;
             const float H = fmaf(f, dh, h0);
             const float e = ex2_approx(fmaf(AVc, a, g0 + g1));
@@ -597,10 +674,27 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
             acc[1] = fmaf(P, a, acc[1]);
             acc[2] = fmaf(we, dh, acc[2]);
             if (DRV) { acc[3] = fmaf(P, TRAIN ? __ldg(pda) : *pda, acc[3]); pda += 16; }
+#if BAYESN_FFMA2
+            {
+                const f32x2 P2 = pack2(P, P);
+#pragma unroll
+                for (int k = 0; k < (LP + 1) / 2; ++k) q2[k] = ffma2(jl2[k], P2, q2[k]);
+            }
+#else
 #pragma unroll
             for (int l = 0; l < LP; ++l) acc[4 + l] = fmaf(jl[l], P, acc[4 + l]);
+#endif
             p0 += 16; pw += 16; pj += 16 * (RS / 4); pa += 16; rem -= 16;
         }
+#if BAYESN_FFMA2
+#pragma unroll
+        for (int k = 0; k < (LP + 1) / 2; ++k) {
+            float lo, hi;
+            unpack2(q2[k], lo, hi);
+            acc[4 + 2 * k] = lo;
+            if (4 + 2 * k + 1 < 16 && 2 * k + 1 < LP) acc[4 + 2 * k + 1] = hi;
+        }
+#endif
         const float val = treduce16h(acc, lane);
         const float F = __shfl_sync(FULL, val, hb);
         const float FA = __shfl_sync(FULL, val, hb | 2);

@@ -285,7 +285,9 @@ def train_leg(args, dev, rank, world):
                        f'GPU(s), {C} chains x ({W}+{S}) (nominal 500+500; shortened), max_tree_depth 10, NUTS step_size 0.1',
            'seconds': dt, 'passes': out['passes'], 'us_per_leapfrog_pass': dt / out['passes'] * 1e6,
            'leapfrog_passes_per_s': out['passes'] / dt, 'sn_evals_per_s': out['passes'] * n_total * C / dt,
-           'gpu_launches': 3 * out['passes'] + 2,        # SN + reduction + control kernel per pass (CUDA-graph replays included) 'allreduce_doubles_per_pass': (C * ctx.train_dims()[2]) if world > 1 else 0,
+           # SN kernel + two reduction stages + control kernel per pass (CUDA-graph replays included)
+           'gpu_launches': 4 * out['passes'] + 2,
+           'allreduce_doubles_per_pass': (C * ctx.train_dims()[2]) if world > 1 else 0,
            'mean_accept_sampling': float(st[:, W:, 0].mean()), 'divergences': float(out['info'][:, 5].sum()),
            'finished': out['finished']}
     if rank == 0 and not args.no_train_cpu:
