@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <type_traits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,6 +30,7 @@ struct bayesn_ctx {
     XchgDev X{};                // peer-memory exchange of the training sums (world 1 = off)
     std::vector<void*> tn_owned;
     bool have_tn = false;
+    unsigned long long* queue = nullptr;   // work-queue counter of the fit sampler
 };
 
 namespace {
@@ -139,21 +141,60 @@ int launch_logp(bayesn_ctx* ctx, int C, const float* q, float* logp, float* grad
 }
 
 template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
-int launch_nuts(bayesn_ctx* ctx, const NutsDev& cfg, const float* q0, float* samples, float* stats, float* info,
-                float* work, cudaStream_t st) {
+int launch_nuts(bayesn_ctx* ctx, const NutsDev& cfg, bool use_queue, const float* q0, float* samples, float* stats,
+                float* info, float* work, cudaStream_t st) {
     const int C = cfg.num_chains;
-    const int ntile = ntile_for(C);
+    const int ntile = use_queue ? WPB : ntile_for(C);      // queue: one slot of SN data per warp
     const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE);
     const size_t bytes = (size_t)P.totalFloats * 4;
     auto kern = nuts_kernel<LP, TP, VPL, RVFREE, STAGE>;
     if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
     CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     const long long units = (long long)ctx->D.N * C;
-    const unsigned grid = (unsigned)((units + WPB - 1) / WPB);
-    kern<<<grid, WPB * 32, bytes, st>>>(ctx->M, ctx->D, cfg, ntile, q0, samples, stats, info, work);
+    unsigned grid = (unsigned)((units + WPB - 1) / WPB);
+    unsigned long long* queue = nullptr;
+    if (use_queue) {
+        int occ = 0, sms = 0;
+        CU_CHECK(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WPB * 32, bytes));
+        if (occ < 1) return fail(ctx, -3, "work-queue schedule does not fit");
+        if (!ctx->queue) CU_CHECK(ctx, cudaMalloc(&ctx->queue, sizeof(unsigned long long)));
+        CU_CHECK(ctx, cudaMemsetAsync(ctx->queue, 0, sizeof(unsigned long long), st));
+        queue = ctx->queue;
+        grid = (unsigned)std::min<long long>(grid, (long long)occ * sms);      // one resident wave
+    }
+    kern<<<grid, WPB * 32, bytes, st>>>(ctx->M, ctx->D, cfg, ntile, q0, samples, stats, info, work, queue);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
+}
+
+// Schedule of the fit sampler.  The work queue (one resident wave of CTAs whose warps fetch (SN, chain)
+// units) needs a slot of SN data per warp instead of per CTA; it is used when that costs no occupancy
+// against the static schedule and there is more than one wave of work.  When the staged slots do not fit
+// (C5: 60 observations, 4.9 KB tiles) the static schedule stays: reading the tiles through L1 instead
+// was measured slower than the imbalance it removes (87 vs 93 SNe/s, profiles/README.md).
+// BAYESN_NUTS_SCHED=static|queue|queue-l1 overrides (measurements, tests).
+void choose_nuts_schedule(bayesn_ctx* ctx, int C, bool* use_queue, bool* stage) {
+    const bool rvfree = ctx->M.rv_mode != BAYESN_RV_FIXED;
+    auto occ = [&](int ntile, bool st) {
+        const SmemPlan P = make_plan(ctx->LP, ctx->TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, rvfree, st);
+        const long long bytes = (long long)P.totalFloats * 4;
+        if (bytes > 227 * 1024) return 0;
+        return (int)std::min<long long>(16 / WPB, (228LL * 1024) / (bytes + 1024));    // 128 registers x 16 warps fill the SM
+    };
+    const bool stage_static = C >= 2;       // one chain per SN: nothing to share, the tile is read through L1
+    const int occ_static = std::max(occ(ntile_for(C), stage_static), 1);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const long long ctas = ((long long)ctx->D.N * C + WPB - 1) / WPB;
+    *use_queue = false;
+    *stage = stage_static;
+    const char* e = getenv("BAYESN_NUTS_SCHED");
+    if (e && !strcmp(e, "static")) return;
+    if (e && !strcmp(e, "queue-l1")) { *use_queue = occ(WPB, false) > 0; if (*use_queue) *stage = false; return; }
+    if (e && !strcmp(e, "queue")) { *use_queue = occ(WPB, stage_static) > 0; return; }
+    *use_queue = ctas > (long long)occ_static * sms && occ(WPB, stage_static) >= occ_static;
 }
 
 // compile-time dispatch over the supported (knots, parameter-vector) shapes
@@ -247,10 +288,10 @@ struct LogpCall {
     int operator()() { return launch_logp<LP, TP, VPL, RV, ST>(ctx, C, q, logp, grad, st); }
 };
 struct NutsCall {
-    bayesn_ctx* ctx; NutsDev cfg; const float* q0; float* samples; float* stats; float* info; float* work;
+    bayesn_ctx* ctx; NutsDev cfg; bool use_queue; const float* q0; float* samples; float* stats; float* info; float* work;
     cudaStream_t st;
     template <int LP, int TP, int VPL, bool RV, bool ST>
-    int operator()() { return launch_nuts<LP, TP, VPL, RV, ST>(ctx, cfg, q0, samples, stats, info, work, st); }
+    int operator()() { return launch_nuts<LP, TP, VPL, RV, ST>(ctx, cfg, use_queue, q0, samples, stats, info, work, st); }
 };
 
 // numpyro.infer.hmc_util.build_adaptation_schedule (Stan windows)
@@ -300,6 +341,7 @@ void bayesn_ctx_destroy(bayesn_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     free_owned(ctx);
+    if (ctx->queue) cudaFree(ctx->queue);
     delete ctx;
 }
 
@@ -424,8 +466,10 @@ int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_
     if (ends.size() > 24) return fail(ctx, -1, "too many adaptation windows");
     nd.n_windows = (int)ends.size();
     for (size_t i = 0; i < 24; ++i) nd.win_end[i] = i < ends.size() ? ends[i] : 0x7fffffff;
-    NutsCall call{ctx, nd, q_init, samples, stats, chain_info, (float*)work, (cudaStream_t)stream};
-    return dispatch(ctx, /*stage=*/cfg->num_chains >= 2, call);
+    bool use_queue = false, stage = false;
+    choose_nuts_schedule(ctx, cfg->num_chains, &use_queue, &stage);
+    NutsCall call{ctx, nd, use_queue, q_init, samples, stats, chain_info, (float*)work, (cudaStream_t)stream};
+    return dispatch(ctx, stage, call);
 }
 
 int bayesn_init_to_median(bayesn_ctx* ctx, int n_chains, uint64_t seed, uint64_t unit_offset, float* q, void* stream) {

@@ -36,8 +36,12 @@ namespace bayesn {
 constexpr int NB = BAYESN_NBINS;
 constexpr int BP = BAYESN_BPAD;
 constexpr int NPH = BAYESN_NPHASE;
+// 8 warps per CTA, 2 CTAs per SM: the CTA-shared tables (J_l, dust basis: 18 KB) are amortised over 8
+// warps, which leaves room for a per-warp slot of SN data (work-queue schedule of the fit sampler) and
+// keeps the L1 carve-out at >= 60 KB; the training SN kernel gains 13 % (131 -> 114 us per pass at C4),
+// logp+grad is unchanged (profiles/README.md).
 #ifndef BAYESN_WPB
-#define BAYESN_WPB 4
+#define BAYESN_WPB 8
 #endif
 constexpr int WPB = BAYESN_WPB;                 // warps (= (SN, chain) units) per CTA
 constexpr float C2 = 1.3287712379549449f;       // 0.4 * log2(10)
@@ -853,7 +857,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
 // ------------------------------------------------------------------------------------------
 template <int LP, int TP, bool RVFREE, bool STAGE, bool TRAIN = false>
 __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, int n_chains, int ntile, float* smem,
-                                          WarpCtx& c, int& sn, int& chain) {
+                                          WarpCtx& c, int& sn, int& chain, bool per_warp = false) {
     const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE, TRAIN);
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long unit0 = (long long)blockIdx.x * WPB;
@@ -862,7 +866,9 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
     long long last_unit = unit0 + WPB - 1;
     if (last_unit >= total) last_unit = total - 1;
     const int s_last = (int)(last_unit / n_chains);
-    const int nt = s_last - s_first + 1;
+    // per_warp: only the model tables are staged here; every warp stages the data of the SN it
+    // takes from the work queue itself (warp_bind)
+    const int nt = per_warp ? 0 : s_last - s_first + 1;
 
     float* sJl = smem + P.oJl;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P.oBar);
@@ -877,8 +883,8 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
         tma_load_1d(sJl, M.Jl, kJlBytes, bar);
         if (RVFREE) tma_load_1d(smem + P.oMf, M.Mf, 9 * BP * 4, bar);
         else tma_load_1d(smem + P.oAd, M.ad, JROWS * 4, bar);
-        tma_load_1d(smem + P.oObs, Dd.obs4 + (size_t)s_first * Dd.N_obs, nt * Dd.N_obs * 16, bar);
-        if (STAGE) tma_load_1d(smem + P.oWt, Dd.wt + (size_t)s_first * Dd.wt_stride, nt * Dd.wt_stride * 4, bar);
+        if (nt) tma_load_1d(smem + P.oObs, Dd.obs4 + (size_t)s_first * Dd.N_obs, nt * Dd.N_obs * 16, bar);
+        if (STAGE && nt) tma_load_1d(smem + P.oWt, Dd.wt + (size_t)s_first * Dd.wt_stride, nt * Dd.wt_stride * 4, bar);
     }
     // small tables with plain loads while the bulk copies are in flight
     for (int i = tid; i < LP * TP; i += blockDim.x) {
@@ -893,10 +899,10 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
     __syncthreads();
 
     const long long unit = unit0 + warp;
-    const bool active = unit < total;
-    sn = active ? (int)(unit / n_chains) : s_first;
-    chain = active ? (int)(unit - (long long)sn * n_chains) : 0;
-    const int slot = sn - s_first;
+    const bool active = per_warp || unit < total;
+    sn = (!per_warp && active) ? (int)(unit / n_chains) : s_first;
+    chain = (!per_warp && active) ? (int)(unit - (long long)sn * n_chains) : 0;
+    const int slot = per_warp ? warp : sn - s_first;
     // Offsets are passed through an empty asm so that ptxas keeps each one in a register instead
     // of re-deriving the whole shared-memory plan from kernel parameters inside the hot loops
     // (seen in the round-1 profile: ~60 integer instructions per observation).
@@ -937,6 +943,31 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
     c.wt_hi = Dd.wt + (size_t)Dd.N * Dd.wt_stride + OVERRUN + 32;
     c.hs_hi = M.hs + (NPH + 1) * BP + OVERRUN + 32;
     return active;
+}
+
+// Work-queue mode (cta_setup with per_warp = true, plan made with ntile = WPB): the warp stages the
+// observations, band supports and - when STAGE - the weight tile of SN `sn` into its own slot and
+// points its context at them.  A few KB of coalesced loads per chain, i.e. per ~10^5 evaluations.
+template <bool STAGE>
+__device__ __forceinline__ void warp_bind(const DataDev& Dd, const SmemPlan& P, float* smem, WarpCtx& c, int sn, int lane) {
+    const int slot = threadIdx.x >> 5;
+    __syncwarp();
+    float4* so = reinterpret_cast<float4*>(smem + P.oObs) + slot * Dd.N_obs;
+    const float4* go = Dd.obs4 + (size_t)sn * Dd.N_obs;
+    for (int i = lane; i < Dd.N_obs; i += 32) so[i] = go[i];
+    int4* ss = reinterpret_cast<int4*>(smem + P.oSup) + slot * Dd.n_b;
+    const int4* gs = Dd.sup + (size_t)sn * Dd.n_b;
+    for (int i = lane; i < Dd.n_b; i += 32) ss[i] = gs[i];
+    if (STAGE) {
+        float* st = smem + P.oWt + slot * Dd.wt_stride;
+        const float* gt = Dd.wt + (size_t)sn * Dd.wt_stride;
+        for (int i = lane; i < Dd.wt_stride; i += 32) st[i] = gt[i];
+    }
+    __syncwarp();
+    c.wt_g = Dd.wt + (size_t)sn * Dd.wt_stride;
+    c.nobs = Dd.n_valid[sn];
+    c.muhat = Dd.muhat[sn];
+    c.lconst = Dd.lconst[sn];
 }
 
 }  // namespace bayesn

@@ -244,15 +244,39 @@ template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
 __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev M, DataDev Dd, NutsDev cfg, int ntile,
                                                         const float* __restrict__ q_init, float* __restrict__ samples,
                                                         float* __restrict__ stats, float* __restrict__ chain_info,
-                                                        float* __restrict__ work) {
+                                                        float* __restrict__ work, unsigned long long* queue) {
     extern __shared__ __align__(16) float smem[];
     WarpCtx c;
     int sn, chain;
     const int C = cfg.num_chains;
-    const bool active = cta_setup<LP, TP, RVFREE, STAGE>(M, Dd, C, ntile, smem, c, sn, chain);
+    // queue != nullptr: work-queue mode.  The grid is one resident wave; every warp takes the next
+    // (SN, chain) unit from an atomic counter when its chain is done and stages that SN's data itself,
+    // so no warp idles while the slowest chain of its CTA finishes and the last wave fills evenly
+    // (C3: +8 % at 1000 SNe, 309 SNe/s at 2368 SNe).  Draws do not depend on the schedule: random
+    // streams and workspace are keyed by the unit.  A variant that kept the chains of an SN on one CTA
+    // (CTA-level current SN + global SN counter) was 2 % slower: locality of the SN's Hsiao rows in L1
+    // does not matter, balance does.  queue == nullptr: CTA b runs units [b WPB, (b+1) WPB), their SN
+    // data staged once per CTA (used when a per-warp slot of SN data would cost occupancy).
+    const bool dyn = queue != nullptr;
+    const bool active = cta_setup<LP, TP, RVFREE, STAGE>(M, Dd, C, ntile, smem, c, sn, chain, dyn);
     if (!active) return;
     const int lane = threadIdx.x & 31;
-    const size_t unit = (size_t)sn * C + chain;
+    const unsigned long long total_units = (unsigned long long)Dd.N * C;
+  for (bool first_unit = true;; first_unit = false) {
+    size_t unit;
+    if (dyn) {
+        unsigned long long u = 0;
+        if (lane == 0) u = atomicAdd(queue, 1ULL);
+        u = __shfl_sync(FULL, u, 0);
+        if (u >= total_units) break;
+        sn = (int)(u / (unsigned)C);
+        chain = (int)(u - (unsigned long long)sn * C);
+        const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE);
+        warp_bind<STAGE>(Dd, P, smem, c, sn, lane);
+    } else {
+        if (!first_unit) break;
+    }
+    unit = (size_t)sn * C + chain;
     const int D = M.D;
     const int nvec = nuts_num_vectors(cfg.max_depth);
     VecIO<VPL> io{work + unit * (size_t)nvec * 32 * VPL, lane};
@@ -526,6 +550,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
 #pragma unroll
     for (int s = 0; s < VPL; ++s)
         if (own[s]) ci[4 + lane + 32 * s] = im[s];
+  }
 }
 
 

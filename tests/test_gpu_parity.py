@@ -210,6 +210,27 @@ def test_nuts_trajectories_match_oracle_sampler():
         assert np.allclose(st[s, 0, :agree, 0], np.array(recs[s]['accept'])[:agree], atol=5e-3)
 
 
+@pytest.mark.parametrize('n_chains', [1, 3, 4])
+def test_nuts_work_queue_schedule_reproduces_static_schedule(n_chains, monkeypatch):
+    """The work-queue schedule of nuts_kernel (warps fetch (SN, chain) units from an atomic counter and
+    stage their own SN data) gives the same draws, bit for bit, as the static CTA-per-units schedule:
+    nothing in a chain depends on which warp runs it or when.  Ragged case (masked observations, a number
+    of units that is not a multiple of the CTA size)."""
+    case = make_case('W22_model', C2_BANDS, np.array([-8.0, 2.0, 12.0, 22.0, 32.0]), N=11, seed=31)
+    m, bi = product_model(case)
+    ctx = m.prepare(case['obs'], case['weights'], bi)
+    q0 = ctx.init_to_median(n_chains, seed=4)
+    outs = {}
+    for sched in ('static', 'queue'):
+        monkeypatch.setenv('BAYESN_NUTS_SCHED', sched)
+        out = ctx.nuts(q0, num_warmup=30, num_samples=20, max_tree_depth=6, seed=9)
+        torch.cuda.synchronize()
+        outs[sched] = {k: out[k].clone() for k in ('samples', 'stats', 'chain_info')}
+    for k in ('samples', 'stats', 'chain_info'):
+        assert torch.isfinite(outs['static'][k]).all()
+        assert torch.equal(outs['static'][k], outs['queue'][k]), k
+
+
 def _fit_2016w(**kw):
     from bayesn_b200 import SEDmodel
     m = SEDmodel(load_model='T21_model')
