@@ -369,7 +369,8 @@ int bayesn_set_model(bayesn_ctx* ctx, const bayesn_model_desc* m) {
     const int RS = jl_row_stride(LP);
     std::vector<float> Jl((size_t)JROWS * RS, 0.f), hs((size_t)(NPH + 1) * BP + OVERRUN + 32, 0.f), Mf((size_t)9 * BP, 0.f), ad(JROWS, 0.f);
     std::vector<float> W0((size_t)LP * TP, 0.f), W1((size_t)LP * TP, 0.f), KD((size_t)TP * TP, 0.f), tau(TP, 0.f);
-    std::vector<float> Ls((size_t)ne * ne), LsT((size_t)ne * ne);
+    const int lss = ls_row_stride(LP, TP);       // >= ne; compile-time row stride of the evaluator
+    std::vector<float> Ls((size_t)ne * lss, 0.f), LsT((size_t)ne * lss, 0.f);
     for (int b = 0; b < NB; ++b) {
         for (int l = 0; l < L; ++l) Jl[(size_t)b * RS + l] = m->J_l[(size_t)b * L + l];
         for (int i = 0; i < NPH; ++i) hs[(size_t)i * BP + b] = m->hsiao[(size_t)b * NPH + i];
@@ -388,8 +389,8 @@ int bayesn_set_model(bayesn_ctx* ctx, const bayesn_model_desc* m) {
     bool lower = true;
     for (int i = 0; i < ne; ++i)
         for (int j = 0; j < ne; ++j) {
-            Ls[(size_t)i * ne + j] = m->L_Sigma[(size_t)i * ne + j];
-            LsT[(size_t)j * ne + i] = m->L_Sigma[(size_t)i * ne + j];
+            Ls[(size_t)i * lss + j] = m->L_Sigma[(size_t)i * ne + j];
+            LsT[(size_t)j * lss + i] = m->L_Sigma[(size_t)i * ne + j];
             if (j > i && m->L_Sigma[(size_t)i * ne + j] != 0.f) lower = false;
         }
     ModelDev& M = ctx->M;

@@ -284,6 +284,11 @@ struct Dims {
 };
 constexpr int JROWS = BP + 32;   // per-bin tables carry 32 zero rows so the last round may overrun
 constexpr int OVERRUN = BAYESN_OVERRUN;     // bins a lane may read past the end of its band's support (values discarded)
+// Row stride of the fit model's L_Sigma tables: a compile-time constant per kernel instantiation, so the
+// column walks of the two triangular mat-vecs use immediate offsets (a runtime stride cost two integer
+// instructions per load: 4 % of the evaluator's instructions in the r01i profile).  Training keeps
+// per-chain tables with stride n_eps.
+__host__ __device__ constexpr int ls_row_stride(int LP, int TP) { return ((LP - 2) * TP + 3) & ~3; }
 __host__ __device__ constexpr int jl_row_stride(int LP) { return ((((LP + 3) & ~3) / 4) % 2 == 1) ? ((LP + 3) & ~3) : ((LP + 3) & ~3) + 4; }
 __host__ __device__ constexpr int rec_stride(int LP, int TP, bool train = false) {
     int raw = ((((LP + 3) & ~3) + (train ? 1 : 2) * TP + 3) & ~3) + 4;
@@ -435,10 +440,11 @@ template <int LP, int TP, int VPL, bool RVFREE, bool STAGE, bool TRAIN = false>
 __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx& c, const float* __restrict__ hs,
                                                const float (&q)[VPL], double& logp_out, float (&grad)[VPL], int lane) {
     using DM = Dims<LP, TP, TRAIN>;
-    constexpr int LP4 = DM::LP4, REC = DM::REC, NPAIR = DM::NPAIR, RS = DM::RS;
+    constexpr int LP4 = DM::LP4, REC = DM::REC, RS = DM::RS;
     constexpr bool DRV = RVFREE || TRAIN;     // the derivative with respect to R_V is needed
     static_assert(!(RVFREE && TRAIN), "training samples one global R_V");
     const int L = M.L, T = M.T, ne = M.n_eps;
+    const int lss = TRAIN ? ne : ls_row_stride(LP, TP);     // row stride of c.Ls / c.LsT
 
     // ---- scalars ------------------------------------------------------------------------
     const float theta_s = vget<VPL>(q, ne + 0);
@@ -485,7 +491,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         float acc = 0.f;
         if (i < ne) {
             const float* col = c.LsT + i;
-            for (int j = 0; j < jend; ++j) acc = fmaf(__ldg(col + j * ne), c.ev[j], acc);
+            for (int j = 0; j < jend; ++j) acc = fmaf(__ldg(col + j * lss), c.ev[j], acc);
             c.eps[i] = acc;
         }
     }
@@ -594,6 +600,13 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
 #pragma unroll
     for (int m = 0; m < TP; ++m) wrow[m] = (hl >= 4 && hl < 4 + LP) ? c.Ws[(hl - 4) * TP + m] : 0.f;
     float gTW = 0.f;
+    // dW[l][.] = sum_o dU_o[l] J_t,o[.] accumulates in the lane that ends each pair's reduction holding dU_o[l]
+    // (one row of 6 per lane and half, added across the halves after the loop) - a separate pass over all
+    // observations with lanes over (l, m) cost 5 % of the evaluation in the r01i profile
+    float dWr[TP];
+#pragma unroll
+    for (int m = 0; m < TP; ++m) dWr[m] = 0.f;
+    const bool qlane = hl >= 4 && hl < 4 + LP;
     for (int p = 0; p < npair; ++p) {
         float* rc = c.rec + (2 * p + hb) * REC;
         float u[LP4];
@@ -724,18 +737,20 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         gAV = fmaf(-KAPPA * coef, FA, gAV);
         gT = fmaf((pk & 256) ? coef : 0.f, FT, gT);
         if (DRV) gRV = fmaf(-KAPPA * AV * coef, __shfl_sync(FULL, val, hb | 6), gRV);
-        // d logL / d(sum_m W[l][m] Jt[m]) for this observation, overwriting u (no longer needed),
-        // and its product with (W J_t'(t))[l] for the gradient through the time spline
-        const float dU = -KAPPA * coef * val;
+        // d logL / d(sum_m W[l][m] Jt[m]) for this observation: its outer product with J_t goes into dW,
+        // its product with (W J_t'(t))[l] into the gradient through the time spline
+        const float dU = qlane ? -KAPPA * coef * val : 0.f;
         if (!TRAIN) {
             float du = 0.f;
 #pragma unroll
             for (int m = 0; m < TP; ++m) du = fmaf(wrow[m], rc[DM::R_DJ + m], du);
             gTW = fmaf(dU, du, gTW);
         }
-        __syncwarp();
-        if (hl >= 4 && hl < 4 + LP) rc[hl - 4] = dU;
+#pragma unroll
+        for (int m = 0; m < TP; ++m) dWr[m] = fmaf(dU, rc[DM::R_JT + m], dWr[m]);
     }
+#pragma unroll
+    for (int m = 0; m < TP; ++m) dWr[m] += __shfl_xor_sync(FULL, dWr[m], 1);
     // the two halves hold the sums over their own observations
     logL += __shfl_xor_sync(FULL, logL, 1);
     gDs += __shfl_xor_sync(FULL, gDs, 1);
@@ -746,29 +761,20 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
 
     gT += wsum(gTW);
 
-    // ---- reverse: dW, theta, eps_tform -------------------------------------------------------
-    float dW[NPAIR];
+    // ---- reverse: theta, eps_tform -----------------------------------------------------------
+    // lane (hl = 4 + l, hb = 0) owns row l of dW
     float gth = 0.f;
+    {
+        const int l = hl - 4;
+        if (qlane && hb == 0) {
 #pragma unroll
-    for (int s = 0; s < NPAIR; ++s) {
-        int p = lane + 32 * s;
-        float acc = 0.f;
-        if (p < LP * TP) {
-            int l = p / TP, m = p - l * TP;
-            for (int o = 0; o < c.nobs; ++o) acc = fmaf(c.rec[o * REC + l], c.rec[o * REC + DM::R_JT + m], acc);
-            gth = fmaf(acc, c.sW1[p], gth);
+            for (int m = 0; m < TP; ++m) {
+                gth = fmaf(dWr[m], c.sW1[l * TP + m], gth);
+                if (l >= 1 && l <= L - 2 && m < T) c.ev[(l - 1) + (L - 2) * m] = dWr[m];
+            }
         }
-        dW[s] = acc;
     }
     gth = wsum(gth);
-#pragma unroll
-    for (int s = 0; s < NPAIR; ++s) {
-        int p = lane + 32 * s;
-        if (p < LP * TP) {
-            int l = p / TP, m = p - l * TP;
-            if (l >= 1 && l <= L - 2 && m < T) c.ev[(l - 1) + (L - 2) * m] = dW[s];
-        }
-    }
     __syncwarp();
 
     // ---- priors, Jacobians, assemble gradient in the unconstrained space ---------------------
@@ -781,7 +787,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         if (i < ne) {
             float acc = 0.f;
             const float* col = c.Ls + i;
-            for (int j = (TRAIN || M.ls_lower) ? 32 * s : 0; j < ne; ++j) acc = fmaf(__ldg(col + j * ne), c.ev[j], acc);
+            for (int j = (TRAIN || M.ls_lower) ? 32 * s : 0; j < ne; ++j) acc = fmaf(__ldg(col + j * lss), c.ev[j], acc);
             gi = acc - q[s];
             ss = fmaf(q[s], q[s], ss);
         }
@@ -809,10 +815,9 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
             if (i == ne + 2) grad[s] = g_Ds;
         }
         // un-reduced contributions to the gradient of the globals (constrained space)
+        if (qlane && hb == 0) {
 #pragma unroll
-        for (int s = 0; s < NPAIR; ++s) {
-            int p = lane + 32 * s;
-            if (p < LP * TP) c.part[p] = dW[s];
+            for (int m = 0; m < TP; ++m) c.part[(hl - 4) * TP + m] = dWr[m];
         }
         if (lane == 0) {
             float* ps = c.part + LP * TP;

@@ -1,5 +1,5 @@
 """Short, deterministic workload for ncu: the fused log p + gradient kernel at C2 scale, the same
-kernel with 4 chains per SN (TMA-staged weight tiles), and a short NUTS run."""
+kernel with 4 chains per SN (TMA-staged weight tiles), and a short NUTS run (work-queue schedule)."""
 import sys
 import numpy as np
 import torch
@@ -14,7 +14,8 @@ q1 = ctx.init_to_median(1, seed=5)
 for _ in range(3):
     ctx.logp_grad(q1)
 torch.cuda.synchronize()
-obs2, w2, bi2 = obs[:, :, :592], w[:592], bi
+# 1184 SNe x 4 chains = two waves of (SN, chain) units: the sampler runs its work-queue schedule
+obs2, w2, bi2 = obs[:, :, :1184], w[:1184], bi
 ctx2 = m.prepare(obs2, w2, bi2)
 q4 = ctx2.init_to_median(4, seed=6)
 for _ in range(3):
