@@ -550,27 +550,50 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     // dummy copy of the last observation with 1/sigma = 0, which contributes exactly nothing.
     const int npair = (c.nobs + 1) >> 1;
     if (lane == 0) c.sc[0] = S;
-    for (int o = lane; o < 2 * npair; o += 32) {
+    for (int o0 = 0; o0 < 2 * npair; o0 += 32) {
+        const int o = o0 + lane;
+        const unsigned act = __ballot_sync(FULL, o < 2 * npair);     // both lanes of a pair are in or out together
+        if (o >= 2 * npair) continue;
         const bool dummy = o >= c.nobs;
         const float4 ob = c.obs[dummy ? c.nobs - 1 : o];
         float t = ob.x - tmax;
         float J[TP], dJ[TP];
         spline_row<TP>(t, T, c.sTau, c.sKD, J, dJ);
         float* rc = c.rec + o * REC;
+        // the record is assembled in registers and written with 128-bit stores: the record stride (an odd
+        // number of 16-byte words) makes those conflict-free, while 32-bit stores at a stride of REC words
+        // were 4-way bank-conflicted (r01i profile)
+        float rv[DM::R_SC];
+#pragma unroll
+        for (int i = 0; i < DM::R_SC; ++i) rv[i] = 0.f;
 #pragma unroll
         for (int m = 0; m < TP; ++m) {
-            rc[DM::R_JT + m] = J[m];
-            if (!TRAIN) rc[DM::R_DJ + m] = dJ[m];
+            rv[DM::R_JT + m] = J[m];
+            if (!TRAIN) rv[DM::R_DJ + m] = dJ[m];
         }
 #pragma unroll
         for (int l = 0; l < LP4; ++l) {
             float u = 0.f;
             if (l < LP) {
+                if constexpr (TP % 2 == 0) {
+                    // rows of W are 8-byte aligned: half as many (broadcast) shared-memory loads
+                    const float2* wr = reinterpret_cast<const float2*>(c.Ws + l * TP);
 #pragma unroll
-                for (int m = 0; m < TP; ++m) u = fmaf(c.Ws[l * TP + m], J[m], u);
+                    for (int m = 0; m < TP; m += 2) {
+                        const float2 w2 = wr[m >> 1];
+                        u = fmaf(w2.x, J[m], u);
+                        u = fmaf(w2.y, J[m + 1], u);
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < TP; ++m) u = fmaf(c.Ws[l * TP + m], J[m], u);
+                }
             }
-            rc[l] = -C2 * u;
+            rv[l] = -C2 * u;
         }
+#pragma unroll
+        for (int i = 0; i < DM::R_SC; i += 4)
+            *reinterpret_cast<float4*>(rc + i) = make_float4(rv[i], rv[i + 1], rv[i + 2], rv[i + 3]);
         float fl = floorf(t);
         int i0 = 19 + (int)fl, i1 = 19 + (int)ceilf(t);
         i0 = min(max(i0, 0), NPH - 1);
@@ -578,8 +601,14 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         // the upper Hsiao row is read at i0 + 1; when ceil == floor (integer phase) or the index
         // is clamped the interpolation degenerates to row i0 and d/dt of it vanishes
         const bool interp = i1 != i0;
+        // rounds of the band-pass loop for this PAIR (the wider of its two supports), so that the pair
+        // prologue does not wait for a support load and a shuffle before it knows its trip count
+        const int band = __float_as_int(ob.w);
+        const int4 spo = c.sup[band];
+        int nro = (spo.y - spo.x + 15) >> 4;
+        nro = max(nro, __shfl_xor_sync(act, nro, 1));
         *reinterpret_cast<float4*>(rc + DM::R_SC) =
-            make_float4(interp ? (t - fl) : 0.f, __int_as_float(i0 | (interp ? 256 : 0) | (__float_as_int(ob.w) << 16)),
+            make_float4(interp ? (t - fl) : 0.f, __int_as_float(i0 | (interp ? 256 : 0) | (nro << 9) | (band << 16)),
                         dummy ? 0.f : ob.y, dummy ? 0.f : ob.z);
     }
     __syncwarp();
@@ -623,8 +652,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         const int pk = __float_as_int(scal.y);
         const float yo = scal.z, iso = scal.w;
         const int4 sp = c.sup[pk >> 16];
-        int nr = (sp.y - sp.x + 15) >> 4;
-        nr = max(nr, __shfl_xor_sync(FULL, nr, 1));
+        const int nr = (pk >> 9) & 0x7f;          // <= 19 rounds of 16 bins
         // running pointers: one add per array per round instead of rebuilding addresses
         const int b_first = sp.x + hl;
         const float* p0 = hs + (pk & 0xff) * BP + b_first;
