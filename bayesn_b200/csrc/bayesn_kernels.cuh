@@ -355,9 +355,13 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
 
     // Flat state machine: every pass through this loop does exactly one log p + gradient
     // evaluation (the very first one initialises the chain, all others are leapfrog steps).
-    bool first = true;
-    int init_tries = 0;
+    // mode 0: leapfrog steps.  mode 1: evaluate the initial point.  modes 2, 3: distance rescue (below).
+    int mode = 1;
+    int init_tries = 0, n_rescue = 0;
+    float rs_S1 = 0.f, rs_h1 = 0.f;
+    const int iD = M.n_eps + 3;             // element of the (shifted) distance
     while (true) {
+        const bool first = mode != 0;
         if (!first) {
 #pragma unroll
             for (int s = 0; s < VPL; ++s) {
@@ -385,7 +389,27 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
                 ++init_tries;
                 continue;
             }
-            first = false;
+            if (mode == 2) {
+                // Second point of the rescue: log L is quadratic in the flux scale S = 10^(-0.4 dD), so
+                // h = (dU/d dD) / (kappa S) = a - b S at two distances gives the optimum S* = a / b.
+                const float dD2 = vget<VPL>(z, iD), S2 = exp2f(-C2 * dD2);
+                const float h2 = vget<VPL>(g, iD) / (KAPPA * S2);
+                const float b = (rs_h1 - h2) / (S2 - rs_S1), a = rs_h1 + b * rs_S1;
+                float dDs = -log2f(a / b) * (1.f / C2);
+                if (!(b > 0.f) || !(a > 0.f) || !isfinite(dDs)) dDs = 0.f;       // fall back to Ds = muhat
+#pragma unroll
+                for (int s = 0; s < VPL; ++s)
+                    if (lane + 32 * s == iD) z[s] = dDs;
+                mode = 3;
+                continue;
+            }
+            if (mode == 3) {
+                // restart step-size adaptation from the rescued point (the mass matrix is kept)
+                step = cfg.init_step;
+                da_x = 0.f; da_xavg = 0.f; da_gavg = 0.f; da_t = 0;
+                da_prox = logf(10.f * step);
+            }
+            mode = 0;
             pe = pe_new;
             begin_transition();
             begin_doubling();
@@ -537,6 +561,24 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
             n_div += diverging ? 1 : 0;
         }
         if (++it >= n_iter) break;
+        // FP32 safeguard (not in numpyro, which runs in float64): a chain whose initial distance is ~2 mag
+        // off starts at log p ~ -2e6, where the rounding noise of a float32 log L (relative 1e-7..1e-6) is
+        // an energy noise of order 1 per leapfrog; no step size reaches the target acceptance, dual
+        // averaging drives the step to ~1e-8, the position stops changing and every transition runs the
+        // full 2^max_depth - 1 leapfrogs (1 chain in 9 472 of the C5 share: 498 k leapfrogs, a third of the
+        // kernel time).  Healthy chains never go below ~1e-3 during warm-up.  Rescue: solve the distance
+        // coordinate in closed form (two evaluations), restart the step-size adaptation, carry on.
+        if (it < cfg.num_warmup && cfg.adapt_step && step < 1e-6f && n_rescue < 3) {
+            ++n_rescue;
+            const float dD1 = vget<VPL>(z, iD);
+            rs_S1 = exp2f(-C2 * dD1);
+            rs_h1 = vget<VPL>(g, iD) / (KAPPA * rs_S1);
+#pragma unroll
+            for (int s = 0; s < VPL; ++s)
+                if (lane + 32 * s == iD) z[s] = dD1 + 0.5f;
+            mode = 2;
+            continue;
+        }
         begin_transition();
         begin_doubling();
     }

@@ -30,4 +30,10 @@ F = bench.flops_per_eval(11, 6, 60)
 res = dict(config=f'C5 share: W22 ugrizy, {N} SNe x 60 obs, 4 x (250+250)', sne_per_s=N / dt, seconds=dt, evals_per_s=lf / dt,
            leapfrogs_per_sn=lf / N, algorithmic_tflops=F * lf / dt / 1e12, prepare_s=t_prep, simulate_s=t_sim,
            divergences=float(out['chain_info'][..., 3].sum()), tile_floats_per_sn=int(ctx._keep['data']['wt_stride']))
+ci = out['chain_info'].cpu().numpy()
+lfc = ci[..., 2]
+res['leapfrogs_per_chain'] = dict(mean=float(lfc.mean()), p50=float(np.median(lfc)), p99=float(np.percentile(lfc, 99)),
+                                  max=float(lfc.max()), argmax=[int(i) for i in np.unravel_index(lfc.argmax(), lfc.shape)],
+                                  top5=[float(x) for x in np.sort(lfc.ravel())[-5:]],
+                                  step_of_max=float(ci[..., 0].ravel()[lfc.argmax()]), step_median=float(np.median(ci[..., 0])))
 print(json.dumps(res))

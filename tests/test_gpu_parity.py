@@ -231,6 +231,34 @@ def test_nuts_work_queue_schedule_reproduces_static_schedule(n_chains, monkeypat
         assert torch.equal(outs['static'][k], outs['queue'][k]), k
 
 
+def test_far_tail_initial_distance_is_rescued():
+    """FP32 safeguard of nuts_kernel: SN 1630 of the C5 share (LSST ugrizy, 60 obs), chain 0, starts 2.1 mag
+    off in distance (log p = -2.2e6); without the rescue its step size collapses to 3e-8 and the chain runs
+    498 000 leapfrogs without moving (scripts/stuck_chain_diag.py).  With it the chain behaves like the
+    other three."""
+    from bayesn_b200 import SEDmodel
+    bands = ['u_LSST', 'g_LSST', 'r_LSST', 'i_LSST', 'z_LSST', 'y_LSST']
+    m = SEDmodel(load_model='W22_model')
+    np.random.seed(20241019)
+    z = np.random.uniform(0.02, 0.09, 2368)
+    data, yerr, params = m.simulate_light_curve(np.arange(-8, 40, 5.0), 2368, bands, yerr=0.05, err_type='mag', z=z,
+                                                mu='z', ebv_mw=0, mag=False)
+    obs, w, bi = m.simulated_obs_array(data, yerr, params)
+    sn = 1630
+    ctx = m.prepare(obs[:, :, sn:sn + 1], None, bi)
+    q0 = ctx.init_to_median(4, seed=0, sn_offset=sn)
+    lp0, _ = ctx.logp_grad(q0)
+    assert float(lp0[0, 0]) < -1e6                      # the far-tail start is what this test is about
+    out = ctx.nuts(q0, 250, 250, 10, seed=0, sn_offset=sn)
+    torch.cuda.synchronize()
+    ci = out['chain_info'].cpu().numpy()[0]
+    assert np.all(ci[:, 0] > 1e-2), ci[:, 0]             # adapted step sizes
+    assert np.all(ci[:, 2] < 1.5e5), ci[:, 2]            # leapfrogs per chain
+    Ds = out['samples'][0, :, :, m.n_eps + 3].cpu().numpy()
+    assert np.ptp(Ds.mean(axis=1)) < 0.05
+    assert abs(Ds.mean() - (params['mu'][sn] + params['del_M'][sn])) < 0.3
+
+
 def _fit_2016w(**kw):
     from bayesn_b200 import SEDmodel
     m = SEDmodel(load_model='T21_model')
