@@ -490,8 +490,10 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         const int jend = (TRAIN || M.ls_lower) ? min(ne, i0 + 32) : ne;      // eps_i = sum_{j <= i} L[i][j] e_j
         float acc = 0.f;
         if (i < ne) {
-            const float* col = c.LsT + i;
-            for (int j = 0; j < jend; ++j) acc = fmaf(__ldg(col + j * lss), c.ev[j], acc);
+            // pointer walk: with the compile-time stride the unrolled loads use immediate offsets
+            // (a 32-bit index j * lss cost two integer instructions per load)
+            const float* pc = c.LsT + i;
+            for (int j = 0; j < jend; ++j, pc += lss) acc = fmaf(__ldg(pc), c.ev[j], acc);
             c.eps[i] = acc;
         }
     }
@@ -814,8 +816,9 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         float gi = 0.f;
         if (i < ne) {
             float acc = 0.f;
-            const float* col = c.Ls + i;
-            for (int j = (TRAIN || M.ls_lower) ? 32 * s : 0; j < ne; ++j) acc = fmaf(__ldg(col + j * lss), c.ev[j], acc);
+            const int j0 = (TRAIN || M.ls_lower) ? 32 * s : 0;
+            const float* pc = c.Ls + i + (size_t)j0 * lss;
+            for (int j = j0; j < ne; ++j, pc += lss) acc = fmaf(__ldg(pc), c.ev[j], acc);
             gi = acc - q[s];
             ss = fmaf(q[s], q[s], ss);
         }
