@@ -113,6 +113,8 @@ def run_ours(args):
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     if world > 1:
+        # keep stdout for the one JSON line: NCCL's own banner ("NCCL version ...", NCCL_DEBUG >= VERSION) goes to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
     import __graft_entry__ as ge
     ge.build()
