@@ -216,9 +216,9 @@ def run_ours(args):
         roofline = {'bound': 'fp32_fma', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                     'frac': achieved / peak, 'traffic': None, 'kernel': 'nuts_kernel',
                     'traffic_note': 'ncu cannot replay this multi-second persistent launch (it stalls under '
-                                    'instrumentation); a short launch of the same kernel (592 SNe, 20+10 transitions, '
-                                    'profiles/r01b_ncu_full_raw.csv) moved 2.7 MB read + 41.5 MB written over 2.37 M '
-                                    'evaluations = 19 B/evaluation against 11.8 KB algorithmic: tiles, tables and the '
+                                    'instrumentation); a short launch of the same kernel (1184 SNe, 20+10 transitions, '
+                                    'profiles/r01k_ncu_full_raw.csv) moved 5.4 MB read + 2.9 MB written over 4.84 M '
+                                    'evaluations = 1.7 B/evaluation against 11.8 KB algorithmic: tiles, tables and the '
                                     'sampler workspace stay in L2/shared memory',
                     'peak_source': 'measured FFMA microbenchmark (bayesn_ffma_peak); MEASURED_PEAKS.json has no '
                                    'FP32 SIMT figure',
