@@ -30,7 +30,6 @@ struct bayesn_ctx {
     XchgDev X{};                // peer-memory exchange of the training sums (world 1 = off)
     std::vector<void*> tn_owned;
     bool have_tn = false;
-    unsigned long long* queue = nullptr;   // work-queue counter of the fit sampler
 };
 
 namespace {
@@ -141,8 +140,9 @@ int launch_logp(bayesn_ctx* ctx, int C, const float* q, float* logp, float* grad
 }
 
 template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
-int launch_nuts(bayesn_ctx* ctx, const NutsDev& cfg, bool use_queue, const float* q0, float* samples, float* stats,
-                float* info, float* work, cudaStream_t st) {
+int launch_nuts(bayesn_ctx* ctx, const NutsDev& cfg, unsigned long long* queue_slot, const float* q0, float* samples,
+                float* stats, float* info, float* work, cudaStream_t st) {
+    const bool use_queue = queue_slot != nullptr;
     const int C = cfg.num_chains;
     const int ntile = use_queue ? WPB : ntile_for(C);      // queue: one slot of SN data per warp
     const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE);
@@ -158,9 +158,8 @@ int launch_nuts(bayesn_ctx* ctx, const NutsDev& cfg, bool use_queue, const float
         CU_CHECK(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
         CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WPB * 32, bytes));
         if (occ < 1) return fail(ctx, -3, "work-queue schedule does not fit");
-        if (!ctx->queue) CU_CHECK(ctx, cudaMalloc(&ctx->queue, sizeof(unsigned long long)));
-        CU_CHECK(ctx, cudaMemsetAsync(ctx->queue, 0, sizeof(unsigned long long), st));
-        queue = ctx->queue;
+        CU_CHECK(ctx, cudaMemsetAsync(queue_slot, 0, sizeof(unsigned long long), st));
+        queue = queue_slot;
         grid = (unsigned)std::min<long long>(grid, (long long)occ * sms);      // one resident wave
     }
     kern<<<grid, WPB * 32, bytes, st>>>(ctx->M, ctx->D, cfg, ntile, q0, samples, stats, info, work, queue);
@@ -288,10 +287,10 @@ struct LogpCall {
     int operator()() { return launch_logp<LP, TP, VPL, RV, ST>(ctx, C, q, logp, grad, st); }
 };
 struct NutsCall {
-    bayesn_ctx* ctx; NutsDev cfg; bool use_queue; const float* q0; float* samples; float* stats; float* info; float* work;
+    bayesn_ctx* ctx; NutsDev cfg; unsigned long long* queue_slot; const float* q0; float* samples; float* stats; float* info; float* work;
     cudaStream_t st;
     template <int LP, int TP, int VPL, bool RV, bool ST>
-    int operator()() { return launch_nuts<LP, TP, VPL, RV, ST>(ctx, cfg, use_queue, q0, samples, stats, info, work, st); }
+    int operator()() { return launch_nuts<LP, TP, VPL, RV, ST>(ctx, cfg, queue_slot, q0, samples, stats, info, work, st); }
 };
 
 // numpyro.infer.hmc_util.build_adaptation_schedule (Stan windows)
@@ -341,7 +340,6 @@ void bayesn_ctx_destroy(bayesn_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     free_owned(ctx);
-    if (ctx->queue) cudaFree(ctx->queue);
     delete ctx;
 }
 
@@ -442,9 +440,16 @@ int bayesn_logp_grad_fit(bayesn_ctx* ctx, int n_chains, const float* q, float* l
     return dispatch(ctx, /*stage=*/n_chains >= 2, call);
 }
 
+static size_t nuts_vector_bytes(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg) {
+    const size_t b = (size_t)ctx->D.N * cfg->num_chains * nuts_num_vectors(cfg->max_tree_depth) * 32 * ctx->VPL * sizeof(float);
+    return (b + 255) & ~(size_t)255;
+}
+
 size_t bayesn_nuts_workspace_bytes(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg) {
     if (!ctx || !cfg || !ctx->have_model || !ctx->have_data) return 0;
-    return (size_t)ctx->D.N * cfg->num_chains * nuts_num_vectors(cfg->max_tree_depth) * 32 * ctx->VPL * sizeof(float);
+    // tree vectors of every (SN, chain) + 256 bytes for the work-queue counter of the launch (kept in the
+    // caller's workspace, not in the context, so that launches on different streams never share one)
+    return nuts_vector_bytes(ctx, cfg) + 256;
 }
 
 int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_init, float* samples, float* stats,
@@ -469,7 +474,9 @@ int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_
     for (size_t i = 0; i < 24; ++i) nd.win_end[i] = i < ends.size() ? ends[i] : 0x7fffffff;
     bool use_queue = false, stage = false;
     choose_nuts_schedule(ctx, cfg->num_chains, &use_queue, &stage);
-    NutsCall call{ctx, nd, use_queue, q_init, samples, stats, chain_info, (float*)work, (cudaStream_t)stream};
+    unsigned long long* queue_slot =
+        use_queue ? reinterpret_cast<unsigned long long*>(static_cast<char*>(work) + nuts_vector_bytes(ctx, cfg)) : nullptr;
+    NutsCall call{ctx, nd, queue_slot, q_init, samples, stats, chain_info, (float*)work, (cudaStream_t)stream};
     return dispatch(ctx, stage, call);
 }
 

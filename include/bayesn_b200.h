@@ -150,7 +150,15 @@ int bayesn_spectra_batch(bayesn_ctx* ctx, int N, int N_obs, const float* theta, 
  *                                              diverging, potential_energy, step_size}
  *   chain_info [N][C][4+D]      device, out  {final step size, mean accept (sampling), total
  *                                              leapfrogs, divergences, inverse mass diag[D]}
- *   work, work_bytes            device scratch of at least bayesn_nuts_workspace_bytes() */
+ *   work, work_bytes            device scratch of at least bayesn_nuts_workspace_bytes(): the tree
+ *                               vectors of every chain and the launch's work-queue counter (one
+ *                               workspace per concurrent launch)
+ * One asynchronous launch on `stream`.  With more than one wave of (SN, chain) units the kernel runs as
+ * one resident wave whose warps fetch units from an atomic counter (draws do not depend on the
+ * schedule; environment BAYESN_NUTS_SCHED=static|queue|queue-l1 overrides the choice for measurements).
+ * Deviation from numpyro (float64): a chain whose adapted step size falls below 1e-6 during warm-up - a
+ * float32 energy-noise stall seen for initial distances ~2 mag off - gets its distance coordinate
+ * re-solved in closed form and its step-size adaptation restarted (bayesn_kernels.cuh). */
 size_t bayesn_nuts_workspace_bytes(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg);
 int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_init, float* samples, float* stats,
                     float* chain_info, void* work, size_t work_bytes, void* stream);
