@@ -282,6 +282,10 @@ struct Dims {
     // number of 16-byte words per row keeps the 8-lane phases of LDS.128 bank-conflict free
     static constexpr int RS = ((LP4 / 4) % 2 == 1) ? LP4 : LP4 + 4;
 };
+// Observations are set up and integrated in chunks of 32 (one setup pass with lanes over observations, then
+// 16 pairs): the per-warp record region does not grow with the light-curve length, so long light curves keep
+// their occupancy (and the C5-sized per-warp slots of the work queue fit twice per SM).
+constexpr int OBS_CHUNK = 32;
 constexpr int JROWS = BP + 32;   // per-bin tables carry 32 zero rows so the last round may overrun
 constexpr int OVERRUN = BAYESN_OVERRUN;     // bins a lane may read past the end of its band's support (values discarded)
 // Row stride of the fit model's L_Sigma tables: a compile-time constant per kernel instantiation, so the
@@ -327,7 +331,7 @@ __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b
     p.wWs = wtake(LP * TP);
     p.wEv = wtake(n_eps);
     p.wEps = wtake(n_eps);
-    p.wRec = wtake(((N_obs + 1) & ~1) * rec);    // observations are processed in pairs
+    p.wRec = wtake((((N_obs + 1) & ~1) < OBS_CHUNK ? ((N_obs + 1) & ~1) : OBS_CHUNK) * rec);    // one chunk of observations (pairs)
     p.wSc = wtake(8);
     p.wAd = wtake(rvfree ? JROWS : 0);
     p.wDad = wtake(rvfree ? JROWS : 0);
@@ -552,16 +556,35 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     // dummy copy of the last observation with 1/sigma = 0, which contributes exactly nothing.
     const int npair = (c.nobs + 1) >> 1;
     if (lane == 0) c.sc[0] = S;
-    for (int o0 = 0; o0 < 2 * npair; o0 += 32) {
+    // log L is accumulated in double: far from the mode |log L| reaches 1e6 while NUTS needs energy
+    // differences to ~1e-2, which float32 partial sums cannot hold (ulp(7.5e5) = 0.06)
+    double logL = 0.0;
+    float gDs = 0.f, gAV = 0.f, gT = 0.f, gRV = 0.f;
+    const float* wtile = STAGE ? c.wt_s : c.wt_g;
+    const int hl = lane >> 1, hb = lane & 1;
+    // lane hl = 4 + l ends every reduction holding Q_l; it also keeps row l of W for the d/dtmax term
+    float wrow[TP];
+#pragma unroll
+    for (int m = 0; m < TP; ++m) wrow[m] = (hl >= 4 && hl < 4 + LP) ? c.Ws[(hl - 4) * TP + m] : 0.f;
+    float gTW = 0.f;
+    // dW[l][.] = sum_o dU_o[l] J_t,o[.] accumulates in the lane that ends each pair's reduction holding dU_o[l]
+    // (one row of 6 per lane and half, added across the halves after the loop) - a separate pass over all
+    // observations with lanes over (l, m) cost 5 % of the evaluation in the r01i profile
+    float dWr[TP];
+#pragma unroll
+    for (int m = 0; m < TP; ++m) dWr[m] = 0.f;
+    const bool qlane = hl >= 4 && hl < 4 + LP;
+  for (int o0 = 0; o0 < 2 * npair; o0 += OBS_CHUNK) {
+    {
         const int o = o0 + lane;
         const unsigned act = __ballot_sync(FULL, o < 2 * npair);     // both lanes of a pair are in or out together
-        if (o >= 2 * npair) continue;
+        if (o < 2 * npair) {
         const bool dummy = o >= c.nobs;
         const float4 ob = c.obs[dummy ? c.nobs - 1 : o];
         float t = ob.x - tmax;
         float J[TP], dJ[TP];
         spline_row<TP>(t, T, c.sTau, c.sKD, J, dJ);
-        float* rc = c.rec + o * REC;
+        float* rc = c.rec + lane * REC;
         // the record is assembled in registers and written with 128-bit stores: the record stride (an odd
         // number of 16-byte words) makes those conflict-free, while 32-bit stores at a stride of REC words
         // were 4-way bank-conflicted (r01i profile)
@@ -612,6 +635,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         *reinterpret_cast<float4*>(rc + DM::R_SC) =
             make_float4(interp ? (t - fl) : 0.f, __int_as_float(i0 | (interp ? 256 : 0) | (nro << 9) | (band << 16)),
                         dummy ? 0.f : ob.y, dummy ? 0.f : ob.z);
+        }
     }
     __syncwarp();
 
@@ -620,26 +644,9 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     // are in the same band - the common case after sorting - neighbouring lanes read the same J_l row
     // and weight, which the shared-memory pipe serves as one broadcast, halving its traffic (the LSU
     // pipe, not the FMA pipe, is the busiest unit of this loop).
-    // log L is accumulated in double: far from the mode |log L| reaches 1e6 while NUTS needs energy
-    // differences to ~1e-2, which float32 partial sums cannot hold (ulp(7.5e5) = 0.06)
-    double logL = 0.0;
-    float gDs = 0.f, gAV = 0.f, gT = 0.f, gRV = 0.f;
-    const float* wtile = STAGE ? c.wt_s : c.wt_g;
-    const int hl = lane >> 1, hb = lane & 1;
-    // lane hl = 4 + l ends every reduction holding Q_l; it also keeps row l of W for the d/dtmax term
-    float wrow[TP];
-#pragma unroll
-    for (int m = 0; m < TP; ++m) wrow[m] = (hl >= 4 && hl < 4 + LP) ? c.Ws[(hl - 4) * TP + m] : 0.f;
-    float gTW = 0.f;
-    // dW[l][.] = sum_o dU_o[l] J_t,o[.] accumulates in the lane that ends each pair's reduction holding dU_o[l]
-    // (one row of 6 per lane and half, added across the halves after the loop) - a separate pass over all
-    // observations with lanes over (l, m) cost 5 % of the evaluation in the r01i profile
-    float dWr[TP];
-#pragma unroll
-    for (int m = 0; m < TP; ++m) dWr[m] = 0.f;
-    const bool qlane = hl >= 4 && hl < 4 + LP;
-    for (int p = 0; p < npair; ++p) {
-        float* rc = c.rec + (2 * p + hb) * REC;
+    const int p_end = min(npair, (o0 + OBS_CHUNK) >> 1);
+    for (int p = o0 >> 1; p < p_end; ++p) {
+        float* rc = c.rec + (2 * p - o0 + hb) * REC;
         float u[LP4];
         {
             const float4* up = reinterpret_cast<const float4*>(rc);
@@ -779,6 +786,8 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
 #pragma unroll
         for (int m = 0; m < TP; ++m) dWr[m] = fmaf(dU, rc[DM::R_JT + m], dWr[m]);
     }
+    __syncwarp();      // the next chunk overwrites the records
+  }
 #pragma unroll
     for (int m = 0; m < TP; ++m) dWr[m] += __shfl_xor_sync(FULL, dWr[m], 1);
     // the two halves hold the sums over their own observations

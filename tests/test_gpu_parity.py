@@ -38,6 +38,11 @@ def _lib(built_library):
     ('popRV', 'pop_RV_model', PS1, np.arange(-8, 40, 4.0), dict(N=5, n_chains=4)),
     ('uniformRV', 'T21_model', PS1, np.arange(-8, 40, 4.0), dict(N=5, n_chains=2, rv='uniform')),
     ('G25_T9_D77', 'G25_85day_model', PS1, np.arange(-8, 80, 6.0), dict(N=4, n_chains=4)),
+    # long light curves: 49 epochs x 6 bands = 294 observations (ten chunks of 32, ragged through the mask);
+    # the per-warp record region does not grow with the light-curve length
+    ('long_W22_lsst_294obs', 'W22_model', ['u_LSST', 'g_LSST', 'r_LSST', 'i_LSST', 'z_LSST', 'y_LSST'],
+     np.arange(-9, 40, 1.0), dict(N=3, n_chains=4, zrange=(0.02, 0.09))),
+    ('long_T21_odd_count', 'T21_model', PS1, np.arange(-8.5, 40, 1.5), dict(N=3, n_chains=1)),
 ])
 def test_logp_grad_parity(name, model, bands, t, kw):
     kw = dict(kw)
