@@ -574,220 +574,218 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
 #pragma unroll
     for (int m = 0; m < TP; ++m) dWr[m] = 0.f;
     const bool qlane = hl >= 4 && hl < 4 + LP;
-  for (int o0 = 0; o0 < 2 * npair; o0 += OBS_CHUNK) {
-    {
+    for (int o0 = 0; o0 < 2 * npair; o0 += OBS_CHUNK) {
         const int o = o0 + lane;
         const unsigned act = __ballot_sync(FULL, o < 2 * npair);     // both lanes of a pair are in or out together
         if (o < 2 * npair) {
-        const bool dummy = o >= c.nobs;
-        const float4 ob = c.obs[dummy ? c.nobs - 1 : o];
-        float t = ob.x - tmax;
-        float J[TP], dJ[TP];
-        spline_row<TP>(t, T, c.sTau, c.sKD, J, dJ);
-        float* rc = c.rec + lane * REC;
-        // the record is assembled in registers and written with 128-bit stores: the record stride (an odd
-        // number of 16-byte words) makes those conflict-free, while 32-bit stores at a stride of REC words
-        // were 4-way bank-conflicted (r01i profile)
-        float rv[DM::R_SC];
+            const bool dummy = o >= c.nobs;
+            const float4 ob = c.obs[dummy ? c.nobs - 1 : o];
+            float t = ob.x - tmax;
+            float J[TP], dJ[TP];
+            spline_row<TP>(t, T, c.sTau, c.sKD, J, dJ);
+            float* rc = c.rec + lane * REC;
+            // the record is assembled in registers and written with 128-bit stores: the record stride (an odd
+            // number of 16-byte words) makes those conflict-free, while 32-bit stores at a stride of REC words
+            // were 4-way bank-conflicted (r01i profile)
+            float rv[DM::R_SC];
 #pragma unroll
-        for (int i = 0; i < DM::R_SC; ++i) rv[i] = 0.f;
+            for (int i = 0; i < DM::R_SC; ++i) rv[i] = 0.f;
 #pragma unroll
-        for (int m = 0; m < TP; ++m) {
-            rv[DM::R_JT + m] = J[m];
-            if (!TRAIN) rv[DM::R_DJ + m] = dJ[m];
-        }
+            for (int m = 0; m < TP; ++m) {
+                rv[DM::R_JT + m] = J[m];
+                if (!TRAIN) rv[DM::R_DJ + m] = dJ[m];
+            }
 #pragma unroll
-        for (int l = 0; l < LP4; ++l) {
-            float u = 0.f;
-            if (l < LP) {
-                if constexpr (TP % 2 == 0) {
-                    // rows of W are 8-byte aligned: half as many (broadcast) shared-memory loads
-                    const float2* wr = reinterpret_cast<const float2*>(c.Ws + l * TP);
+            for (int l = 0; l < LP4; ++l) {
+                float u = 0.f;
+                if (l < LP) {
+                    if constexpr (TP % 2 == 0) {
+                        // rows of W are 8-byte aligned: half as many (broadcast) shared-memory loads
+                        const float2* wr = reinterpret_cast<const float2*>(c.Ws + l * TP);
 #pragma unroll
-                    for (int m = 0; m < TP; m += 2) {
-                        const float2 w2 = wr[m >> 1];
-                        u = fmaf(w2.x, J[m], u);
-                        u = fmaf(w2.y, J[m + 1], u);
+                        for (int m = 0; m < TP; m += 2) {
+                            const float2 w2 = wr[m >> 1];
+                            u = fmaf(w2.x, J[m], u);
+                            u = fmaf(w2.y, J[m + 1], u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < TP; ++m) u = fmaf(c.Ws[l * TP + m], J[m], u);
                     }
-                } else {
+                }
+                rv[l] = -C2 * u;
+            }
 #pragma unroll
-                    for (int m = 0; m < TP; ++m) u = fmaf(c.Ws[l * TP + m], J[m], u);
+            for (int i = 0; i < DM::R_SC; i += 4)
+                *reinterpret_cast<float4*>(rc + i) = make_float4(rv[i], rv[i + 1], rv[i + 2], rv[i + 3]);
+            float fl = floorf(t);
+            int i0 = 19 + (int)fl, i1 = 19 + (int)ceilf(t);
+            i0 = min(max(i0, 0), NPH - 1);
+            i1 = min(max(i1, 0), NPH - 1);
+            // the upper Hsiao row is read at i0 + 1; when ceil == floor (integer phase) or the index
+            // is clamped the interpolation degenerates to row i0 and d/dt of it vanishes
+            const bool interp = i1 != i0;
+            // rounds of the band-pass loop for this PAIR (the wider of its two supports), so that the pair
+            // prologue does not wait for a support load and a shuffle before it knows its trip count
+            const int band = __float_as_int(ob.w);
+            const int4 spo = c.sup[band];
+            int nro = (spo.y - spo.x + 15) >> 4;
+            nro = max(nro, __shfl_xor_sync(act, nro, 1));
+            *reinterpret_cast<float4*>(rc + DM::R_SC) =
+                make_float4(interp ? (t - fl) : 0.f, __int_as_float(i0 | (interp ? 256 : 0) | (nro << 9) | (band << 16)),
+                            dummy ? 0.f : ob.y, dummy ? 0.f : ob.z);
+        }
+        __syncwarp();
+
+        // ---- band-pass integrals: two observations per pass, 16 lanes over wavelength bins each ---------
+        // The lanes of the two observations are INTERLEAVED (even lanes: first, odd lanes: second): when both
+        // are in the same band - the common case after sorting - neighbouring lanes read the same J_l row
+        // and weight, which the shared-memory pipe serves as one broadcast, halving its traffic (the LSU
+        // pipe, not the FMA pipe, is the busiest unit of this loop).
+        const int p_end = min(npair, (o0 + OBS_CHUNK) >> 1);
+        for (int p = o0 >> 1; p < p_end; ++p) {
+            float* rc = c.rec + (2 * p - o0 + hb) * REC;
+            float u[LP4];
+            {
+                const float4* up = reinterpret_cast<const float4*>(rc);
+#pragma unroll
+                for (int j = 0; j < LP4 / 4; ++j) {
+                    float4 a = up[j];
+                    u[4 * j] = a.x; u[4 * j + 1] = a.y; u[4 * j + 2] = a.z; u[4 * j + 3] = a.w;
                 }
             }
-            rv[l] = -C2 * u;
-        }
+            const float4 scal = *reinterpret_cast<const float4*>(rc + DM::R_SC);
+            const float f = scal.x;
+            const int pk = __float_as_int(scal.y);
+            const float yo = scal.z, iso = scal.w;
+            const int4 sp = c.sup[pk >> 16];
+            const int nr = (pk >> 9) & 0x7f;          // <= 19 rounds of 16 bins
+            // running pointers: one add per array per round instead of rebuilding addresses
+            const int b_first = sp.x + hl;
+            const float* p0 = hs + (pk & 0xff) * BP + b_first;
+            const float* pw = wtile + sp.z + hl;
+            const float4* pj = reinterpret_cast<const float4*>(c.sJl) + b_first * (RS / 4);
+            const float* pa = adv + b_first;
+            const float* pda = RVFREE ? (c.wdad + b_first) : (TRAIN ? c.dad_g + b_first : nullptr);
+            int rem = sp.y - b_first;                // this lane is inside the support while rem > 0
+            float acc[16];
 #pragma unroll
-        for (int i = 0; i < DM::R_SC; i += 4)
-            *reinterpret_cast<float4*>(rc + i) = make_float4(rv[i], rv[i + 1], rv[i + 2], rv[i + 3]);
-        float fl = floorf(t);
-        int i0 = 19 + (int)fl, i1 = 19 + (int)ceilf(t);
-        i0 = min(max(i0, 0), NPH - 1);
-        i1 = min(max(i1, 0), NPH - 1);
-        // the upper Hsiao row is read at i0 + 1; when ceil == floor (integer phase) or the index
-        // is clamped the interpolation degenerates to row i0 and d/dt of it vanishes
-        const bool interp = i1 != i0;
-        // rounds of the band-pass loop for this PAIR (the wider of its two supports), so that the pair
-        // prologue does not wait for a support load and a shuffle before it knows its trip count
-        const int band = __float_as_int(ob.w);
-        const int4 spo = c.sup[band];
-        int nro = (spo.y - spo.x + 15) >> 4;
-        nro = max(nro, __shfl_xor_sync(act, nro, 1));
-        *reinterpret_cast<float4*>(rc + DM::R_SC) =
-            make_float4(interp ? (t - fl) : 0.f, __int_as_float(i0 | (interp ? 256 : 0) | (nro << 9) | (band << 16)),
-                        dummy ? 0.f : ob.y, dummy ? 0.f : ob.z);
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#if BAYESN_FFMA2
+            // knot pairs (l, l+1) share one packed FMA: u and the J_l row arrive as aligned pairs from LDS.128,
+            // the even / odd halves are exactly the two FFMA chains of the scalar loop
+            f32x2 u2[LP4 / 2], q2[LP4 / 2];
+#pragma unroll
+            for (int k = 0; k < LP4 / 2; ++k) { u2[k] = pack2(u[2 * k], u[2 * k + 1]); q2[k] = pack2(0.f, 0.f); }
+#endif
+            for (int it = 0; it < nr; ++it) {
+#if BAYESN_FFMA2
+                f32x2 jl2[LP4 / 2];
+#pragma unroll
+                for (int j = 0; j < LP4 / 4; ++j) {
+                    const ulonglong2 v = reinterpret_cast<const ulonglong2*>(pj)[j];
+                    jl2[2 * j] = v.x; jl2[2 * j + 1] = v.y;
+                }
+#else
+                float jl[LP4];
+#pragma unroll
+                for (int j = 0; j < LP4 / 4; ++j) {
+                    const float4 v = pj[j];
+                    jl[4 * j] = v.x; jl[4 * j + 1] = v.y; jl[4 * j + 2] = v.z; jl[4 * j + 3] = v.w;
+                }
+#endif
+                BAYESN_ASSERT((const float*)pj >= c.smem_lo && (const float*)(pj + LP4 / 4) <= c.smem_hi);
+                BAYESN_ASSERT(STAGE ? (pw >= c.smem_lo && pw < c.smem_hi) : (pw >= c.wt_lo && pw < c.wt_hi));
+                BAYESN_ASSERT(p0 >= hs && p0 + BP < c.hs_hi);
+                BAYESN_ASSERT(TRAIN || (pa >= c.smem_lo && pa < c.smem_hi));
+                const float wl = STAGE ? *pw : __ldg(pw);
+                const float h0 = __ldg(p0), h1 = __ldg(p0 + BP);
+                const float a = TRAIN ? __ldg(pa) : *pa;
+                // two independent FFMA chains (4-cycle dependent-issue latency)
+                float g0 = 0.f, g1 = 0.f;
+#if BAYESN_FFMA2
+                {
+                    f32x2 g2 = pack2(0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < (LP + 1) / 2; ++k) g2 = ffma2(jl2[k], u2[k], g2);
+                    unpack2(g2, g0, g1);
+                }
+#else
+#pragma unroll
+                for (int l = 0; l < LP; l += 2) {
+                    g0 = fmaf(jl[l], u[l], g0);
+                    if (l + 1 < LP) g1 = fmaf(jl[l + 1], u[l + 1], g1);
+                }
+#endif
+                const float dh = h1 - h0;
+                const float H = fmaf(f, dh, h0);
+                const float e = ex2_approx(fmaf(AVc, a, g0 + g1));
+                const float we = (rem > 0) ? wl * e : 0.f;     // select, not multiply: e may be garbage past the support
+                const float P = we * H;
+                acc[0] += P;
+                acc[1] = fmaf(P, a, acc[1]);
+                acc[2] = fmaf(we, dh, acc[2]);
+                if (DRV) { acc[3] = fmaf(P, TRAIN ? __ldg(pda) : *pda, acc[3]); pda += 16; }
+#if BAYESN_FFMA2
+                {
+                    const f32x2 P2 = pack2(P, P);
+#pragma unroll
+                    for (int k = 0; k < (LP + 1) / 2; ++k) q2[k] = ffma2(jl2[k], P2, q2[k]);
+                }
+#else
+#pragma unroll
+                for (int l = 0; l < LP; ++l) acc[4 + l] = fmaf(jl[l], P, acc[4 + l]);
+#endif
+                p0 += 16; pw += 16; pj += 16 * (RS / 4); pa += 16; rem -= 16;
+            }
+#if BAYESN_FFMA2
+#pragma unroll
+            for (int k = 0; k < (LP + 1) / 2; ++k) {
+                float lo, hi;
+                unpack2(q2[k], lo, hi);
+                acc[4 + 2 * k] = lo;
+                if (4 + 2 * k + 1 < 16 && 2 * k + 1 < LP) acc[4 + 2 * k + 1] = hi;
+            }
+#endif
+            const float val = treduce16h(acc, lane);
+            const float F = __shfl_sync(FULL, val, hb);
+            const float FA = __shfl_sync(FULL, val, hb | 2);
+            const float FT = __shfl_sync(FULL, val, hb | 4);
+            const float Sv = c.sc[0];
+            const float flux = Sv * F;
+            float chi, r;                      // r = d log L / d flux
+            if (TRAIN) {
+                // magnitude-space likelihood (get_mag_batch :711-759, :1178-1182): m = 27.5 - 2.5 log10 flux.
+                // The host folds 10^(0.4 (ybar_s - 27.5)) into the weights and stores y - ybar_s, so that
+                // both magnitudes are O(1) and their float32 difference keeps ~1e-7 mag (the gradient
+                // multiplies it by n_obs / sigma^2)
+                const float mg = -0.7525749891599529f * log2f(flux);
+                chi = (yo - mg) * iso;
+                r = chi * iso * (-1.0857362047581296f) / flux;
+            } else {
+                chi = (yo - flux) * iso;
+                r = chi * iso;
+            }
+            logL += (double)(-0.5f * chi * chi);
+            const float coef = r * Sv;
+            gDs = fmaf(-KAPPA * r, flux, gDs);
+            gAV = fmaf(-KAPPA * coef, FA, gAV);
+            gT = fmaf((pk & 256) ? coef : 0.f, FT, gT);
+            if (DRV) gRV = fmaf(-KAPPA * AV * coef, __shfl_sync(FULL, val, hb | 6), gRV);
+            // d logL / d(sum_m W[l][m] Jt[m]) for this observation: its outer product with J_t goes into dW,
+            // its product with (W J_t'(t))[l] into the gradient through the time spline
+            const float dU = qlane ? -KAPPA * coef * val : 0.f;
+            if (!TRAIN) {
+                float du = 0.f;
+#pragma unroll
+                for (int m = 0; m < TP; ++m) du = fmaf(wrow[m], rc[DM::R_DJ + m], du);
+                gTW = fmaf(dU, du, gTW);
+            }
+#pragma unroll
+            for (int m = 0; m < TP; ++m) dWr[m] = fmaf(dU, rc[DM::R_JT + m], dWr[m]);
         }
+        __syncwarp();      // the next chunk overwrites the records
     }
-    __syncwarp();
-
-    // ---- band-pass integrals: two observations per pass, 16 lanes over wavelength bins each ---------
-    // The lanes of the two observations are INTERLEAVED (even lanes: first, odd lanes: second): when both
-    // are in the same band - the common case after sorting - neighbouring lanes read the same J_l row
-    // and weight, which the shared-memory pipe serves as one broadcast, halving its traffic (the LSU
-    // pipe, not the FMA pipe, is the busiest unit of this loop).
-    const int p_end = min(npair, (o0 + OBS_CHUNK) >> 1);
-    for (int p = o0 >> 1; p < p_end; ++p) {
-        float* rc = c.rec + (2 * p - o0 + hb) * REC;
-        float u[LP4];
-        {
-            const float4* up = reinterpret_cast<const float4*>(rc);
-#pragma unroll
-            for (int j = 0; j < LP4 / 4; ++j) {
-                float4 a = up[j];
-                u[4 * j] = a.x; u[4 * j + 1] = a.y; u[4 * j + 2] = a.z; u[4 * j + 3] = a.w;
-            }
-        }
-        const float4 scal = *reinterpret_cast<const float4*>(rc + DM::R_SC);
-        const float f = scal.x;
-        const int pk = __float_as_int(scal.y);
-        const float yo = scal.z, iso = scal.w;
-        const int4 sp = c.sup[pk >> 16];
-        const int nr = (pk >> 9) & 0x7f;          // <= 19 rounds of 16 bins
-        // running pointers: one add per array per round instead of rebuilding addresses
-        const int b_first = sp.x + hl;
-        const float* p0 = hs + (pk & 0xff) * BP + b_first;
-        const float* pw = wtile + sp.z + hl;
-        const float4* pj = reinterpret_cast<const float4*>(c.sJl) + b_first * (RS / 4);
-        const float* pa = adv + b_first;
-        const float* pda = RVFREE ? (c.wdad + b_first) : (TRAIN ? c.dad_g + b_first : nullptr);
-        int rem = sp.y - b_first;                // this lane is inside the support while rem > 0
-        float acc[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-#if BAYESN_FFMA2
-        // knot pairs (l, l+1) share one packed FMA: u and the J_l row arrive as aligned pairs from LDS.128,
-        // the even / odd halves are exactly the two FFMA chains of the scalar loop
-        f32x2 u2[LP4 / 2], q2[LP4 / 2];
-#pragma unroll
-        for (int k = 0; k < LP4 / 2; ++k) { u2[k] = pack2(u[2 * k], u[2 * k + 1]); q2[k] = pack2(0.f, 0.f); }
-#endif
-        for (int it = 0; it < nr; ++it) {
-#if BAYESN_FFMA2
-            f32x2 jl2[LP4 / 2];
-#pragma unroll
-            for (int j = 0; j < LP4 / 4; ++j) {
-                const ulonglong2 v = reinterpret_cast<const ulonglong2*>(pj)[j];
-                jl2[2 * j] = v.x; jl2[2 * j + 1] = v.y;
-            }
-#else
-            float jl[LP4];
-#pragma unroll
-            for (int j = 0; j < LP4 / 4; ++j) {
-                const float4 v = pj[j];
-                jl[4 * j] = v.x; jl[4 * j + 1] = v.y; jl[4 * j + 2] = v.z; jl[4 * j + 3] = v.w;
-            }
-#endif
-            BAYESN_ASSERT((const float*)pj >= c.smem_lo && (const float*)(pj + LP4 / 4) <= c.smem_hi);
-            BAYESN_ASSERT(STAGE ? (pw >= c.smem_lo && pw < c.smem_hi) : (pw >= c.wt_lo && pw < c.wt_hi));
-            BAYESN_ASSERT(p0 >= hs && p0 + BP < c.hs_hi);
-            BAYESN_ASSERT(TRAIN || (pa >= c.smem_lo && pa < c.smem_hi));
-            const float wl = STAGE ? *pw : __ldg(pw);
-            const float h0 = __ldg(p0), h1 = __ldg(p0 + BP);
-            const float a = TRAIN ? __ldg(pa) : *pa;
-            // two independent FFMA chains (4-cycle dependent-issue latency)
-            float g0 = 0.f, g1 = 0.f;
-#if BAYESN_FFMA2
-            {
-                f32x2 g2 = pack2(0.f, 0.f);
-#pragma unroll
-                for (int k = 0; k < (LP + 1) / 2; ++k) g2 = ffma2(jl2[k], u2[k], g2);
-                unpack2(g2, g0, g1);
-            }
-#else
-#pragma unroll
-            for (int l = 0; l < LP; l += 2) {
-                g0 = fmaf(jl[l], u[l], g0);
-                if (l + 1 < LP) g1 = fmaf(jl[l + 1], u[l + 1], g1);
-            }
-#endif
-            const float dh = h1 - h0;
-            const float H = fmaf(f, dh, h0);
-            const float e = ex2_approx(fmaf(AVc, a, g0 + g1));
-            const float we = (rem > 0) ? wl * e : 0.f;     // select, not multiply: e may be garbage past the support
-            const float P = we * H;
-            acc[0] += P;
-            acc[1] = fmaf(P, a, acc[1]);
-            acc[2] = fmaf(we, dh, acc[2]);
-            if (DRV) { acc[3] = fmaf(P, TRAIN ? __ldg(pda) : *pda, acc[3]); pda += 16; }
-#if BAYESN_FFMA2
-            {
-                const f32x2 P2 = pack2(P, P);
-#pragma unroll
-                for (int k = 0; k < (LP + 1) / 2; ++k) q2[k] = ffma2(jl2[k], P2, q2[k]);
-            }
-#else
-#pragma unroll
-            for (int l = 0; l < LP; ++l) acc[4 + l] = fmaf(jl[l], P, acc[4 + l]);
-#endif
-            p0 += 16; pw += 16; pj += 16 * (RS / 4); pa += 16; rem -= 16;
-        }
-#if BAYESN_FFMA2
-#pragma unroll
-        for (int k = 0; k < (LP + 1) / 2; ++k) {
-            float lo, hi;
-            unpack2(q2[k], lo, hi);
-            acc[4 + 2 * k] = lo;
-            if (4 + 2 * k + 1 < 16 && 2 * k + 1 < LP) acc[4 + 2 * k + 1] = hi;
-        }
-#endif
-        const float val = treduce16h(acc, lane);
-        const float F = __shfl_sync(FULL, val, hb);
-        const float FA = __shfl_sync(FULL, val, hb | 2);
-        const float FT = __shfl_sync(FULL, val, hb | 4);
-        const float Sv = c.sc[0];
-        const float flux = Sv * F;
-        float chi, r;                      // r = d log L / d flux
-        if (TRAIN) {
-            // magnitude-space likelihood (get_mag_batch :711-759, :1178-1182): m = 27.5 - 2.5 log10 flux.
-            // The host folds 10^(0.4 (ybar_s - 27.5)) into the weights and stores y - ybar_s, so that
-            // both magnitudes are O(1) and their float32 difference keeps ~1e-7 mag (the gradient
-            // multiplies it by n_obs / sigma^2)
-            const float mg = -0.7525749891599529f * log2f(flux);
-            chi = (yo - mg) * iso;
-            r = chi * iso * (-1.0857362047581296f) / flux;
-        } else {
-            chi = (yo - flux) * iso;
-            r = chi * iso;
-        }
-        logL += (double)(-0.5f * chi * chi);
-        const float coef = r * Sv;
-        gDs = fmaf(-KAPPA * r, flux, gDs);
-        gAV = fmaf(-KAPPA * coef, FA, gAV);
-        gT = fmaf((pk & 256) ? coef : 0.f, FT, gT);
-        if (DRV) gRV = fmaf(-KAPPA * AV * coef, __shfl_sync(FULL, val, hb | 6), gRV);
-        // d logL / d(sum_m W[l][m] Jt[m]) for this observation: its outer product with J_t goes into dW,
-        // its product with (W J_t'(t))[l] into the gradient through the time spline
-        const float dU = qlane ? -KAPPA * coef * val : 0.f;
-        if (!TRAIN) {
-            float du = 0.f;
-#pragma unroll
-            for (int m = 0; m < TP; ++m) du = fmaf(wrow[m], rc[DM::R_DJ + m], du);
-            gTW = fmaf(dU, du, gTW);
-        }
-#pragma unroll
-        for (int m = 0; m < TP; ++m) dWr[m] = fmaf(dU, rc[DM::R_JT + m], dWr[m]);
-    }
-    __syncwarp();      // the next chunk overwrites the records
-  }
 #pragma unroll
     for (int m = 0; m < TP; ++m) dWr[m] += __shfl_xor_sync(FULL, dWr[m], 1);
     // the two halves hold the sums over their own observations

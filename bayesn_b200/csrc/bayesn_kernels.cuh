@@ -262,337 +262,337 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
     if (!active) return;
     const int lane = threadIdx.x & 31;
     const unsigned long long total_units = (unsigned long long)Dd.N * C;
-  for (bool first_unit = true;; first_unit = false) {
-    size_t unit;
-    if (dyn) {
-        unsigned long long u = 0;
-        if (lane == 0) u = atomicAdd(queue, 1ULL);
-        u = __shfl_sync(FULL, u, 0);
-        if (u >= total_units) break;
-        sn = (int)(u / (unsigned)C);
-        chain = (int)(u - (unsigned long long)sn * C);
-        const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE);
-        warp_bind<STAGE>(Dd, P, smem, c, sn, lane);
-    } else {
-        if (!first_unit) break;
-    }
-    unit = (size_t)sn * C + chain;
-    const int D = M.D;
-    const int nvec = nuts_num_vectors(cfg.max_depth);
-    VecIO<VPL> io{work + unit * (size_t)nvec * 32 * VPL, lane};
-    const uint2 key = make_uint2(cfg.seed_lo, cfg.seed_hi);
-    const uint32_t gunit = (uint32_t)unit + cfg.unit_offset;      // random streams do not depend on the sharding
-    bool own[VPL];
+    for (bool first_unit = true;; first_unit = false) {
+        size_t unit;
+        if (dyn) {
+            unsigned long long u = 0;
+            if (lane == 0) u = atomicAdd(queue, 1ULL);
+            u = __shfl_sync(FULL, u, 0);
+            if (u >= total_units) break;
+            sn = (int)(u / (unsigned)C);
+            chain = (int)(u - (unsigned long long)sn * C);
+            const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE);
+            warp_bind<STAGE>(Dd, P, smem, c, sn, lane);
+        } else {
+            if (!first_unit) break;
+        }
+        unit = (size_t)sn * C + chain;
+        const int D = M.D;
+        const int nvec = nuts_num_vectors(cfg.max_depth);
+        VecIO<VPL> io{work + unit * (size_t)nvec * 32 * VPL, lane};
+        const uint2 key = make_uint2(cfg.seed_lo, cfg.seed_hi);
+        const uint32_t gunit = (uint32_t)unit + cfg.unit_offset;      // random streams do not depend on the sharding
+        bool own[VPL];
 #pragma unroll
-    for (int s = 0; s < VPL; ++s) own[s] = (lane + 32 * s) < D;
+        for (int s = 0; s < VPL; ++s) own[s] = (lane + 32 * s) < D;
 
-    float z[VPL], r[VPL], g[VPL], im[VPL], rsum[VPL], tmp[VPL], tmp2[VPL];
+        float z[VPL], r[VPL], g[VPL], im[VPL], rsum[VPL], tmp[VPL], tmp2[VPL];
 #pragma unroll
-    for (int s = 0; s < VPL; ++s) {
-        z[s] = own[s] ? q_init[unit * D + lane + 32 * s] : 0.f;
-        if (lane + 32 * s == M.n_eps + 3) z[s] -= c.muhat;   // sample Ds - muhat (float32 resolution)
-        im[s] = own[s] ? 1.f : 0.f;
-        tmp[s] = 0.f;
-    }
-    io.st(V_WMEAN, tmp);
-    io.st(V_WM2, tmp);
-    // adaptation state (numpyro warmup_adapter / dual_averaging / welford_covariance)
-    double pe = 0.0;   // potential energy = -log p (double: see eval_logp_grad)
-    float step = cfg.init_step;
-    float da_x = 0.f, da_xavg = 0.f, da_gavg = 0.f, da_prox = logf(10.f * step);
-    int da_t = 0, wf_n = 0, window = 0;
-    float mean_acc = 0.f;
-    long long total_steps = 0;
-    int n_div = 0;
-    const int n_iter = cfg.num_warmup + cfg.num_samples;
+        for (int s = 0; s < VPL; ++s) {
+            z[s] = own[s] ? q_init[unit * D + lane + 32 * s] : 0.f;
+            if (lane + 32 * s == M.n_eps + 3) z[s] -= c.muhat;   // sample Ds - muhat (float32 resolution)
+            im[s] = own[s] ? 1.f : 0.f;
+            tmp[s] = 0.f;
+        }
+        io.st(V_WMEAN, tmp);
+        io.st(V_WM2, tmp);
+        // adaptation state (numpyro warmup_adapter / dual_averaging / welford_covariance)
+        double pe = 0.0;   // potential energy = -log p (double: see eval_logp_grad)
+        float step = cfg.init_step;
+        float da_x = 0.f, da_xavg = 0.f, da_gavg = 0.f, da_prox = logf(10.f * step);
+        int da_t = 0, wf_n = 0, window = 0;
+        float mean_acc = 0.f;
+        long long total_steps = 0;
+        int n_div = 0;
+        const int n_iter = cfg.num_warmup + cfg.num_samples;
 
-    // per-transition / per-doubling state
-    int it = 0;
-    uint32_t rk = 0;
-    double E0 = 0.0, prop_pe = 0.0, sprop_pe = 0.0;
-    float w_main = 0.f, sum_acc = 0.f;
-    int depth = 0, n_prop = 0;
-    bool turning = false, diverging = false;
-    bool going_right = false;
-    float u_main = 0.f, eps_dir = 0.f;
-    int n_max = 1, n_sub = 0;
-    bool s_turn = false, s_div = false;
-    float w_sub = -INFINITY, s_acc = 0.f;
+        // per-transition / per-doubling state
+        int it = 0;
+        uint32_t rk = 0;
+        double E0 = 0.0, prop_pe = 0.0, sprop_pe = 0.0;
+        float w_main = 0.f, sum_acc = 0.f;
+        int depth = 0, n_prop = 0;
+        bool turning = false, diverging = false;
+        bool going_right = false;
+        float u_main = 0.f, eps_dir = 0.f;
+        int n_max = 1, n_sub = 0;
+        bool s_turn = false, s_div = false;
+        float w_sub = -INFINITY, s_acc = 0.f;
 
-    auto begin_transition = [&]() {
-        rk = 0;
-        // momentum refresh r ~ N(0, M)
-        uint4 ra = philox4x32(make_uint4((uint32_t)it, 0x40000000u, (uint32_t)lane, gunit), key);
-        float n0 = sqrtf(-2.f * logf(u01(ra.x) + 5.9604644775390625e-8f));
-        float n1 = sqrtf(-2.f * logf(u01(ra.z) + 5.9604644775390625e-8f));
-        float sn0, cs0, sn1, cs1;
-        sincospif(2.f * u01(ra.y), &sn0, &cs0);
-        sincospif(2.f * u01(ra.w), &sn1, &cs1);
-        float nrm[4] = {n0 * cs0, n0 * sn0, n1 * cs1, n1 * sn1};
+        auto begin_transition = [&]() {
+            rk = 0;
+            // momentum refresh r ~ N(0, M)
+            uint4 ra = philox4x32(make_uint4((uint32_t)it, 0x40000000u, (uint32_t)lane, gunit), key);
+            float n0 = sqrtf(-2.f * logf(u01(ra.x) + 5.9604644775390625e-8f));
+            float n1 = sqrtf(-2.f * logf(u01(ra.z) + 5.9604644775390625e-8f));
+            float sn0, cs0, sn1, cs1;
+            sincospif(2.f * u01(ra.y), &sn0, &cs0);
+            sincospif(2.f * u01(ra.w), &sn1, &cs1);
+            float nrm[4] = {n0 * cs0, n0 * sn0, n1 * cs1, n1 * sn1};
 #pragma unroll
-        for (int s = 0; s < VPL; ++s) r[s] = own[s] ? nrm[s & 3] * rsqrtf(im[s]) : 0.f;
-        E0 = pe + 0.5 * (double)vdot_im<VPL>(im, r, r);
-        io.st(V_ZL, z); io.st(V_RL, r); io.st(V_GL, g);
-        io.st(V_ZR, z); io.st(V_RR, r); io.st(V_GR, g);
-        io.st(V_ZP, z); io.st(V_GP, g); io.st(V_RSUM, r);
-        prop_pe = pe;
-        w_main = 0.f; sum_acc = 0.f;
-        depth = 0; n_prop = 0;
-        turning = false; diverging = false;
-    };
-    auto begin_doubling = [&]() {
-        uint4 rd = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, gunit), key);
-        going_right = (rd.x >> 31) != 0;
-        u_main = u01(rd.y);
-        if (going_right) { io.ld(V_ZR, z); io.ld(V_RR, r); io.ld(V_GR, g); }
-        else { io.ld(V_ZL, z); io.ld(V_RL, r); io.ld(V_GL, g); }
-        eps_dir = going_right ? step : -step;
-        n_max = 1 << depth;
-        n_sub = 0;
-        s_turn = false; s_div = false;
-        w_sub = -INFINITY; s_acc = 0.f; sprop_pe = 0.0;
-    };
+            for (int s = 0; s < VPL; ++s) r[s] = own[s] ? nrm[s & 3] * rsqrtf(im[s]) : 0.f;
+            E0 = pe + 0.5 * (double)vdot_im<VPL>(im, r, r);
+            io.st(V_ZL, z); io.st(V_RL, r); io.st(V_GL, g);
+            io.st(V_ZR, z); io.st(V_RR, r); io.st(V_GR, g);
+            io.st(V_ZP, z); io.st(V_GP, g); io.st(V_RSUM, r);
+            prop_pe = pe;
+            w_main = 0.f; sum_acc = 0.f;
+            depth = 0; n_prop = 0;
+            turning = false; diverging = false;
+        };
+        auto begin_doubling = [&]() {
+            uint4 rd = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, gunit), key);
+            going_right = (rd.x >> 31) != 0;
+            u_main = u01(rd.y);
+            if (going_right) { io.ld(V_ZR, z); io.ld(V_RR, r); io.ld(V_GR, g); }
+            else { io.ld(V_ZL, z); io.ld(V_RL, r); io.ld(V_GL, g); }
+            eps_dir = going_right ? step : -step;
+            n_max = 1 << depth;
+            n_sub = 0;
+            s_turn = false; s_div = false;
+            w_sub = -INFINITY; s_acc = 0.f; sprop_pe = 0.0;
+        };
 
-    // Flat state machine: every pass through this loop does exactly one log p + gradient
-    // evaluation (the very first one initialises the chain, all others are leapfrog steps).
-    // mode 0: leapfrog steps.  mode 1: evaluate the initial point.  modes 2, 3: distance rescue (below).
-    int mode = 1;
-    int init_tries = 0, n_rescue = 0;
-    float rs_S1 = 0.f, rs_h1 = 0.f;
-    const int iD = M.n_eps + 3;             // element of the (shifted) distance
-    while (true) {
-        const bool first = mode != 0;
-        if (!first) {
-#pragma unroll
-            for (int s = 0; s < VPL; ++s) {
-                r[s] = fmaf(-0.5f * eps_dir, g[s], r[s]);
-                z[s] = fmaf(eps_dir * im[s], r[s], z[s]);
-            }
-        }
-        double lp;
-        eval_logp_grad<LP, TP, VPL, RVFREE, STAGE>(M, c, M.hs, z, lp, g, lane);
-        const double pe_new = -lp;
-#pragma unroll
-        for (int s = 0; s < VPL; ++s) g[s] = -g[s];
-        if (first) {
-            // numpyro rejects initial points with a non-finite potential or gradient and retries
-            // with init_to_uniform(radius=2) (infer/util.py find_valid_initial_params); same here.
-            bool ok = isfinite(pe_new);
-#pragma unroll
-            for (int s = 0; s < VPL; ++s) ok = ok && isfinite(g[s]);
-            ok = __all_sync(FULL, ok);
-            if (!ok && init_tries < 100) {
-                uint4 ra = philox4x32(make_uint4((uint32_t)init_tries, 0x20000000u, (uint32_t)lane, gunit), key);
-                float uu[4] = {u01(ra.x), u01(ra.y), u01(ra.z), u01(ra.w)};
-#pragma unroll
-                for (int s = 0; s < VPL; ++s) z[s] = own[s] ? (4.f * uu[s & 3] - 2.f) : 0.f;
-                ++init_tries;
-                continue;
-            }
-            if (mode == 2) {
-                // Second point of the rescue: log L is quadratic in the flux scale S = 10^(-0.4 dD), so
-                // h = (dU/d dD) / (kappa S) = a - b S at two distances gives the optimum S* = a / b.
-                const float dD2 = vget<VPL>(z, iD), S2 = exp2f(-C2 * dD2);
-                const float h2 = vget<VPL>(g, iD) / (KAPPA * S2);
-                const float b = (rs_h1 - h2) / (S2 - rs_S1), a = rs_h1 + b * rs_S1;
-                float dDs = -log2f(a / b) * (1.f / C2);
-                if (!(b > 0.f) || !(a > 0.f) || !isfinite(dDs)) dDs = 0.f;       // fall back to Ds = muhat
-#pragma unroll
-                for (int s = 0; s < VPL; ++s)
-                    if (lane + 32 * s == iD) z[s] = dDs;
-                mode = 3;
-                continue;
-            }
-            if (mode == 3) {
-                // restart step-size adaptation from the rescued point (the mass matrix is kept)
-                step = cfg.init_step;
-                da_x = 0.f; da_xavg = 0.f; da_gavg = 0.f; da_t = 0;
-                da_prox = logf(10.f * step);
-            }
-            mode = 0;
-            pe = pe_new;
-            begin_transition();
-            begin_doubling();
-            continue;
-        }
-        // ---- finish the leapfrog, account for the new leaf --------------------------------------
-#pragma unroll
-        for (int s = 0; s < VPL; ++s) r[s] = fmaf(-0.5f * eps_dir, g[s], r[s]);
-        {
-            const double E_new = pe_new + 0.5 * (double)vdot_im<VPL>(im, r, r);
-            float dE = (float)(E_new - E0);
-            if (!(dE == dE)) dE = INFINITY;
-            const float leaf_w = -dE;
-            s_div = dE > 1000.f;
-            s_acc += fminf(1.f, expf(-dE));
-            if (n_sub == 0) {
-#pragma unroll
-                for (int s = 0; s < VPL; ++s) rsum[s] = r[s];
-                w_sub = leaf_w;
-                io.st(V_SZP, z); io.st(V_SGP, g);
-                sprop_pe = pe_new;
-            } else {
-#pragma unroll
-                for (int s = 0; s < VPL; ++s) rsum[s] += r[s];
-                uint4 rl = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, gunit), key);
-                const float tp = 1.f / (1.f + expf(-(leaf_w - w_sub)));   // uniform transition kernel
-                if (u01(rl.x) < tp) {
-                    io.st(V_SZP, z); io.st(V_SGP, g);
-                    sprop_pe = pe_new;
-                }
-                w_sub = logaddexpf(w_sub, leaf_w);
-            }
-            const int leaf = n_sub;
-            ++n_sub;
-            // checkpoint indices (numpyro _leaf_idx_to_ckpt_idxs)
-            const int idx_max = __popc(leaf >> 1);
-            const int n_sub_trees = __ffs(~leaf) - 1;   // trailing ones
-            const int idx_min = idx_max - n_sub_trees + 1;
-            if ((leaf & 1) == 0) {
-                io.st(V_CKPT + 2 * idx_max, r);
-                io.st(V_CKPT + 2 * idx_max + 1, rsum);
-            }
-            for (int i = idx_max; i >= idx_min && !s_turn; --i) {
-                io.ld(V_CKPT + 2 * i, tmp);          // r_ckpt
-                io.ld(V_CKPT + 2 * i + 1, tmp2);     // r_sum_ckpt
-#pragma unroll
-                for (int s = 0; s < VPL; ++s) tmp2[s] = rsum[s] - tmp2[s] + tmp[s];
-                s_turn = is_turning<VPL>(im, tmp, r, tmp2);
-            }
-        }
-        if (n_sub < n_max && !s_turn && !s_div) continue;
-
-        // ---- subtree finished: merge into the trajectory (biased progressive sampling) ----------
-        total_steps += n_sub;
-        if (going_right) { io.st(V_ZR, z); io.st(V_RR, r); io.st(V_GR, g); }
-        else { io.st(V_ZL, z); io.st(V_RL, r); io.st(V_GL, g); }
-        io.ld(V_RSUM, tmp);
-#pragma unroll
-        for (int s = 0; s < VPL; ++s) tmp[s] += rsum[s];
-        io.st(V_RSUM, tmp);
-        {
-            const float tp = (s_turn || s_div) ? 0.f : fminf(1.f, expf(w_sub - w_main));
-            if (u_main < tp) {
-                io.ld(V_SZP, tmp2); io.st(V_ZP, tmp2);
-                io.ld(V_SGP, tmp2); io.st(V_GP, tmp2);
-                prop_pe = sprop_pe;
-            }
-        }
-        if (s_turn) turning = true;
-        else {
-            io.ld(V_RL, tmp2);
-            float rr_[VPL];
-            io.ld(V_RR, rr_);
-            turning = is_turning<VPL>(im, tmp2, rr_, tmp);
-        }
-        w_main = logaddexpf(w_main, w_sub);
-        diverging = s_div;
-        sum_acc += s_acc;
-        n_prop += n_sub;
-        ++depth;
-        if (depth < cfg.max_depth && !turning && !diverging) {
-            begin_doubling();
-            continue;
-        }
-
-        // ---- transition finished ---------------------------------------------------------------
-        const float accept = sum_acc / (float)max(n_prop, 1);
-        io.ld(V_ZP, z); io.ld(V_GP, g);
-        pe = prop_pe;
-        if (lane == 0) {
-            float* srow = stats + (unit * (size_t)n_iter + it) * 5;
-            srow[0] = accept;
-            srow[1] = (float)n_prop;
-            srow[2] = diverging ? 1.f : 0.f;
-            srow[3] = (float)pe;
-            srow[4] = step;     // step size this transition was run with
-        }
-        if (it < cfg.num_warmup) {
-            // warm-up adaptation (numpyro warmup_adapter.update_fn)
-            if (cfg.adapt_step) {
-                ++da_t;
-                const float gg = cfg.target_accept - accept;
-                da_gavg = (1.f - 1.f / (da_t + 10.f)) * da_gavg + gg / (da_t + 10.f);
-                da_x = da_prox - sqrtf((float)da_t) / 0.05f * da_gavg;
-                const float wt = powf((float)da_t, -0.75f);
-                da_xavg = (1.f - wt) * da_xavg + wt * da_x;
-                step = (it == cfg.num_warmup - 1) ? expf(da_xavg) : expf(da_x);
-                step = fmaxf(step, 1.17549435e-38f);
-            }
-            const bool middle = (window > 0) && (window < cfg.n_windows - 1);
-            if (cfg.adapt_mass && middle) {
-                ++wf_n;
-                io.ld(V_WMEAN, tmp); io.ld(V_WM2, tmp2);
+        // Flat state machine: every pass through this loop does exactly one log p + gradient
+        // evaluation (the very first one initialises the chain, all others are leapfrog steps).
+        // mode 0: leapfrog steps.  mode 1: evaluate the initial point.  modes 2, 3: distance rescue (below).
+        int mode = 1;
+        int init_tries = 0, n_rescue = 0;
+        float rs_S1 = 0.f, rs_h1 = 0.f;
+        const int iD = M.n_eps + 3;             // element of the (shifted) distance
+        while (true) {
+            const bool first = mode != 0;
+            if (!first) {
 #pragma unroll
                 for (int s = 0; s < VPL; ++s) {
-                    float dpre = z[s] - tmp[s];
-                    tmp[s] += dpre / (float)wf_n;
-                    tmp2[s] = fmaf(dpre, z[s] - tmp[s], tmp2[s]);
+                    r[s] = fmaf(-0.5f * eps_dir, g[s], r[s]);
+                    z[s] = fmaf(eps_dir * im[s], r[s], z[s]);
                 }
-                io.st(V_WMEAN, tmp); io.st(V_WM2, tmp2);
             }
-            const bool at_end = (it == cfg.win_end[window]);
-            if (at_end) ++window;
-            if (at_end && middle) {
-                if (cfg.adapt_mass) {
-                    io.ld(V_WM2, tmp2);
+            double lp;
+            eval_logp_grad<LP, TP, VPL, RVFREE, STAGE>(M, c, M.hs, z, lp, g, lane);
+            const double pe_new = -lp;
+#pragma unroll
+            for (int s = 0; s < VPL; ++s) g[s] = -g[s];
+            if (first) {
+                // numpyro rejects initial points with a non-finite potential or gradient and retries
+                // with init_to_uniform(radius=2) (infer/util.py find_valid_initial_params); same here.
+                bool ok = isfinite(pe_new);
+#pragma unroll
+                for (int s = 0; s < VPL; ++s) ok = ok && isfinite(g[s]);
+                ok = __all_sync(FULL, ok);
+                if (!ok && init_tries < 100) {
+                    uint4 ra = philox4x32(make_uint4((uint32_t)init_tries, 0x20000000u, (uint32_t)lane, gunit), key);
+                    float uu[4] = {u01(ra.x), u01(ra.y), u01(ra.z), u01(ra.w)};
+#pragma unroll
+                    for (int s = 0; s < VPL; ++s) z[s] = own[s] ? (4.f * uu[s & 3] - 2.f) : 0.f;
+                    ++init_tries;
+                    continue;
+                }
+                if (mode == 2) {
+                    // Second point of the rescue: log L is quadratic in the flux scale S = 10^(-0.4 dD), so
+                    // h = (dU/d dD) / (kappa S) = a - b S at two distances gives the optimum S* = a / b.
+                    const float dD2 = vget<VPL>(z, iD), S2 = exp2f(-C2 * dD2);
+                    const float h2 = vget<VPL>(g, iD) / (KAPPA * S2);
+                    const float b = (rs_h1 - h2) / (S2 - rs_S1), a = rs_h1 + b * rs_S1;
+                    float dDs = -log2f(a / b) * (1.f / C2);
+                    if (!(b > 0.f) || !(a > 0.f) || !isfinite(dDs)) dDs = 0.f;       // fall back to Ds = muhat
+#pragma unroll
+                    for (int s = 0; s < VPL; ++s)
+                        if (lane + 32 * s == iD) z[s] = dDs;
+                    mode = 3;
+                    continue;
+                }
+                if (mode == 3) {
+                    // restart step-size adaptation from the rescued point (the mass matrix is kept)
+                    step = cfg.init_step;
+                    da_x = 0.f; da_xavg = 0.f; da_gavg = 0.f; da_t = 0;
+                    da_prox = logf(10.f * step);
+                }
+                mode = 0;
+                pe = pe_new;
+                begin_transition();
+                begin_doubling();
+                continue;
+            }
+            // ---- finish the leapfrog, account for the new leaf --------------------------------------
+#pragma unroll
+            for (int s = 0; s < VPL; ++s) r[s] = fmaf(-0.5f * eps_dir, g[s], r[s]);
+            {
+                const double E_new = pe_new + 0.5 * (double)vdot_im<VPL>(im, r, r);
+                float dE = (float)(E_new - E0);
+                if (!(dE == dE)) dE = INFINITY;
+                const float leaf_w = -dE;
+                s_div = dE > 1000.f;
+                s_acc += fminf(1.f, expf(-dE));
+                if (n_sub == 0) {
+#pragma unroll
+                    for (int s = 0; s < VPL; ++s) rsum[s] = r[s];
+                    w_sub = leaf_w;
+                    io.st(V_SZP, z); io.st(V_SGP, g);
+                    sprop_pe = pe_new;
+                } else {
+#pragma unroll
+                    for (int s = 0; s < VPL; ++s) rsum[s] += r[s];
+                    uint4 rl = philox4x32(make_uint4((uint32_t)it, rk++, 0xffffffffu, gunit), key);
+                    const float tp = 1.f / (1.f + expf(-(leaf_w - w_sub)));   // uniform transition kernel
+                    if (u01(rl.x) < tp) {
+                        io.st(V_SZP, z); io.st(V_SGP, g);
+                        sprop_pe = pe_new;
+                    }
+                    w_sub = logaddexpf(w_sub, leaf_w);
+                }
+                const int leaf = n_sub;
+                ++n_sub;
+                // checkpoint indices (numpyro _leaf_idx_to_ckpt_idxs)
+                const int idx_max = __popc(leaf >> 1);
+                const int n_sub_trees = __ffs(~leaf) - 1;   // trailing ones
+                const int idx_min = idx_max - n_sub_trees + 1;
+                if ((leaf & 1) == 0) {
+                    io.st(V_CKPT + 2 * idx_max, r);
+                    io.st(V_CKPT + 2 * idx_max + 1, rsum);
+                }
+                for (int i = idx_max; i >= idx_min && !s_turn; --i) {
+                    io.ld(V_CKPT + 2 * i, tmp);          // r_ckpt
+                    io.ld(V_CKPT + 2 * i + 1, tmp2);     // r_sum_ckpt
+#pragma unroll
+                    for (int s = 0; s < VPL; ++s) tmp2[s] = rsum[s] - tmp2[s] + tmp[s];
+                    s_turn = is_turning<VPL>(im, tmp, r, tmp2);
+                }
+            }
+            if (n_sub < n_max && !s_turn && !s_div) continue;
+
+            // ---- subtree finished: merge into the trajectory (biased progressive sampling) ----------
+            total_steps += n_sub;
+            if (going_right) { io.st(V_ZR, z); io.st(V_RR, r); io.st(V_GR, g); }
+            else { io.st(V_ZL, z); io.st(V_RL, r); io.st(V_GL, g); }
+            io.ld(V_RSUM, tmp);
+#pragma unroll
+            for (int s = 0; s < VPL; ++s) tmp[s] += rsum[s];
+            io.st(V_RSUM, tmp);
+            {
+                const float tp = (s_turn || s_div) ? 0.f : fminf(1.f, expf(w_sub - w_main));
+                if (u_main < tp) {
+                    io.ld(V_SZP, tmp2); io.st(V_ZP, tmp2);
+                    io.ld(V_SGP, tmp2); io.st(V_GP, tmp2);
+                    prop_pe = sprop_pe;
+                }
+            }
+            if (s_turn) turning = true;
+            else {
+                io.ld(V_RL, tmp2);
+                float rr_[VPL];
+                io.ld(V_RR, rr_);
+                turning = is_turning<VPL>(im, tmp2, rr_, tmp);
+            }
+            w_main = logaddexpf(w_main, w_sub);
+            diverging = s_div;
+            sum_acc += s_acc;
+            n_prop += n_sub;
+            ++depth;
+            if (depth < cfg.max_depth && !turning && !diverging) {
+                begin_doubling();
+                continue;
+            }
+
+            // ---- transition finished ---------------------------------------------------------------
+            const float accept = sum_acc / (float)max(n_prop, 1);
+            io.ld(V_ZP, z); io.ld(V_GP, g);
+            pe = prop_pe;
+            if (lane == 0) {
+                float* srow = stats + (unit * (size_t)n_iter + it) * 5;
+                srow[0] = accept;
+                srow[1] = (float)n_prop;
+                srow[2] = diverging ? 1.f : 0.f;
+                srow[3] = (float)pe;
+                srow[4] = step;     // step size this transition was run with
+            }
+            if (it < cfg.num_warmup) {
+                // warm-up adaptation (numpyro warmup_adapter.update_fn)
+                if (cfg.adapt_step) {
+                    ++da_t;
+                    const float gg = cfg.target_accept - accept;
+                    da_gavg = (1.f - 1.f / (da_t + 10.f)) * da_gavg + gg / (da_t + 10.f);
+                    da_x = da_prox - sqrtf((float)da_t) / 0.05f * da_gavg;
+                    const float wt = powf((float)da_t, -0.75f);
+                    da_xavg = (1.f - wt) * da_xavg + wt * da_x;
+                    step = (it == cfg.num_warmup - 1) ? expf(da_xavg) : expf(da_x);
+                    step = fmaxf(step, 1.17549435e-38f);
+                }
+                const bool middle = (window > 0) && (window < cfg.n_windows - 1);
+                if (cfg.adapt_mass && middle) {
+                    ++wf_n;
+                    io.ld(V_WMEAN, tmp); io.ld(V_WM2, tmp2);
 #pragma unroll
                     for (int s = 0; s < VPL; ++s) {
-                        float cov = tmp2[s] / (float)(wf_n - 1);
-                        if (cfg.regularize) cov = (wf_n / (wf_n + 5.f)) * cov + 1e-3f * (5.f / (wf_n + 5.f));
-                        im[s] = own[s] ? cov : 0.f;
-                        tmp[s] = 0.f;
+                        float dpre = z[s] - tmp[s];
+                        tmp[s] += dpre / (float)wf_n;
+                        tmp2[s] = fmaf(dpre, z[s] - tmp[s], tmp2[s]);
                     }
-                    io.st(V_WMEAN, tmp); io.st(V_WM2, tmp);
-                    wf_n = 0;
+                    io.st(V_WMEAN, tmp); io.st(V_WM2, tmp2);
                 }
-                if (cfg.adapt_step) {
-                    da_prox = logf(10.f * step);
-                    da_x = 0.f; da_xavg = 0.f; da_gavg = 0.f; da_t = 0;
+                const bool at_end = (it == cfg.win_end[window]);
+                if (at_end) ++window;
+                if (at_end && middle) {
+                    if (cfg.adapt_mass) {
+                        io.ld(V_WM2, tmp2);
+#pragma unroll
+                        for (int s = 0; s < VPL; ++s) {
+                            float cov = tmp2[s] / (float)(wf_n - 1);
+                            if (cfg.regularize) cov = (wf_n / (wf_n + 5.f)) * cov + 1e-3f * (5.f / (wf_n + 5.f));
+                            im[s] = own[s] ? cov : 0.f;
+                            tmp[s] = 0.f;
+                        }
+                        io.st(V_WMEAN, tmp); io.st(V_WM2, tmp);
+                        wf_n = 0;
+                    }
+                    if (cfg.adapt_step) {
+                        da_prox = logf(10.f * step);
+                        da_x = 0.f; da_xavg = 0.f; da_gavg = 0.f; da_t = 0;
+                    }
                 }
+            } else {
+                const int k = it - cfg.num_warmup;
+                const size_t row = unit * cfg.num_samples + k;
+#pragma unroll
+                for (int s = 0; s < VPL; ++s)
+                    if (own[s]) samples[row * D + lane + 32 * s] = z[s] + ((lane + 32 * s == M.n_eps + 3) ? c.muhat : 0.f);
+                mean_acc += (accept - mean_acc) / (float)(k + 1);
+                n_div += diverging ? 1 : 0;
             }
-        } else {
-            const int k = it - cfg.num_warmup;
-            const size_t row = unit * cfg.num_samples + k;
+            if (++it >= n_iter) break;
+            // FP32 safeguard (not in numpyro, which runs in float64): a chain whose initial distance is ~2 mag
+            // off starts at log p ~ -2e6, where the rounding noise of a float32 log L (relative 1e-7..1e-6) is
+            // an energy noise of order 1 per leapfrog; no step size reaches the target acceptance, dual
+            // averaging drives the step to ~1e-8, the position stops changing and every transition runs the
+            // full 2^max_depth - 1 leapfrogs (1 chain in 9 472 of the C5 share: 498 k leapfrogs, a third of the
+            // kernel time).  Healthy chains never go below ~1e-3 during warm-up.  Rescue: solve the distance
+            // coordinate in closed form (two evaluations), restart the step-size adaptation, carry on.
+            if (it < cfg.num_warmup && cfg.adapt_step && step < 1e-6f && n_rescue < 3) {
+                ++n_rescue;
+                const float dD1 = vget<VPL>(z, iD);
+                rs_S1 = exp2f(-C2 * dD1);
+                rs_h1 = vget<VPL>(g, iD) / (KAPPA * rs_S1);
 #pragma unroll
-            for (int s = 0; s < VPL; ++s)
-                if (own[s]) samples[row * D + lane + 32 * s] = z[s] + ((lane + 32 * s == M.n_eps + 3) ? c.muhat : 0.f);
-            mean_acc += (accept - mean_acc) / (float)(k + 1);
-            n_div += diverging ? 1 : 0;
+                for (int s = 0; s < VPL; ++s)
+                    if (lane + 32 * s == iD) z[s] = dD1 + 0.5f;
+                mode = 2;
+                continue;
+            }
+            begin_transition();
+            begin_doubling();
         }
-        if (++it >= n_iter) break;
-        // FP32 safeguard (not in numpyro, which runs in float64): a chain whose initial distance is ~2 mag
-        // off starts at log p ~ -2e6, where the rounding noise of a float32 log L (relative 1e-7..1e-6) is
-        // an energy noise of order 1 per leapfrog; no step size reaches the target acceptance, dual
-        // averaging drives the step to ~1e-8, the position stops changing and every transition runs the
-        // full 2^max_depth - 1 leapfrogs (1 chain in 9 472 of the C5 share: 498 k leapfrogs, a third of the
-        // kernel time).  Healthy chains never go below ~1e-3 during warm-up.  Rescue: solve the distance
-        // coordinate in closed form (two evaluations), restart the step-size adaptation, carry on.
-        if (it < cfg.num_warmup && cfg.adapt_step && step < 1e-6f && n_rescue < 3) {
-            ++n_rescue;
-            const float dD1 = vget<VPL>(z, iD);
-            rs_S1 = exp2f(-C2 * dD1);
-            rs_h1 = vget<VPL>(g, iD) / (KAPPA * rs_S1);
-#pragma unroll
-            for (int s = 0; s < VPL; ++s)
-                if (lane + 32 * s == iD) z[s] = dD1 + 0.5f;
-            mode = 2;
-            continue;
+        float* ci = chain_info + unit * (4 + D);
+        if (lane == 0) {
+            ci[0] = step;
+            ci[1] = mean_acc;
+            ci[2] = (float)total_steps;
+            ci[3] = (float)n_div;
         }
-        begin_transition();
-        begin_doubling();
-    }
-    float* ci = chain_info + unit * (4 + D);
-    if (lane == 0) {
-        ci[0] = step;
-        ci[1] = mean_acc;
-        ci[2] = (float)total_steps;
-        ci[3] = (float)n_div;
-    }
 #pragma unroll
-    for (int s = 0; s < VPL; ++s)
-        if (own[s]) ci[4 + lane + 32 * s] = im[s];
-  }
+        for (int s = 0; s < VPL; ++s)
+            if (own[s]) ci[4 + lane + 32 * s] = im[s];
+    }
 }
 
 
