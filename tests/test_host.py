@@ -30,6 +30,43 @@ def test_library_is_sm100a_with_tma_and_no_tensor_fallback(built_library):
     assert 'sm_100a' in out
 
 
+def _sass_loops(path, mangled_substr):
+    """(start, end, [instructions]) of every backward-branch loop of the first kernel whose mangled name
+    contains ``mangled_substr``."""
+    names = subprocess.run(['cuobjdump', '-sass', path], capture_output=True, text=True).stdout
+    fn = [m for m in re.findall(r'Function : (\S+)', names) if mangled_substr in m][0]
+    txt = subprocess.run(['cuobjdump', '-sass', '-fun', fn, path], capture_output=True, text=True).stdout
+    ins = [(int(m.group(1), 16), m.group(2).strip()) for m in re.finditer(r'/\*([0-9a-f]{4,5})\*/\s+([^;]+);', txt)]
+    loops = []
+    for a, t in ins:
+        m = re.search(r'BRA\S*\s+(?:\S+,\s*)?0x([0-9a-f]+)', t)
+        if m and int(m.group(1), 16) < a:
+            tgt = int(m.group(1), 16)
+            loops.append((tgt, a, [x for addr, x in ins if tgt <= addr <= a]))
+    return loops
+
+
+def test_band_pass_loop_of_the_sampler_kernel_is_spill_free_and_vectorised(built_library):
+    """Performance guard on the SASS of nuts_kernel<11,6,2,0,1> (W22 fits, the bench kernel): the innermost
+    loop that holds the exp2 of the band-pass integral reads the J_l row with LDS.128, does the two knot
+    contractions (>= 22 FFMA per round), and neither it nor the pair loop around it touches local memory
+    (the kernel's few spills belong to the sampler's bookkeeping)."""
+    from bayesn_b200 import native
+    loops = _sass_loops(native.LIB_PATH, 'nuts_kernelILi11ELi6ELi2ELb0ELb1')
+    ex2 = sorted((len(b), b) for _, _, b in loops if any('MUFU.EX2' in x for x in b))
+    assert len(ex2) >= 2
+    inner, pair = ex2[0][1], ex2[1][1]
+    rounds = sum('MUFU.EX2' in x for x in inner)
+    assert rounds >= 1 and len(inner) <= 60 * rounds, (rounds, len(inner))
+    assert sum(x.startswith('LDS.128') or ' LDS.128' in x for x in inner) >= 3 * rounds
+    assert sum('FFMA' in x for x in inner) >= 22 * rounds
+    for body in (inner, pair):
+        assert not any(('LDL' in x) or ('STL' in x) for x in body)
+    # the L_Sigma column walks use immediate-offset loads (compile-time row stride)
+    txt = ' '.join(x for _, _, b in loops for x in b)
+    assert re.search(r'LDG\.E\.CONSTANT \S+, desc\[\S+\]\[\S+\+0x[0-9a-f]+\]', txt)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
 def test_product_path_fails_loudly_without_gpu():
     from bayesn_b200 import native
