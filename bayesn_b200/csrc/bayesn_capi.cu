@@ -120,38 +120,50 @@ int train_prepare(bayesn_ctx* ctx, int C) {
 struct Combo { int LP, TP, VPL; };
 const Combo kCombos[] = {{6, 6, 1}, {9, 6, 2}, {11, 6, 2}, {10, 9, 3}, {12, 10, 4}};
 
-// capacity (number of distinct SNe) of a CTA of WPB consecutive (SN, chain) units
-int ntile_for(int C) { return (C % WPB == 0) ? 1 : ((WPB % C == 0) ? WPB / C : (WPB + C - 1) / C + 1); }
+// capacity (number of distinct SNe) of a CTA of upc consecutive (SN, chain) units (upc = WPB / warps per unit)
+int ntile_for(int C, int upc = WPB) { return (C % upc == 0) ? 1 : ((upc % C == 0) ? upc / C : (upc + C - 1) / C + 1); }
+
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// the model descriptor of one launch in latency mode: kw warps per (SN, chain) unit, where the teammates'
+// exchange slots are (bayesn_device.cuh: ModelDev::kw)
+ModelDev team_model(const ModelDev& M0, int kw, const SmemPlan& P) {
+    ModelDev M = M0;
+    M.kw = kw; M.kwl = ilog2(kw); M.xstride = P.warpStride; M.xoff = P.wX - P.wSc;
+    return M;
+}
 
 template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
-int launch_logp(bayesn_ctx* ctx, int C, const float* q, float* logp, float* grad, cudaStream_t st) {
-    const int ntile = ntile_for(C);
-    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE);
+int launch_logp(bayesn_ctx* ctx, int C, int kw, const float* q, float* logp, float* grad, cudaStream_t st) {
+    const int upc = WPB / kw;
+    const int ntile = ntile_for(C, upc);
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE, false, kw);
     const size_t bytes = (size_t)P.totalFloats * 4;
     auto kern = logp_grad_kernel<LP, TP, VPL, RVFREE, STAGE>;
     if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
     CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     const long long units = (long long)ctx->D.N * C;
-    const unsigned grid = (unsigned)((units + WPB - 1) / WPB);
-    kern<<<grid, WPB * 32, bytes, st>>>(ctx->M, ctx->D, C, ntile, q, logp, grad);
+    const unsigned grid = (unsigned)((units + upc - 1) / upc);
+    kern<<<grid, WPB * 32, bytes, st>>>(team_model(ctx->M, kw, P), ctx->D, C, ntile, q, logp, grad);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
 }
 
 template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
-int launch_nuts(bayesn_ctx* ctx, const NutsDev& cfg, unsigned long long* queue_slot, const float* q0, float* samples,
+int launch_nuts(bayesn_ctx* ctx, const NutsDev& cfg, int kw, unsigned long long* queue_slot, const float* q0, float* samples,
                 float* stats, float* info, float* work, cudaStream_t st) {
     const bool use_queue = queue_slot != nullptr;
     const int C = cfg.num_chains;
-    const int ntile = use_queue ? WPB : ntile_for(C);      // queue: one slot of SN data per warp
-    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE);
+    const int upc = WPB / kw;
+    const int ntile = use_queue ? upc : ntile_for(C, upc);      // queue: one slot of SN data per team
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE, false, kw);
     const size_t bytes = (size_t)P.totalFloats * 4;
     auto kern = nuts_kernel<LP, TP, VPL, RVFREE, STAGE>;
     if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
     CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     const long long units = (long long)ctx->D.N * C;
-    unsigned grid = (unsigned)((units + WPB - 1) / WPB);
+    unsigned grid = (unsigned)((units + upc - 1) / upc);
     unsigned long long* queue = nullptr;
     if (use_queue) {
         int occ = 0, sms = 0;
@@ -162,7 +174,7 @@ int launch_nuts(bayesn_ctx* ctx, const NutsDev& cfg, unsigned long long* queue_s
         queue = queue_slot;
         grid = (unsigned)std::min<long long>(grid, (long long)occ * sms);      // one resident wave
     }
-    kern<<<grid, WPB * 32, bytes, st>>>(ctx->M, ctx->D, cfg, ntile, q0, samples, stats, info, work, queue);
+    kern<<<grid, WPB * 32, bytes, st>>>(team_model(ctx->M, kw, P), ctx->D, cfg, ntile, q0, samples, stats, info, work, queue);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -174,26 +186,27 @@ int launch_nuts(bayesn_ctx* ctx, const NutsDev& cfg, unsigned long long* queue_s
 // (C5: 60 observations, 4.9 KB tiles) the static schedule stays: reading the tiles through L1 instead
 // was measured slower than the imbalance it removes (87 vs 93 SNe/s, profiles/README.md).
 // BAYESN_NUTS_SCHED=static|queue|queue-l1 overrides (measurements, tests).
-void choose_nuts_schedule(bayesn_ctx* ctx, int C, bool* use_queue, bool* stage) {
+void choose_nuts_schedule(bayesn_ctx* ctx, int C, int kw, bool* use_queue, bool* stage) {
     const bool rvfree = ctx->M.rv_mode != BAYESN_RV_FIXED;
+    const int upc = WPB / kw;
     auto occ = [&](int ntile, bool st) {
-        const SmemPlan P = make_plan(ctx->LP, ctx->TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, rvfree, st);
+        const SmemPlan P = make_plan(ctx->LP, ctx->TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, rvfree, st, false, kw);
         const long long bytes = (long long)P.totalFloats * 4;
         if (bytes > 227 * 1024) return 0;
         return (int)std::min<long long>(16 / WPB, (228LL * 1024) / (bytes + 1024));    // 128 registers x 16 warps fill the SM
     };
     const bool stage_static = C >= 2;       // one chain per SN: nothing to share, the tile is read through L1
-    const int occ_static = std::max(occ(ntile_for(C), stage_static), 1);
+    const int occ_static = std::max(occ(ntile_for(C, upc), stage_static), 1);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const long long ctas = ((long long)ctx->D.N * C + WPB - 1) / WPB;
+    const long long ctas = ((long long)ctx->D.N * C + upc - 1) / upc;
     *use_queue = false;
     *stage = stage_static;
     const char* e = getenv("BAYESN_NUTS_SCHED");
     if (e && !strcmp(e, "static")) return;
-    if (e && !strcmp(e, "queue-l1")) { *use_queue = occ(WPB, false) > 0; if (*use_queue) *stage = false; return; }
-    if (e && !strcmp(e, "queue")) { *use_queue = occ(WPB, stage_static) > 0; return; }
-    *use_queue = ctas > (long long)occ_static * sms && occ(WPB, stage_static) >= occ_static;
+    if (e && !strcmp(e, "queue-l1")) { *use_queue = occ(upc, false) > 0; if (*use_queue) *stage = false; return; }
+    if (e && !strcmp(e, "queue")) { *use_queue = occ(upc, stage_static) > 0; return; }
+    *use_queue = ctas > (long long)occ_static * sms && occ(upc, stage_static) >= occ_static;
 }
 
 // compile-time dispatch over the supported (knots, parameter-vector) shapes
@@ -282,16 +295,24 @@ struct TrainNutsSnCall {
 };
 
 struct LogpCall {
-    bayesn_ctx* ctx; int C; const float* q; float* logp; float* grad; cudaStream_t st;
+    bayesn_ctx* ctx; int C; int kw; const float* q; float* logp; float* grad; cudaStream_t st;
     template <int LP, int TP, int VPL, bool RV, bool ST>
-    int operator()() { return launch_logp<LP, TP, VPL, RV, ST>(ctx, C, q, logp, grad, st); }
+    int operator()() { return launch_logp<LP, TP, VPL, RV, ST>(ctx, C, kw, q, logp, grad, st); }
 };
 struct NutsCall {
-    bayesn_ctx* ctx; NutsDev cfg; unsigned long long* queue_slot; const float* q0; float* samples; float* stats; float* info; float* work;
+    bayesn_ctx* ctx; NutsDev cfg; int kw; unsigned long long* queue_slot; const float* q0; float* samples; float* stats; float* info; float* work;
     cudaStream_t st;
     template <int LP, int TP, int VPL, bool RV, bool ST>
-    int operator()() { return launch_nuts<LP, TP, VPL, RV, ST>(ctx, cfg, queue_slot, q0, samples, stats, info, work, st); }
+    int operator()() { return launch_nuts<LP, TP, VPL, RV, ST>(ctx, cfg, kw, queue_slot, q0, samples, stats, info, work, st); }
 };
+
+// warps per (SN, chain) unit: 0 / 1 = throughput layout, else a power of two that divides the CTA
+int team_width(bayesn_ctx* ctx, int w, int* kw) {
+    if (w <= 1) { *kw = 1; return 0; }
+    if ((w & (w - 1)) || w > WPB) return fail(ctx, -1, "warps_per_chain must be 1, 2, 4 or 8");
+    *kw = w;
+    return 0;
+}
 
 // numpyro.infer.hmc_util.build_adaptation_schedule (Stan windows)
 std::vector<int> adaptation_window_ends(int num_steps) {
@@ -322,7 +343,7 @@ std::vector<int> adaptation_window_ends(int num_steps) {
 
 extern "C" {
 
-int bayesn_abi_version(void) { return 1; }
+int bayesn_abi_version(void) { return 2; }
 
 int bayesn_ctx_create(int device, bayesn_ctx** out) {
     if (!out) return -1;
@@ -393,6 +414,7 @@ int bayesn_set_model(bayesn_ctx* ctx, const bayesn_model_desc* m) {
         }
     ModelDev& M = ctx->M;
     M = ModelDev{};
+    M.kw = 1; M.kwl = 0; M.xstride = 0; M.xoff = 0;
     M.L = L; M.T = T; M.n_eps = ne; M.D = D; M.n_sc = n_sc; M.rv_mode = m->rv_mode;
     M.ls_lower = lower ? 1 : 0;
     M.fix_tmax = m->fix_tmax; M.fix_theta = m->fix_theta; M.fix_AV = m->fix_AV;
@@ -431,17 +453,26 @@ int bayesn_bind_dataset(bayesn_ctx* ctx, const bayesn_dataset_desc* d) {
     return 0;
 }
 
-int bayesn_logp_grad_fit(bayesn_ctx* ctx, int n_chains, const float* q, float* logp, float* grad, void* stream) {
+int bayesn_logp_grad_fit_team(bayesn_ctx* ctx, int n_chains, int warps_per_chain, const float* q, float* logp,
+                              float* grad, void* stream) {
     if (!ctx) return -1;
     if (!ctx->have_model || !ctx->have_data) return fail(ctx, -1, "set_model and bind_dataset first");
     if (n_chains < 1) return fail(ctx, -1, "n_chains must be >= 1");
+    int kw = 1;
+    if (int rc = team_width(ctx, warps_per_chain, &kw)) return rc;
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
-    LogpCall call{ctx, n_chains, q, logp, grad, (cudaStream_t)stream};
+    LogpCall call{ctx, n_chains, kw, q, logp, grad, (cudaStream_t)stream};
     return dispatch(ctx, /*stage=*/n_chains >= 2, call);
 }
 
+int bayesn_logp_grad_fit(bayesn_ctx* ctx, int n_chains, const float* q, float* logp, float* grad, void* stream) {
+    return bayesn_logp_grad_fit_team(ctx, n_chains, 1, q, logp, grad, stream);
+}
+
 static size_t nuts_vector_bytes(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg) {
-    const size_t b = (size_t)ctx->D.N * cfg->num_chains * nuts_num_vectors(cfg->max_tree_depth) * 32 * ctx->VPL * sizeof(float);
+    // every warp of a team keeps its own copy of the tree vectors (latency mode)
+    const size_t kw = cfg->warps_per_chain > 1 ? (size_t)cfg->warps_per_chain : 1;
+    const size_t b = (size_t)ctx->D.N * cfg->num_chains * kw * nuts_num_vectors(cfg->max_tree_depth) * 32 * ctx->VPL * sizeof(float);
     return (b + 255) & ~(size_t)255;
 }
 
@@ -459,6 +490,8 @@ int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_
     if (cfg->num_chains < 1 || cfg->num_samples < 1 || cfg->num_warmup < 0 || cfg->max_tree_depth < 1 ||
         cfg->max_tree_depth > 12)
         return fail(ctx, -1, "bad NUTS configuration");
+    int kw = 1;
+    if (int rc = team_width(ctx, cfg->warps_per_chain, &kw)) return rc;
     if (work_bytes < bayesn_nuts_workspace_bytes(ctx, cfg)) return fail(ctx, -1, "workspace too small");
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
     NutsDev nd{};
@@ -473,10 +506,10 @@ int bayesn_nuts_fit(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, const float* q_
     nd.n_windows = (int)ends.size();
     for (size_t i = 0; i < 24; ++i) nd.win_end[i] = i < ends.size() ? ends[i] : 0x7fffffff;
     bool use_queue = false, stage = false;
-    choose_nuts_schedule(ctx, cfg->num_chains, &use_queue, &stage);
+    choose_nuts_schedule(ctx, cfg->num_chains, kw, &use_queue, &stage);
     unsigned long long* queue_slot =
         use_queue ? reinterpret_cast<unsigned long long*>(static_cast<char*>(work) + nuts_vector_bytes(ctx, cfg)) : nullptr;
-    NutsCall call{ctx, nd, queue_slot, q_init, samples, stats, chain_info, (float*)work, (cudaStream_t)stream};
+    NutsCall call{ctx, nd, kw, queue_slot, q_init, samples, stats, chain_info, (float*)work, (cudaStream_t)stream};
     return dispatch(ctx, stage, call);
 }
 
@@ -546,7 +579,7 @@ int bayesn_flux_batch(bayesn_ctx* ctx, int N, int N_obs, int n_b, int mag, float
     A.band = band_indices; A.mask = mask; A.J_t = J_t; A.hsi = hsiao_interp; A.weights = weights;
     A.bscale = dbs; A.Jl = ctx->M.Jl; A.hs = ctx->M.hs; A.Mf = ctx->M.Mf; A.LPs = jl_row_stride(ctx->LP); A.out = out;
     const long long items = (long long)N * N_obs;
-    flux_kernel<<<(unsigned)((items + 3) / 4), 128, 0, st>>>(A);
+    flux_kernel<false><<<(unsigned)((items + 3) / 4), 128, 0, st>>>(A);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     CU_CHECK(ctx, cudaFreeAsync(dbs, st));
@@ -566,7 +599,37 @@ int bayesn_spectra_batch(bayesn_ctx* ctx, int N, int N_obs, const float* theta, 
     A.theta = theta; A.AV = AV; A.W0 = W0; A.W1 = W1; A.eps = eps; A.RV = RV; A.J_t = J_t; A.hsi = hsiao_interp;
     A.Jl = ctx->M.Jl; A.hs = ctx->M.hs; A.Mf = ctx->M.Mf; A.LPs = jl_row_stride(ctx->LP); A.out = out;
     const long long items = (long long)N * N_obs;
-    spectra_kernel<<<(unsigned)((items + 3) / 4), 128, 0, (cudaStream_t)stream>>>(A);
+    flux_kernel<true><<<(unsigned)((items + 3) / 4), 128, 0, (cudaStream_t)stream>>>(A);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+int bayesn_chain_flux(bayesn_ctx* ctx, int N, int S, int n_t, int max_bands, int n_b, int mag, int rv_per_draw,
+                      const float* t, const float* theta, const float* AV, const float* tmax, const float* dD,
+                      const float* RV, const float* eps, const int32_t* bands, const float* weights,
+                      const int32_t* support, int wt_stride, float* out, void* stream) {
+    if (!ctx) return -1;
+    if (!ctx->have_model) return fail(ctx, -1, "set_model first");
+    if (N <= 0 || S <= 0 || n_t <= 0 || max_bands <= 0) return 0;
+    if (rv_per_draw && !RV) return fail(ctx, -1, "rv_per_draw needs RV");
+    if (wt_stride <= 0 || (wt_stride % 4) || ((uintptr_t)support & 15))
+        return fail(ctx, -1, "support must be 16-byte aligned and wt_stride a positive multiple of 4");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    ChainFluxArgs A{};
+    A.N = N; A.S = S; A.n_t = n_t; A.max_bands = max_bands; A.n_b = n_b; A.L = ctx->M.L; A.T = ctx->M.T;
+    A.n_eps = ctx->M.n_eps; A.LP = ctx->LP; A.TP = ctx->TP; A.RS = jl_row_stride(ctx->LP); A.mag = mag; A.rvfree = rv_per_draw;
+    A.t = t; A.theta = theta; A.AV = AV; A.tmax = tmax; A.dD = dD; A.RV = RV; A.eps = eps; A.bands = bands;
+    A.wt = weights; A.sup = reinterpret_cast<const int4*>(support); A.wt_stride = wt_stride;
+    A.Jl = ctx->M.Jl; A.hs = ctx->M.hs; A.Mf = ctx->M.Mf; A.ad = ctx->M.ad; A.W0 = ctx->M.W0; A.W1 = ctx->M.W1;
+    A.KD = ctx->M.KD; A.tau = ctx->M.tau; A.out = out;
+    const long long items = (long long)N * S * n_t;
+    const unsigned grid = (unsigned)((items + 3) / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->TP == 6) chain_flux_kernel<6><<<grid, 128, 0, st>>>(A);
+    else if (ctx->TP == 9) chain_flux_kernel<9><<<grid, 128, 0, st>>>(A);
+    else if (ctx->TP == 10) chain_flux_kernel<10><<<grid, 128, 0, st>>>(A);
+    else return fail(ctx, -4, "no kernel instantiation for this model shape");
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -669,6 +732,7 @@ int bayesn_train_nuts_init(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, int sn_o
 int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream) {
     if (!ctx) return -1;
     if (!ctx->have_tn) return fail(ctx, -1, "bayesn_train_nuts_init first");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     TrainNutsSnCall call{ctx, st};
     if (int rc = dispatch(ctx, /*stage=*/ctx->T.C >= 2, call)) return rc;
@@ -681,6 +745,7 @@ int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream) {
 int bayesn_train_nuts_ctl(bayesn_ctx* ctx, double* red, void* stream) {
     if (!ctx) return -1;
     if (!ctx->have_tn) return fail(ctx, -1, "bayesn_train_nuts_init first");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
     const size_t csm = (size_t)ctx->T.R * sizeof(double) +
                        ((size_t)ctx->M.n_eps * ctx->M.n_eps + ctx->T.G) * sizeof(float);
     CU_CHECK(ctx, cudaFuncSetAttribute(train_nuts_ctl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
@@ -693,6 +758,7 @@ int bayesn_train_nuts_ctl(bayesn_ctx* ctx, double* red, void* stream) {
 int bayesn_train_nuts_status(bayesn_ctx* ctx, float* out, void* stream) {
     if (!ctx || !out) return -1;
     if (!ctx->have_tn) return fail(ctx, -1, "bayesn_train_nuts_init first");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
     const int C = ctx->T.C;
     std::vector<TrainCtl> h(C);
     CU_CHECK(ctx, cudaMemcpyAsync(h.data(), ctx->TN.ctl, C * sizeof(TrainCtl), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -767,6 +833,17 @@ int bayesn_train_set_exchange(bayesn_ctx* ctx, int world, int rank, const uint64
     ctx->X = X;
     return 0;
 }
+
+#ifdef BAYESN_PHASE_TIMING
+int bayesn_debug_phase(unsigned long long* out16, int reset) {
+    if (out16 && cudaMemcpyFromSymbol(out16, bayesn::g_phase, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[16] = {};
+        if (cudaMemcpyToSymbol(bayesn::g_phase, z, sizeof(z)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif
 
 #ifdef CTL_TIMING
 int bayesn_debug_ctl_times(long long* out) { return cudaMemcpyFromSymbol(out, bayesn::g_ctl_t, sizeof(long long) * 16) == cudaSuccess ? 0 : -1; }

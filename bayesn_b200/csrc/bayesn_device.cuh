@@ -33,6 +33,25 @@
 
 namespace bayesn {
 
+// -DBAYESN_PHASE_TIMING: clock64() deltas of the evaluator's phases, accumulated for warp 0 of CTA 0 (diagnostic
+// build, scripts/phase_timing.py): 0 scalars, 1 eps + W (+ dust basis), 2 per-observation setup, 3 pair loop,
+// 4 combine / team exchange, 5 reverse + priors, 6 sampler bookkeeping between evaluations, 7 evaluations.
+#ifdef BAYESN_PHASE_TIMING
+__device__ unsigned long long g_phase[16];
+#define BAYESN_PHASE_BEGIN long long _pt = clock64();
+#define BAYESN_PHASE(i)                                                          \
+    do {                                                                         \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                               \
+            const long long _t = clock64();                                      \
+            atomicAdd(&g_phase[i], (unsigned long long)(_t - _pt));              \
+            _pt = _t;                                                            \
+        }                                                                        \
+    } while (0)
+#else
+#define BAYESN_PHASE_BEGIN
+#define BAYESN_PHASE(i)
+#endif
+
 constexpr int NB = BAYESN_NBINS;
 constexpr int BP = BAYESN_BPAD;
 constexpr int NPH = BAYESN_NPHASE;
@@ -50,6 +69,12 @@ constexpr float LN2 = 0.6931471805599453f;
 constexpr unsigned FULL = 0xffffffffu;
 
 struct ModelDev {
+    // Latency mode: kw = 2^kwl consecutive warps of a CTA form a team that evaluates ONE (SN, chain) unit, each
+    // warp integrating the observation pairs p = rank (mod kw); set per launch by the host (kw = 1: one warp does
+    // everything, the throughput layout).  xstride / xoff locate the teammates' exchange slots relative to a
+    // warp's own scalar slot (floats); they live here - in the constant bank - so that the team logic costs the
+    // one-warp path no registers.
+    int kw, kwl, xstride, xoff;
     int L, T, n_eps, D, n_sc, rv_mode;
     int ls_lower;       // L_Sigma is exactly lower triangular (true for every shipped model): halve the mat-vecs
     int fix_tmax, fix_theta, fix_AV;
@@ -223,6 +248,11 @@ __device__ __forceinline__ float treduce16h(float (&v)[16], int lane) {
     return v[0];
 }
 
+// named barrier over the kw warps of a team (ids 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void team_sync(int team, int kw) {
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(kw * 32) : "memory");
+}
+
 // mbarrier + 1-D TMA bulk copy (global -> shared)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -264,6 +294,28 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }  // [0,1)
 
+// Fitzpatrick (1999) spline ordinates yk(R_V) - R_V at the nine knots xk (reference :604-623; the constant
+// "- R_V" of the optical/IR knots is folded in: 1.00270 R - R = 0.00270 R) and their R_V derivatives.
+// One definition for the fit evaluator (per-chain R_V), the forward kernels and the flux-from-chains kernel.
+__device__ __forceinline__ void f99_yk(float R, float (&yk)[9], float (&dyk)[9]) {
+    const float R2 = R * R, R3 = R2 * R;
+    const float c2f = -0.824f + 4.717f / R, c1f = 2.030f - 3.007f * c2f;
+    const float dc2 = -4.717f / R2, dc1 = -3.007f * dc2;
+    const float x7 = 1e4f / 2700.f, x8 = 1e4f / 2600.f, x0 = 4.596f, gm = 0.99f;
+    const float d1 = x7 * x7 / ((x7 * x7 - x0 * x0) * (x7 * x7 - x0 * x0) + gm * gm * x7 * x7);
+    const float d2 = x8 * x8 / ((x8 * x8 - x0 * x0) * (x8 * x8 - x0 * x0) + gm * gm * x8 * x8);
+    yk[0] = -R;                                   dyk[0] = -1.f;
+    yk[1] = 0.26469f * R / 3.1f - R;              dyk[1] = 0.26469f / 3.1f - 1.f;
+    yk[2] = 0.82925f * R / 3.1f - R;              dyk[2] = 0.82925f / 3.1f - 1.f;
+    yk[3] = -0.422809f + 0.00270f * R + 2.13572e-4f * R2;     dyk[3] = 0.00270f + 2.f * 2.13572e-4f * R;
+    yk[4] = -5.13540e-2f + 0.00216f * R - 7.35778e-5f * R2;   dyk[4] = 0.00216f - 2.f * 7.35778e-5f * R;
+    yk[5] = 0.700127f + 0.00184f * R - 3.32598e-5f * R2;      dyk[5] = 0.00184f - 2.f * 3.32598e-5f * R;
+    yk[6] = 1.19456f + 0.01707f * R - 5.46959e-3f * R2 + 7.97809e-4f * R3 - 4.45636e-5f * R2 * R2;
+    dyk[6] = 0.01707f - 2.f * 5.46959e-3f * R + 3.f * 7.97809e-4f * R2 - 4.f * 4.45636e-5f * R3;
+    yk[7] = c1f + c2f * x7 + 3.23f * d1;          dyk[7] = dc1 + dc2 * x7;
+    yk[8] = c1f + c2f * x8 + 3.23f * d2;          dyk[8] = dc1 + dc2 * x8;
+}
+
 // ------------------------------------------------------------------------------------------
 // shared-memory plan
 // ------------------------------------------------------------------------------------------
@@ -304,12 +356,15 @@ struct SmemPlan {
     int oJl, oAd, oMf, oW0, oW1, oKD, oTau, oWt, oSup, oObs, oBar;
     int oWarp, warpStride;     // per-warp region
     // inside the per-warp region
-    int wWs, wEv, wEps, wRec, wSc, wAd, wDad;
+    int wWs, wEv, wEps, wRec, wSc, wAd, wDad, wX;
     int totalFloats;
 };
 
+// floats one warp of a team publishes per evaluation: its dW rows + {log L (double), gDs, gAV, gT, gRV}
+__host__ __device__ constexpr int xchg_words(int LP, int TP) { return ((LP * TP + 6) + 3) & ~3; }
+
 __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b, int N_obs, int wt_stride, int ntile,
-                                              bool rvfree, bool stage, bool train = false) {
+                                              bool rvfree, bool stage, bool train = false, int kw = 1) {
     SmemPlan p;
     const int rec = rec_stride(LP, TP, train);
     int o = 0;
@@ -333,6 +388,7 @@ __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b
     p.wEps = wtake(n_eps);
     p.wRec = wtake((((N_obs + 1) & ~1) < OBS_CHUNK ? ((N_obs + 1) & ~1) : OBS_CHUNK) * rec);    // one chunk of observations (pairs)
     p.wSc = wtake(8);
+    p.wX = wtake(kw > 1 ? 2 * xchg_words(LP, TP) : 0);      // double-buffered exchange slot (latency mode)
     p.wAd = wtake(rvfree ? JROWS : 0);
     p.wDad = wtake(rvfree ? JROWS : 0);
     p.warpStride = w;
@@ -449,6 +505,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     static_assert(!(RVFREE && TRAIN), "training samples one global R_V");
     const int L = M.L, T = M.T, ne = M.n_eps;
     const int lss = TRAIN ? ne : ls_row_stride(LP, TP);     // row stride of c.Ls / c.LsT
+    BAYESN_PHASE_BEGIN
 
     // ---- scalars ------------------------------------------------------------------------
     const float theta_s = vget<VPL>(q, ne + 0);
@@ -482,6 +539,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     const float AVc = -C2 * AV;
     const float S = exp2f(-C2 * dD);
 
+    BAYESN_PHASE(0);
     // ---- eps = L_Sigma eps_tform, W = W0 + theta W1 + eps ---------------------------------
 #pragma unroll
     for (int s = 0; s < VPL; ++s) {
@@ -515,24 +573,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     if (RVFREE) {
         // per-chain dust basis a[b] = 1 + (M_fitz yk(RV))/RV and its RV derivative (reference :604-625)
         float yk[9], dyk[9];
-        {
-            const float R = RVv, R2 = R * R, R3 = R2 * R;
-            const float c2f = -0.824f + 4.717f / R, c1f = 2.030f - 3.007f * c2f;
-            const float dc2 = -4.717f / R2, dc1 = -3.007f * dc2;
-            const float x7 = 1e4f / 2700.f, x8 = 1e4f / 2600.f, x0 = 4.596f, gm = 0.99f;
-            const float d1 = x7 * x7 / ((x7 * x7 - x0 * x0) * (x7 * x7 - x0 * x0) + gm * gm * x7 * x7);
-            const float d2 = x8 * x8 / ((x8 * x8 - x0 * x0) * (x8 * x8 - x0 * x0) + gm * gm * x8 * x8);
-            yk[0] = -R;                                   dyk[0] = -1.f;
-            yk[1] = 0.26469f * R / 3.1f - R;              dyk[1] = 0.26469f / 3.1f - 1.f;
-            yk[2] = 0.82925f * R / 3.1f - R;              dyk[2] = 0.82925f / 3.1f - 1.f;
-            yk[3] = -0.422809f + 0.00270f * R + 2.13572e-4f * R2;     dyk[3] = 0.00270f + 2.f * 2.13572e-4f * R;
-            yk[4] = -5.13540e-2f + 0.00216f * R - 7.35778e-5f * R2;   dyk[4] = 0.00216f - 2.f * 7.35778e-5f * R;
-            yk[5] = 0.700127f + 0.00184f * R - 3.32598e-5f * R2;      dyk[5] = 0.00184f - 2.f * 3.32598e-5f * R;
-            yk[6] = 1.19456f + 0.01707f * R - 5.46959e-3f * R2 + 7.97809e-4f * R3 - 4.45636e-5f * R2 * R2;
-            dyk[6] = 0.01707f - 2.f * 5.46959e-3f * R + 3.f * 7.97809e-4f * R2 - 4.f * 4.45636e-5f * R3;
-            yk[7] = c1f + c2f * x7 + 3.23f * d1;          dyk[7] = dc1 + dc2 * x7;
-            yk[8] = c1f + c2f * x8 + 3.23f * d2;          dyk[8] = dc1 + dc2 * x8;
-        }
+        f99_yk(RVv, yk, dyk);
         const float iR = 1.f / RVv;
         for (int b = lane; b < JROWS; b += 32) {
             float my = 0.f, dmy = 0.f;
@@ -554,7 +595,12 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     // ---- per-observation setup, lanes over observations -------------------------------------
     // Observations are processed in pairs (16 interleaved lanes each); an odd count is completed by a
     // dummy copy of the last observation with 1/sigma = 0, which contributes exactly nothing.
-    const int npair = (c.nobs + 1) >> 1;
+    // Latency mode (M.kw > 1): this warp is rank tk of a team of kw warps that all hold the same position; it
+    // integrates the pairs p = tk (mod kw) and the teams' partial sums are exchanged after the loop.  Pairs are
+    // sorted by band width, so the ranks get equal work.  kw = 1: nlp = npair and every index below is the identity.
+    const int tk = (threadIdx.x >> 5) & (M.kw - 1);
+    const int npair_all = (c.nobs + 1) >> 1;
+    const int npair = (npair_all + M.kw - 1 - tk) >> M.kwl;      // pairs of this warp
     if (lane == 0) c.sc[0] = S;
     // log L is accumulated in double: far from the mode |log L| reaches 1e6 while NUTS needs energy
     // differences to ~1e-2, which float32 partial sums cannot hold (ulp(7.5e5) = 0.06)
@@ -574,12 +620,14 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
 #pragma unroll
     for (int m = 0; m < TP; ++m) dWr[m] = 0.f;
     const bool qlane = hl >= 4 && hl < 4 + LP;
+    BAYESN_PHASE(1);
     for (int o0 = 0; o0 < 2 * npair; o0 += OBS_CHUNK) {
         const int o = o0 + lane;
         const unsigned act = __ballot_sync(FULL, o < 2 * npair);     // both lanes of a pair are in or out together
         if (o < 2 * npair) {
-            const bool dummy = o >= c.nobs;
-            const float4 ob = c.obs[dummy ? c.nobs - 1 : o];
+            const int go = ((((o >> 1) << M.kwl) + tk) << 1) | (o & 1);      // observation index in the light curve
+            const bool dummy = go >= c.nobs;
+            const float4 ob = c.obs[dummy ? c.nobs - 1 : go];
             float t = ob.x - tmax;
             float J[TP], dJ[TP];
             spline_row<TP>(t, T, c.sTau, c.sKD, J, dJ);
@@ -636,6 +684,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
                             dummy ? 0.f : ob.y, dummy ? 0.f : ob.z);
         }
         __syncwarp();
+        BAYESN_PHASE(2);
 
         // ---- band-pass integrals: two observations per pass, 16 lanes over wavelength bins each ---------
         // The lanes of the two observations are INTERLEAVED (even lanes: first, odd lanes: second): when both
@@ -785,6 +834,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
             for (int m = 0; m < TP; ++m) dWr[m] = fmaf(dU, rc[DM::R_JT + m], dWr[m]);
         }
         __syncwarp();      // the next chunk overwrites the records
+        BAYESN_PHASE(3);
     }
 #pragma unroll
     for (int m = 0; m < TP; ++m) dWr[m] += __shfl_xor_sync(FULL, dWr[m], 1);
@@ -798,6 +848,43 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
 
     gT += wsum(gTW);
 
+    if (M.kw > 1) {
+        // ---- team exchange: every warp publishes its partial sums, all add them in rank order ----------
+        // (identical additions in every warp -> the replicated sampler states stay bit-identical).  The slots
+        // are double-buffered by the evaluation's parity, so ONE barrier per evaluation is enough: a warp can
+        // only overwrite a slot after passing the next barrier, which every teammate reaches after its reads.
+        constexpr int XW = xchg_words(LP, TP);
+        const int par = __float_as_int(c.sc[1]);
+        if (lane == 0) c.sc[1] = __int_as_float(par ^ XW);
+        float* mine = c.sc + M.xoff + par;
+        if (qlane && hb == 0) {
+#pragma unroll
+            for (int m = 0; m < TP; ++m) mine[(hl - 4) * TP + m] = dWr[m];
+        }
+        if (lane == 0) {
+            float* ps = mine + LP * TP;
+            ps[0] = __int_as_float(__double2loint(logL));
+            ps[1] = __int_as_float(__double2hiint(logL));
+            ps[2] = gDs; ps[3] = gAV; ps[4] = gT; ps[5] = DRV ? gRV : 0.f;
+        }
+        team_sync((threadIdx.x >> 5) >> M.kwl, M.kw);
+        const float* base = mine - tk * M.xstride;
+        logL = 0.0; gDs = 0.f; gAV = 0.f; gT = 0.f; gRV = 0.f;
+#pragma unroll
+        for (int m = 0; m < TP; ++m) dWr[m] = 0.f;
+        for (int kk = 0; kk < M.kw; ++kk, base += M.xstride) {
+            if (qlane && hb == 0) {
+#pragma unroll
+                for (int m = 0; m < TP; ++m) dWr[m] += base[(hl - 4) * TP + m];
+            }
+            const float* ps = base + LP * TP;
+            logL += __hiloint2double(__float_as_int(ps[1]), __float_as_int(ps[0]));
+            gDs += ps[2]; gAV += ps[3]; gT += ps[4];
+            if (DRV) gRV += ps[5];
+        }
+    }
+
+    BAYESN_PHASE(4);
     // ---- reverse: theta, eps_tform -----------------------------------------------------------
     // lane (hl = 4 + l, hb = 0) owns row l of dW
     float gth = 0.f;
@@ -852,12 +939,12 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
             if (i == ne + 1) grad[s] = g_uAV;
             if (i == ne + 2) grad[s] = g_Ds;
         }
-        // un-reduced contributions to the gradient of the globals (constrained space)
-        if (qlane && hb == 0) {
+        // un-reduced contributions to the gradient of the globals (constrained space); one writer per team
+        if (qlane && hb == 0 && tk == 0) {
 #pragma unroll
             for (int m = 0; m < TP; ++m) c.part[(hl - 4) * TP + m] = dWr[m];
         }
-        if (lane == 0) {
+        if (lane == 0 && tk == 0) {
             float* ps = c.part + LP * TP;
             ps[0] = (dD * dD * isd2 - 1.f) * isd2 * c.sigma0;          // d/dsigma0
             ps[1] = gRV;                                                 // d/dRV
@@ -893,6 +980,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         if (RVFREE && i == ne + 4) grad[s] = g_uR;
     }
     logp_out = lp;
+    BAYESN_PHASE(5);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -901,12 +989,14 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
 template <int LP, int TP, bool RVFREE, bool STAGE, bool TRAIN = false>
 __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, int n_chains, int ntile, float* smem,
                                           WarpCtx& c, int& sn, int& chain, bool per_warp = false) {
-    const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE, TRAIN);
+    const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE, TRAIN, M.kw);
     const int tid = threadIdx.x, warp = tid >> 5;
-    const long long unit0 = (long long)blockIdx.x * WPB;
+    const int upc = WPB >> M.kwl;                  // (SN, chain) units per CTA: one per team of kw warps
+    const int team = warp >> M.kwl;
+    const long long unit0 = (long long)blockIdx.x * upc;
     const long long total = (long long)Dd.N * n_chains;
     const int s_first = (int)(unit0 / n_chains);
-    long long last_unit = unit0 + WPB - 1;
+    long long last_unit = unit0 + upc - 1;
     if (last_unit >= total) last_unit = total - 1;
     const int s_last = (int)(last_unit / n_chains);
     // per_warp: only the model tables are staged here; every warp stages the data of the SN it
@@ -941,11 +1031,11 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
     mbar_wait(bar, 0);
     __syncthreads();
 
-    const long long unit = unit0 + warp;
+    const long long unit = unit0 + team;
     const bool active = per_warp || unit < total;
     sn = (!per_warp && active) ? (int)(unit / n_chains) : s_first;
     chain = (!per_warp && active) ? (int)(unit - (long long)sn * n_chains) : 0;
-    const int slot = per_warp ? warp : sn - s_first;
+    const int slot = per_warp ? team : sn - s_first;
     // Offsets are passed through an empty asm so that ptxas keeps each one in a register instead
     // of re-deriving the whole shared-memory plan from kernel parameters inside the hot loops
     // (seen in the round-1 profile: ~60 integer instructions per observation).
@@ -970,6 +1060,7 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
     c.eps = smem + wbase + P.wEps;
     c.rec = at(wbase + P.wRec);
     c.sc = at(wbase + P.wSc);
+    if ((tid & 31) == 0) c.sc[1] = 0.f;          // parity of the team exchange slots (latency mode)
     c.wad = at(wbase + P.wAd);
     c.wdad = at(wbase + P.wDad);
     c.nobs = Dd.n_valid[sn];
@@ -992,21 +1083,26 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
 // observations, band supports and - when STAGE - the weight tile of SN `sn` into its own slot and
 // points its context at them.  A few KB of coalesced loads per chain, i.e. per ~10^5 evaluations.
 template <bool STAGE>
-__device__ __forceinline__ void warp_bind(const DataDev& Dd, const SmemPlan& P, float* smem, WarpCtx& c, int sn, int lane) {
-    const int slot = threadIdx.x >> 5;
+__device__ __forceinline__ void warp_bind(const ModelDev& M, const DataDev& Dd, const SmemPlan& P, float* smem, WarpCtx& c,
+                                          int sn, int lane) {
+    const int warp = threadIdx.x >> 5;
+    const int slot = warp >> M.kwl;                // one slot of SN data per team
     __syncwarp();
-    float4* so = reinterpret_cast<float4*>(smem + P.oObs) + slot * Dd.N_obs;
-    const float4* go = Dd.obs4 + (size_t)sn * Dd.N_obs;
-    for (int i = lane; i < Dd.N_obs; i += 32) so[i] = go[i];
-    int4* ss = reinterpret_cast<int4*>(smem + P.oSup) + slot * Dd.n_b;
-    const int4* gs = Dd.sup + (size_t)sn * Dd.n_b;
-    for (int i = lane; i < Dd.n_b; i += 32) ss[i] = gs[i];
-    if (STAGE) {
-        float* st = smem + P.oWt + slot * Dd.wt_stride;
-        const float* gt = Dd.wt + (size_t)sn * Dd.wt_stride;
-        for (int i = lane; i < Dd.wt_stride; i += 32) st[i] = gt[i];
+    if ((warp & (M.kw - 1)) == 0) {                // the team's first warp stages, the others wait at the barrier
+        float4* so = reinterpret_cast<float4*>(smem + P.oObs) + slot * Dd.N_obs;
+        const float4* go = Dd.obs4 + (size_t)sn * Dd.N_obs;
+        for (int i = lane; i < Dd.N_obs; i += 32) so[i] = go[i];
+        int4* ss = reinterpret_cast<int4*>(smem + P.oSup) + slot * Dd.n_b;
+        const int4* gs = Dd.sup + (size_t)sn * Dd.n_b;
+        for (int i = lane; i < Dd.n_b; i += 32) ss[i] = gs[i];
+        if (STAGE) {
+            float* st = smem + P.oWt + slot * Dd.wt_stride;
+            const float* gt = Dd.wt + (size_t)sn * Dd.wt_stride;
+            for (int i = lane; i < Dd.wt_stride; i += 32) st[i] = gt[i];
+        }
     }
     __syncwarp();
+    if (M.kw > 1) team_sync(slot, M.kw);
     c.wt_g = Dd.wt + (size_t)sn * Dd.wt_stride;
     c.nobs = Dd.n_valid[sn];
     c.muhat = Dd.muhat[sn];

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(WPB * 32) logp_grad_kernel(ModelDev M, DataDev
     }
     double lp;
     eval_logp_grad<LP, TP, VPL, RVFREE, STAGE>(M, c, M.hs, q, lp, g, lane);
+    if (((threadIdx.x >> 5) & (M.kw - 1)) != 0) return;       // latency mode: the team's warps hold identical results
     if (lane == 0) logp_out[unit] = (float)lp;
 #pragma unroll
     for (int s = 0; s < VPL; ++s) {
@@ -53,6 +54,10 @@ struct FluxArgs {
     float* out;
 };
 
+// SPECTRA = false: the band-pass integral of every (observation, SN) -> out (N_obs, N), flux or magnitude.
+// SPECTRA = true : SEDmodel.get_spectra (bayesn/bayesn_model.py:556-643), the host-dust-extinguished
+//                  rest-frame SED on the 300-bin model grid, out [N][300][N_obs].
+template <bool SPECTRA>
 __global__ void __launch_bounds__(128) flux_kernel(FluxArgs A) {
     __shared__ float su[4][BAYESN_MAX_L];
     __shared__ float syk[4][12];
@@ -62,7 +67,6 @@ __global__ void __launch_bounds__(128) flux_kernel(FluxArgs A) {
     if (item >= total) return;
     const int s = (int)(item / A.N_obs), o = (int)(item - (long long)s * A.N_obs);
     const size_t on = (size_t)o * A.N + s;
-    const bool msk = A.mask[on] != 0;
     const int L = A.L, T = A.T;
     // u[l] = -c2 * sum_m (W0 + theta W1 + eps)[l][m] J_t[s][m][o]
     if (lane < L) {
@@ -75,31 +79,20 @@ __global__ void __launch_bounds__(128) flux_kernel(FluxArgs A) {
     }
     const float RV = A.RV[s];
     if (lane == 0) {
-        const float R = RV, R2 = R * R, R3 = R2 * R;
-        const float c2f = -0.824f + 4.717f / R, c1f = 2.030f - 3.007f * c2f;
-        const float x7 = 1e4f / 2700.f, x8 = 1e4f / 2600.f, x0 = 4.596f, gm = 0.99f;
-        const float d1 = x7 * x7 / ((x7 * x7 - x0 * x0) * (x7 * x7 - x0 * x0) + gm * gm * x7 * x7);
-        const float d2 = x8 * x8 / ((x8 * x8 - x0 * x0) * (x8 * x8 - x0 * x0) + gm * gm * x8 * x8);
-        float* yk = syk[warp];
-        yk[0] = -R;
-        yk[1] = 0.26469f * R / 3.1f - R;
-        yk[2] = 0.82925f * R / 3.1f - R;
-        yk[3] = -0.422809f + 0.00270f * R + 2.13572e-4f * R2;
-        yk[4] = -5.13540e-2f + 0.00216f * R - 7.35778e-5f * R2;
-        yk[5] = 0.700127f + 0.00184f * R - 3.32598e-5f * R2;
-        yk[6] = 1.19456f + 0.01707f * R - 5.46959e-3f * R2 + 7.97809e-4f * R3 - 4.45636e-5f * R2 * R2;
-        yk[7] = c1f + c2f * x7 + 3.23f * d1;
-        yk[8] = c1f + c2f * x8 + 3.23f * d2;
+        float yk[9], dyk[9];
+        f99_yk(RV, yk, dyk);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) syk[warp][j] = yk[j];
     }
     __syncwarp();
-    const int k = A.band[on];
     const float AVc = -C2 * A.AV[s];
     const float iR = 1.f / RV;
     int i0 = (int)A.hsi[on], i1 = (int)A.hsi[(size_t)A.N_obs * A.N + on];
     const float f = A.hsi[2 * (size_t)A.N_obs * A.N + on];
     i0 = min(max(i0, 0), NPH - 1);
     i1 = min(max(i1, 0), NPH - 1);
-    const float* wcol = A.weights + (size_t)s * NB * A.n_b + k;
+    const int k = SPECTRA ? 0 : A.band[on];
+    const float* wcol = SPECTRA ? nullptr : A.weights + (size_t)s * NB * A.n_b + k;
     float F = 0.f;
     for (int b = lane; b < NB; b += 32) {
         float g = 0.f;
@@ -110,10 +103,14 @@ __global__ void __launch_bounds__(128) flux_kernel(FluxArgs A) {
         const float a = 1.f + my * iR;
         const float h0 = A.hs[i0 * BP + b], h1 = A.hs[i1 * BP + b];
         const float H = fmaf(f, h1 - h0, h0);
-        F = fmaf(wcol[(size_t)b * A.n_b] * H, ex2_approx(fmaf(AVc, a, g)), F);
+        const float sed = H * ex2_approx(fmaf(AVc, a, g));
+        if (SPECTRA) A.out[((size_t)s * NB + b) * A.N_obs + o] = sed;
+        else F = fmaf(wcol[(size_t)b * A.n_b], sed, F);
     }
+    if (SPECTRA) return;
     F = wsum(F);
     if (lane == 0) {
+        const bool msk = A.mask[on] != 0;
         // scale = 10^(-0.4 (M0 + Ds)) * band scale, assembled in the log2 domain
         float flux = F * (float)exp2(A.bscale[k] - 1.3287712379549449 * ((double)A.M0 + (double)A.Ds[s]));
         flux = msk ? flux : 0.f;
@@ -126,61 +123,118 @@ __global__ void __launch_bounds__(128) flux_kernel(FluxArgs A) {
     }
 }
 
-// (2b) SEDmodel.get_spectra (bayesn/bayesn_model.py:556-643): the host-dust-extinguished rest-frame
-//      SED on the 300-bin model grid, out [N][300][N_obs]; one warp per (observation, SN).
-__global__ void __launch_bounds__(128) spectra_kernel(FluxArgs A) {
+// ------------------------------------------------------------------------------------------
+// (2c) SEDmodel.get_flux_from_chains (bayesn/bayesn_model.py:3426-3524): model photometry of posterior
+//      draws on a phase grid, ONE launch over (SN x draw x phase).  The reference loops over SNe and
+//      runs simulate_light_curve per SN (4.91 s per SN in example_fits.ipynb); here a warp takes one
+//      (SN, draw, phase): it builds the extinguished SED on the 300-bin grid once (lanes over bins, staged
+//      in shared memory) and integrates it through every band the SN was observed in, reading the SN's
+//      compact weight tile (the same tiles + supports the fit kernels read, built by bayesn_tiles_*).
+//      out [N][S][max_bands][n_t], flux (FLUXCAL) or magnitudes.
+// ------------------------------------------------------------------------------------------
+struct ChainFluxArgs {
+    int N, S, n_t, max_bands, n_b, L, T, n_eps, LP, TP, RS, mag, rvfree;
+    const float* t;          // [n_t] rest-frame phases
+    const float* theta;      // [N][S]
+    const float* AV;         // [N][S]
+    const float* tmax;       // [N][S]
+    const float* dD;         // [N][S]  (mu + delM) - fold_s: the distance relative to the exponent folded into the tile
+    const float* RV;         // [N][S] when rvfree
+    const float* eps;        // [N][S][n_eps], eps = L_Sigma eps_tform, element (l-1) + (L-2) m
+    const int* bands;        // [N][max_bands] column of the SN's tile (index into its support rows), -1 = none
+    const float* wt;         // [N][wt_stride]
+    const int4* sup;         // [N][n_b]
+    int wt_stride;
+    const float *Jl, *hs, *Mf, *ad, *W0, *W1, *KD, *tau;      // model tables (layouts of ModelDev)
+    float* out;
+};
+
+template <int TP>
+__global__ void __launch_bounds__(128) chain_flux_kernel(ChainFluxArgs A) {
     __shared__ float su[4][BAYESN_MAX_L];
     __shared__ float syk[4][12];
+    __shared__ float ssed[4][BP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long item = (long long)blockIdx.x * 4 + warp;
-    const long long total = (long long)A.N * A.N_obs;
+    const long long total = (long long)A.N * A.S * A.n_t;
     if (item >= total) return;
-    const int s = (int)(item / A.N_obs), o = (int)(item - (long long)s * A.N_obs);
-    const size_t on = (size_t)o * A.N + s;
+    const int it = (int)(item % A.n_t);
+    const long long ns = item / A.n_t;            // (SN, draw)
+    const int sn = (int)(ns / A.S);
     const int L = A.L, T = A.T;
+    const float t = A.t[it] - A.tmax[ns];
+    const float theta = A.theta[ns];
+    // u[l] = -c2 sum_m (W0 + theta W1 + eps)[l][m] J_t(t)[m]; every lane l < L builds the spline row itself
     if (lane < L) {
-        float th = A.theta[s], acc = 0.f;
-        for (int m = 0; m < T; ++m) {
-            float w = A.W0[lane * T + m] + th * A.W1[lane * T + m] + A.eps[((size_t)s * L + lane) * T + m];
-            acc = fmaf(w, A.J_t[((size_t)s * T + m) * A.N_obs + o], acc);
+        float J[TP], dJ[TP];
+        spline_row<TP>(t, T, A.tau, A.KD, J, dJ);
+        float acc = 0.f;
+#pragma unroll
+        for (int m = 0; m < TP; ++m) {
+            if (m < T) {
+                float w = fmaf(theta, A.W1[lane * A.TP + m], A.W0[lane * A.TP + m]);
+                if (lane >= 1 && lane <= L - 2) w += A.eps[(size_t)ns * A.n_eps + (lane - 1) + (L - 2) * m];
+                acc = fmaf(w, J[m], acc);
+            }
         }
         su[warp][lane] = -C2 * acc;
     }
-    const float RV = A.RV[s];
-    if (lane == 0) {
-        const float R = RV, R2 = R * R, R3 = R2 * R;
-        const float c2f = -0.824f + 4.717f / R, c1f = 2.030f - 3.007f * c2f;
-        const float x7 = 1e4f / 2700.f, x8 = 1e4f / 2600.f, x0 = 4.596f, gm = 0.99f;
-        const float d1 = x7 * x7 / ((x7 * x7 - x0 * x0) * (x7 * x7 - x0 * x0) + gm * gm * x7 * x7);
-        const float d2 = x8 * x8 / ((x8 * x8 - x0 * x0) * (x8 * x8 - x0 * x0) + gm * gm * x8 * x8);
-        float* yk = syk[warp];
-        yk[0] = -R;
-        yk[1] = 0.26469f * R / 3.1f - R;
-        yk[2] = 0.82925f * R / 3.1f - R;
-        yk[3] = -0.422809f + 0.00270f * R + 2.13572e-4f * R2;
-        yk[4] = -5.13540e-2f + 0.00216f * R - 7.35778e-5f * R2;
-        yk[5] = 0.700127f + 0.00184f * R - 3.32598e-5f * R2;
-        yk[6] = 1.19456f + 0.01707f * R - 5.46959e-3f * R2 + 7.97809e-4f * R3 - 4.45636e-5f * R2 * R2;
-        yk[7] = c1f + c2f * x7 + 3.23f * d1;
-        yk[8] = c1f + c2f * x8 + 3.23f * d2;
+    float iR = 0.f;
+    if (A.rvfree) {
+        const float RV = A.RV[ns];
+        iR = 1.f / RV;
+        if (lane == 0) {
+            float yk[9], dyk[9];
+            f99_yk(RV, yk, dyk);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) syk[warp][j] = yk[j];
+        }
     }
     __syncwarp();
-    const float AVc = -C2 * A.AV[s];
-    const float iR = 1.f / RV;
-    int i0 = (int)A.hsi[on], i1 = (int)A.hsi[(size_t)A.N_obs * A.N + on];
-    const float f = A.hsi[2 * (size_t)A.N_obs * A.N + on];
+    const float AVc = -C2 * A.AV[ns];
+    const float fl = floorf(t);
+    int i0 = 19 + (int)fl, i1 = 19 + (int)ceilf(t);
     i0 = min(max(i0, 0), NPH - 1);
     i1 = min(max(i1, 0), NPH - 1);
-    for (int b = lane; b < NB; b += 32) {
-        float g = 0.f;
-        for (int l = 0; l < L; ++l) g = fmaf(A.Jl[b * A.LPs + l], su[warp][l], g);
-        float my = 0.f;
+    const float f = t - fl;
+    for (int b = lane; b < BP; b += 32) {
+        float sed = 0.f;
+        if (b < NB) {
+            float g = 0.f;
+            for (int l = 0; l < L; ++l) g = fmaf(A.Jl[b * A.RS + l], su[warp][l], g);
+            float a;
+            if (A.rvfree) {
+                float my = 0.f;
 #pragma unroll
-        for (int j = 0; j < 9; ++j) my = fmaf(A.Mf[j * BP + b], syk[warp][j], my);
-        const float a = 1.f + my * iR;
-        const float h0 = A.hs[i0 * BP + b], h1 = A.hs[i1 * BP + b];
-        const float H = fmaf(f, h1 - h0, h0);
-        A.out[((size_t)s * NB + b) * A.N_obs + o] = H * ex2_approx(fmaf(AVc, a, g));
+                for (int j = 0; j < 9; ++j) my = fmaf(A.Mf[j * BP + b], syk[warp][j], my);
+                a = 1.f + my * iR;
+            } else {
+                a = A.ad[b];
+            }
+            const float h0 = A.hs[i0 * BP + b], h1 = A.hs[i1 * BP + b];
+            sed = fmaf(f, h1 - h0, h0) * ex2_approx(fmaf(AVc, a, g));
+        }
+        ssed[warp][b] = sed;
+    }
+    __syncwarp();
+    const float S = exp2f(-C2 * A.dD[ns]);
+    const float* tile = A.wt + (size_t)sn * A.wt_stride;
+    for (int j = 0; j < A.max_bands; ++j) {
+        const int k = A.bands[(size_t)sn * A.max_bands + j];
+        float F = 0.f;
+        if (k >= 0) {
+            const int4 sp = A.sup[(size_t)sn * A.n_b + k];
+            for (int b = sp.x + lane; b < sp.y; b += 32) F = fmaf(tile[sp.z + b - sp.x], ssed[warp][b], F);
+            F = wsum(F);
+        }
+        if (lane == 0) {
+            float outv = 0.f;
+            if (k >= 0) {
+                const float flux = S * F;
+                outv = A.mag ? (-2.5f * log10f(flux) + 27.5f) : flux;
+            }
+            A.out[(((size_t)ns) * A.max_bands + j) * A.n_t + it] = outv;
+        }
     }
 }
 
@@ -261,25 +315,39 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
     const bool active = cta_setup<LP, TP, RVFREE, STAGE>(M, Dd, C, ntile, smem, c, sn, chain, dyn);
     if (!active) return;
     const int lane = threadIdx.x & 31;
+    // Latency mode (M.kw > 1): the kw warps of a team run this whole state machine redundantly on the same unit -
+    // identical inputs, identical decisions - and only split the observation pairs inside eval_logp_grad; each
+    // keeps its own copy of the tree vectors, the team's first warp writes the results.
+    const int tk = (threadIdx.x >> 5) & (M.kw - 1);
+    const bool writer = tk == 0;
     const unsigned long long total_units = (unsigned long long)Dd.N * C;
     for (bool first_unit = true;; first_unit = false) {
         size_t unit;
         if (dyn) {
             unsigned long long u = 0;
-            if (lane == 0) u = atomicAdd(queue, 1ULL);
-            u = __shfl_sync(FULL, u, 0);
+            if (tk == 0) {
+                if (lane == 0) u = atomicAdd(queue, 1ULL);
+                u = __shfl_sync(FULL, u, 0);
+            }
+            if (M.kw > 1) {
+                // the team's first warp fetched the unit; it hands it to the others through its scalar slot
+                // (rewritten only a whole chain - many team barriers - later)
+                if (tk == 0 && lane == 0) *reinterpret_cast<unsigned long long*>(c.sc + 2) = u;
+                team_sync((threadIdx.x >> 5) >> M.kwl, M.kw);
+                u = *reinterpret_cast<const unsigned long long*>(c.sc - tk * M.xstride + 2);
+            }
             if (u >= total_units) break;
             sn = (int)(u / (unsigned)C);
             chain = (int)(u - (unsigned long long)sn * C);
-            const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE);
-            warp_bind<STAGE>(Dd, P, smem, c, sn, lane);
+            const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE, false, M.kw);
+            warp_bind<STAGE>(M, Dd, P, smem, c, sn, lane);
         } else {
             if (!first_unit) break;
         }
         unit = (size_t)sn * C + chain;
         const int D = M.D;
         const int nvec = nuts_num_vectors(cfg.max_depth);
-        VecIO<VPL> io{work + unit * (size_t)nvec * 32 * VPL, lane};
+        VecIO<VPL> io{work + ((unit << M.kwl) + tk) * (size_t)nvec * 32 * VPL, lane};
         const uint2 key = make_uint2(cfg.seed_lo, cfg.seed_hi);
         const uint32_t gunit = (uint32_t)unit + cfg.unit_offset;      // random streams do not depend on the sharding
         bool own[VPL];
@@ -357,6 +425,9 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
         // evaluation (the very first one initialises the chain, all others are leapfrog steps).
         // mode 0: leapfrog steps.  mode 1: evaluate the initial point.  modes 2, 3: distance rescue (below).
         int mode = 1;
+#ifdef BAYESN_PHASE_TIMING
+        long long t_prev_eval = 0;
+#endif
         int init_tries = 0, n_rescue = 0;
         float rs_S1 = 0.f, rs_h1 = 0.f;
         const int iD = M.n_eps + 3;             // element of the (shifted) distance
@@ -370,7 +441,17 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
                 }
             }
             double lp;
+#ifdef BAYESN_PHASE_TIMING
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                const long long t_now = clock64();
+                if (t_prev_eval) atomicAdd(&g_phase[6], (unsigned long long)(t_now - t_prev_eval));
+                atomicAdd(&g_phase[7], 1ULL);
+            }
+#endif
             eval_logp_grad<LP, TP, VPL, RVFREE, STAGE>(M, c, M.hs, z, lp, g, lane);
+#ifdef BAYESN_PHASE_TIMING
+            t_prev_eval = clock64();
+#endif
             const double pe_new = -lp;
 #pragma unroll
             for (int s = 0; s < VPL; ++s) g[s] = -g[s];
@@ -499,7 +580,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
             const float accept = sum_acc / (float)max(n_prop, 1);
             io.ld(V_ZP, z); io.ld(V_GP, g);
             pe = prop_pe;
-            if (lane == 0) {
+            if (lane == 0 && writer) {
                 float* srow = stats + (unit * (size_t)n_iter + it) * 5;
                 srow[0] = accept;
                 srow[1] = (float)n_prop;
@@ -556,7 +637,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
                 const size_t row = unit * cfg.num_samples + k;
 #pragma unroll
                 for (int s = 0; s < VPL; ++s)
-                    if (own[s]) samples[row * D + lane + 32 * s] = z[s] + ((lane + 32 * s == M.n_eps + 3) ? c.muhat : 0.f);
+                    if (own[s] && writer) samples[row * D + lane + 32 * s] = z[s] + ((lane + 32 * s == M.n_eps + 3) ? c.muhat : 0.f);
                 mean_acc += (accept - mean_acc) / (float)(k + 1);
                 n_div += diverging ? 1 : 0;
             }
@@ -583,6 +664,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
             begin_doubling();
         }
         float* ci = chain_info + unit * (4 + D);
+        if (!writer) continue;
         if (lane == 0) {
             ci[0] = step;
             ci[1] = mean_acc;

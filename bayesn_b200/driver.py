@@ -44,7 +44,19 @@ def parse_yaml_input(model, args, cmd_args=None):
         raise NotImplementedError('the VI path is outside the scope of this implementation; use fit_method: mcmc')
     if 'mode' not in args:
         raise ValueError("input needs a 'mode'")
-    os.makedirs(args['outputdir'], exist_ok=True)
+    # SNANA batch mode (reference :1703-1709): jobsplit = [job id, number of jobs]
+    args['jobsplit'] = args.get('jobsplit')
+    if args['jobsplit'] is not None:
+        args['snana'] = True
+    else:
+        args['jobsplit'] = [1, 1]
+        args['snana'] = False
+    args['jobid'] = args['jobsplit'][0]
+    args['njobtot'] = args['jobsplit'][1] * args['sim_prescale']
+    args['save_chains'] = args.get('save_chains', True)
+    args['warps_per_chain'] = args.get('warps_per_chain', 'auto')
+    if not (args['mode'].lower() == 'fitting' and args['snana']):
+        os.makedirs(args['outputdir'], exist_ok=True)
     return args
 
 
@@ -63,8 +75,10 @@ def process_dataset(model, args):
     fmap = dict(args.get('map', {}))
     used = [0]
     lcs, names, peaks, cols = [], [], [], {k: [] for k in ('zHEL', 'zHELERR', 'zHD', 'zHDERR', 'MWEBV', 'HOST_LOGMASS')}
+    survey = 'NULL'
     for fn in sn_files:
         meta, lc = snana.read_snana_ascii(os.path.join(data_dir, str(fn)))
+        survey = str(meta.get('SURVEY', 'NULL'))          # reference :2688
         peak = meta['PEAKMJD'] if 'PEAKMJD' in meta else meta['SEARCH_PEAKMJD']
         zhel = float(meta['REDSHIFT_HELIO'])
         zcmb = float(meta.get('REDSHIFT_FINAL', meta.get('REDSHIFT_CMB', zhel)))
@@ -125,20 +139,48 @@ def process_dataset(model, args):
         obs[4, :n, i] = np.where(obs[9, :n, i] != 0, [local[g] for g in l['gl']], 0)
         obs[3, :, i], obs[5, :, i], obs[6, :, i], obs[7, :, i], obs[8, :, i] = l['mass'], l['z'], l['zerr'], l['mu'], l['ebv']
     lcplot = [dict(CID=names[i], MJD=l['mjd'], FLUXCAL=l['flux'], FLUXCALERR=l['ferr'], FLT=l['flt']) for i, l in enumerate(lcs)]
-    return dict(obs=obs, band_inds=band_inds, sn_names=names, peak_mjds=np.array(peaks), lcplot=lcplot,
+    return dict(obs=obs, band_inds=band_inds, sn_names=names, peak_mjds=np.array(peaks), lcplot=lcplot, survey=survey,
                 fitres={k: np.array(v) for k, v in cols.items()})
 
 
-def write_lcplot(model, path, ds, samples, save_fit_errors=False):
-    """``<prefix>.LCPLOT`` (reference :2256-2293): the photometry that was fitted (DATA_FLAG 1) followed
-    by the model light curve of every SN on a 2-day rest-frame grid in its own bands (DATA_FLAG 0):
-    the curve at the posterior mean, or mean / std over the draws with ``save_fit_errors``."""
+def lcplot_curves(model, ds, cons, lo, hi, save_fit_errors=False, chunk=512):
+    """Model light curves for the LCPLOT file (reference :2256-2272): every SN of the shard [lo, hi) on a 2-day
+    rest-frame grid in its own bands, from the device draws ``cons`` - the posterior 'mean' curve (which, like the
+    reference's ``get_flux_from_chains(mean=True)``, is the first draw: SURVEY Appendix E) or mean / std over all
+    draws with ``save_fit_errors``.  One ``bayesn_chain_flux`` launch per ``chunk`` SNe; only (n, bands, phases)
+    means / stds leave the device."""
     import pandas as pd
     t = np.arange(model.tau_knots[0], model.tau_knots[-1], 2)
-    z_hel, ebv = ds['obs'][5, 0, :], ds['obs'][8, 0, :]
-    bands = [list(pd.unique(l['FLT'])) for l in ds['lcplot']]
-    f = model.get_flux_from_chains(t, bands, samples, z_hel, ebv, num_samples=None, mag=False, mean=not save_fit_errors)
-    fm, fe = f.mean(axis=1), f.std(axis=1)
+    z_hel, ebv = ds['obs'][5, 0, lo:hi], ds['obs'][8, 0, lo:hi]
+    bands = [list(pd.unique(l['FLT'])) for l in ds['lcplot'][lo:hi]]
+    nb = max(len(b) for b in ds_bands(ds))
+    n = hi - lo
+    fm, fe = np.zeros((n, nb, len(t))), np.zeros((n, nb, len(t)))
+    flat = lambda v, a, b: v[a:b].transpose(1, 2).reshape(b - a, -1)          # (n, S*C): draw index c + C s
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        sl = (lambda v: flat(v, a, b)) if save_fit_errors else (lambda v: v[a:b, :1, 0])
+        eps = cons['eps'][a:b]
+        eps = eps.transpose(1, 2).reshape(b - a, -1, eps.shape[-1]) if save_fit_errors else eps[:, :1, 0]
+        RV = sl(cons['RV']) if 'RV' in cons else None
+        f = model.chain_flux_device(t, bands[a:b], sl(cons['theta']), sl(cons['AV']), sl(cons['tmax']),
+                                    sl(cons['mu']) + sl(cons['delM']), eps.contiguous(), z_hel[a:b], ebv[a:b], RV=RV, mag=False)
+        fm[a:b, :f.shape[2]] = f.double().mean(dim=1).cpu().numpy()
+        fe[a:b, :f.shape[2]] = f.double().std(dim=1, unbiased=False).cpu().numpy()
+    return t, fm, fe
+
+
+def ds_bands(ds):
+    import pandas as pd
+    return [list(pd.unique(l['FLT'])) for l in ds['lcplot']]
+
+
+def write_lcplot(model, path, ds, t, fm, fe):
+    """``<prefix>.LCPLOT`` (reference :2256-2293): the photometry that was fitted (DATA_FLAG 1) followed
+    by the model light curve of every SN (DATA_FLAG 0)."""
+    import pandas as pd
+    z_hel = ds['obs'][5, 0, :]
+    bands = ds_bands(ds)
     frames = []
     for i, l in enumerate(ds['lcplot']):
         d = pd.DataFrame({'CID': l['CID'], 'MJD': l['MJD'], 'FLUXCAL': l['FLUXCAL'], 'FLUXCALERR': l['FLUXCALERR'],
@@ -153,53 +195,108 @@ def write_lcplot(model, path, ds, samples, save_fit_errors=False):
     return out
 
 
-def run(model, args, cmd_args=None):
+def survey_id(survey):
+    """IDSURVEY from $SNDATA_ROOT/SURVEY.DEF (reference :2421-2431); 0 when SNANA is not installed."""
+    root = os.environ.get('SNDATA_ROOT')
+    if root and os.path.exists(os.path.join(root, 'SURVEY.DEF')):
+        with open(os.path.join(root, 'SURVEY.DEF')) as fh:
+            for line in fh:
+                sp = line.split()
+                if len(sp) >= 3 and sp[0] == 'SURVEY:' and sp[1] == survey:
+                    return int(sp[2])
+    return 0
+
+
+def run(model, args, cmd_args=None, group=None):
     """Reference ``SEDmodel.run`` for ``mode: fitting`` (per-object NUTS fits of every SN in the data
     set, :1809-1849) and ``mode: training_globalRV`` (:1766-1770, :1913-1924).  Returns the samples
-    dict (reference site names; (chains, draws, ..., N) for fits)."""
+    dict (reference site names; (chains, draws, ..., N) for fits).
+
+    Multi-GPU (``torchrun``, one process per GPU): with an initialised ``torch.distributed`` default group (or an
+    explicit ``group``) every rank fits the block ``shard_bounds(N, rank, world)`` of the data set - no data-path
+    collective; per-SN summaries and light-curve tables are reduced on the device and only those rows are gathered
+    for the FITRES / LCPLOT files that rank 0 writes.  The full draws are gathered (and ``chains.pkl`` /
+    ``fit_summary.csv`` written) only with ``save_chains`` (default, as in the reference; switch it off for
+    LSST-sized jobs: 100k SNe are 23 GB of draws)."""
+    import torch
     import yaml
     from . import outputs
+    from .distributed import shard_bounds, gather_rows
     args = parse_yaml_input(model, args, cmd_args)
     mode = args['mode'].lower()
+    rank, world = 0, 1
+    if group is None and torch.distributed.is_available() and torch.distributed.is_initialized() \
+            and torch.distributed.get_world_size() > 1:
+        group = torch.distributed.group.WORLD
+    if group is not None:
+        rank, world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
     ds = process_dataset(model, args)
     model.data, model.sn_list, model.peak_mjds = ds['obs'], ds['sn_names'], ds['peak_mjds']
     model.used_band_inds = ds['band_inds']
+    model.survey = ds.get('survey', 'NULL')
+    model.survey_id = survey_id(model.survey)
     if model.verbose:
         print(f'Current mode: {args["mode"]}\nRunning...')
     start = time.time()
+    drop_count = 0
     if mode == 'fitting':
-        cons, raw = model.fit_batch(ds['obs'], None, ds['band_inds'], num_chains=args['num_chains'],
+        N = ds['obs'].shape[-1]
+        lo, hi = shard_bounds(N, rank, world)
+        cons, raw = model.fit_batch(ds['obs'][:, :, lo:hi], None, ds['band_inds'], num_chains=args['num_chains'],
                                     num_warmup=args['num_warmup'], num_samples=args['num_samples'], max_tree_depth=10,
-                                    seed=0, return_device=True)
-        cols, dropped = outputs.postprocess_fits(model, cons, ds['obs'], sn_names=ds['sn_names'], outputdir=args['outputdir'],
-                                                 outfile_prefix=args['outfile_prefix'], save_chains=True,
-                                                 extra_columns={k: v for k, v in ds['fitres'].items() if k not in ('zHEL', 'MWEBV')})
-        samples = {}
-        for k, v in cons.items():
-            v = v.cpu().numpy().astype(np.float64)
-            samples[k] = (v.transpose(1, 2, 3, 0) if k == 'eps' else v.transpose(1, 2, 0, 3)) if v.ndim == 4 else v.transpose(1, 2, 0)
-        muhat = ds['obs'][7, 0, :][None, None, :]
-        s0 = float(model.sigma0)
-        samples['mu'] = np.random.normal((samples['Ds'] * 25.0 + muhat * s0 ** 2) / (25.0 + s0 ** 2),
-                                         np.sqrt(s0 ** 2 * 25.0 / (25.0 + s0 ** 2)))        # reference :2250-2254
-        samples['delM'] = samples['Ds'] - samples['mu']
-        write_lcplot(model, os.path.join(args['outputdir'], f'{args["outfile_prefix"]}.LCPLOT'), ds, samples,
-                     args['save_fit_errors'])
-        if 'tmax' in samples:
-            samples['peak_MJD'] = ds['peak_mjds'][None, None, :] + samples['tmax'] * (1 + ds['obs'][5, 0, :][None, None, :])
+                                    seed=0, return_device=True, sn_offset=lo, warps_per_chain=args['warps_per_chain'])
+        muhat = ds['obs'][7, 0, lo:hi]
+        outputs.draw_mu_device(model, cons, muhat, seed=0, sn_offset=lo)          # reference :2250-2254
+        summ = outputs.device_fit_summary(model, cons, muhat)
+        t, fm, fe = lcplot_curves(model, ds, cons, lo, hi, args['save_fit_errors'])
+        keys = list(summ.keys())
+        rows = np.stack([summ[k] for k in keys], axis=1)
+        if world > 1:
+            dev = cons['Ds'].device
+            g = lambda a: gather_rows(torch.as_tensor(np.ascontiguousarray(a), device=dev), N, group).cpu().numpy()
+            rows, fm, fe = g(rows), g(fm), g(fe)
+        samples = None
+        want_chains = args['save_chains'] and not args['snana']
+        if want_chains or world == 1:
+            full = {k: (gather_rows(v.contiguous(), N, group) if world > 1 else v) for k, v in cons.items()}
+            samples = outputs.host_samples(full)
+            if 'tmax' in samples:
+                samples['peak_MJD'] = ds['peak_mjds'][None, None, :] + samples['tmax'] * (1 + ds['obs'][5, 0, :][None, None, :])
+        else:
+            samples = outputs.host_samples(cons)           # this rank's shard only
+        if rank == 0:
+            cols = {'zHEL': ds['obs'][5, 0, :], 'MWEBV': ds['obs'][8, 0, :], 'MUHAT': ds['obs'][7, 0, :]}
+            cols.update({k: v for k, v in ds['fitres'].items() if k not in ('zHEL', 'MWEBV')})
+            cols.update({k: rows[:, i] for i, k in enumerate(keys)})
+            pre = args['outfile_prefix']
+            base = pre if os.path.isabs(pre) else os.path.join(args['outputdir'], pre)
+            os.makedirs(os.path.dirname(base) or '.', exist_ok=True)
+            drop_count = outputs.write_fitres(base + '.FITRES.TEXT', ds['sn_names'], cols,
+                                              version_photometry=args.get('version_photometry', 'NULL'))
+            write_lcplot(model, base + '.LCPLOT', ds, t, fm, fe)
+            if want_chains:
+                outputs.write_chains(samples, args['outputdir'])
     elif mode == 'training_globalrv':
         init = args['initialisation']
-        if init in ('median', 'sample'):
-            raise NotImplementedError("training starts from a reference model: set 'initialisation' to a model name "
-                                      "(e.g. M20_model) or a BAYESN.YAML path")
         samples, _ = model.train(ds['obs'], None, ds['band_inds'], num_chains=args['num_chains'],
                                  num_warmup=args['num_warmup'], num_samples=args['num_samples'], initialisation=init,
-                                 outputdir=args['outputdir'], mode=args['mode'])
+                                 outputdir=args['outputdir'], mode=args['mode'], group=group)
     else:
         raise ValueError("Invalid mode, this implementation runs 'training_globalRV' and 'fitting'")
     model.end_time = time.time()
     if model.verbose:
         print(f'Total inference runtime: {model.end_time - start} seconds')
-    with open(os.path.join(args['outputdir'], 'input.yaml'), 'w') as fh:
-        yaml.safe_dump({k: (v if isinstance(v, (int, float, str, bool, list, dict, type(None))) else str(v)) for k, v in args.items()}, fh)
+    if rank != 0:
+        return samples
+    if args['snana']:
+        # SNANA batch job summary (reference :2342-2356)
+        n = ds['obs'].shape[-1]
+        out_dict = {'ABORT_IF_ZERO': 1, 'SURVEY': model.survey, 'IDSURVEY': int(model.survey_id), 'NEVT_TOT': n,
+                    'NEVT_LC_CUTS': n, 'NEVT_LCFIT_CUTS': int(n - drop_count),
+                    'CPU_MINUTES': round((model.end_time - model.start_time) / 60, 2)}
+        with open(f'{args["outfile_prefix"]}.YAML', 'w') as fh:
+            yaml.safe_dump(out_dict, fh)
+    if not (mode == 'fitting' and args['snana']):
+        with open(os.path.join(args['outputdir'], 'input.yaml'), 'w') as fh:
+            yaml.safe_dump({k: (v if isinstance(v, (int, float, str, bool, list, dict, type(None))) else str(v)) for k, v in args.items()}, fh)
     return samples

@@ -356,47 +356,126 @@ class SEDmodel(object):
         weights = self._calculate_band_weights(data[-5, 0, :], data[-2, 0, :], band_inds)
         return data, weights, band_inds
 
+    def _fit_devices(self, N):
+        """Devices one process spreads a batch fit over.  The reference's ``num_devices`` (:202) asks numpyro
+        for that many local devices and falls back with a warning when there are fewer (:1831,
+        ``chain_method='parallel'``); here SNe - not chains - are the parallel axis.  Under ``torchrun`` (one
+        process per GPU) or with an explicit ``device=`` the process owns exactly one GPU."""
+        import torch
+        if self._device is not None or 'LOCAL_RANK' in os.environ or not torch.cuda.is_available():
+            return [self._device_index()]
+        n = max(1, min(int(self.num_devices or 1), torch.cuda.device_count(), int(N)))
+        return list(range(n))
+
     def fit_batch(self, obs, weights, band_inds=None, num_chains=4, num_warmup=250, num_samples=250,
                   max_tree_depth=10, seed=0, RV=None, fix_tmax=False, fix_theta=False, theta_val=0.0, fix_AV=False,
-                  AV_val=0.0, init='median', return_device=False, q_init=None, sn_offset=0):
+                  AV_val=0.0, init='median', return_device=False, q_init=None, sn_offset=0, group=None,
+                  warps_per_chain=1, gather=True):
         """Independent NUTS fits of N supernovae (the vmapped ``fit_vmap_mcmc`` of reference
         :1809-1849).  Returns (samples dict with arrays shaped (chains, draws, [dim,] N) like
-        the reference after :1839-1848, extras dict).  ``sn_offset``: index of the first SN of
-        ``obs`` in the whole job when SNe are sharded over GPUs - the random streams are keyed by
-        the global SN index, so a shard reproduces the single-GPU draws bit for bit."""
+        the reference after :1839-1848, extras dict).
+
+        Sharding (SNe are independent posteriors, so there is no data-path collective): with ``group`` (a
+        ``torch.distributed`` process group, one process per GPU) every rank fits the contiguous block
+        ``shard_bounds(N, rank, world)`` of ``obs`` and - with ``gather`` - the per-SN rows are all-gathered so
+        every rank returns the full arrays; without a group one process spreads the SNe over
+        ``min(num_devices, visible GPUs)`` devices.  ``sn_offset``: index of the first SN of ``obs`` in the
+        whole job - the random streams are keyed by the global SN index, so any sharding reproduces the
+        single-GPU draws bit for bit (for the same ``warps_per_chain``).
+
+        ``warps_per_chain`` (1, 2, 4, 8 or 'auto'): latency mode - K warps share the observations of one
+        (SN, chain); 'auto' picks the largest K whose warps still fit the GPU in one resident wave."""
         import torch
+        from .distributed import shard_bounds, gather_rows
+        obs = np.asarray(obs)
+        N = obs.shape[-1]
         rv_mode = self._rv_mode(RV)
-        ctx = self.prepare(obs, weights, band_inds, rv_mode, fix_tmax=bool(fix_tmax), fix_theta=bool(fix_theta),
-                           theta_val=float(theta_val), fix_AV=bool(fix_AV), AV_val=float(AV_val))
-        dev = f'cuda:{ctx.device}'
-        muhat = np.asarray(obs)[-3, 0, :]
-        if q_init is None:
-            q_init = ctx.init_to_median(num_chains, seed=seed, sn_offset=sn_offset)      # device kernel
-        out = ctx.nuts(q_init, num_warmup=num_warmup, num_samples=num_samples, max_tree_depth=max_tree_depth,
-                       seed=seed, sn_offset=sn_offset)
-        torch.cuda.synchronize()
-        cons = self.constrain(out['samples'], rv_mode)     # (N, C, S, ...)
+        fix = dict(fix_tmax=bool(fix_tmax), fix_theta=bool(fix_theta), theta_val=float(theta_val), fix_AV=bool(fix_AV),
+                   AV_val=float(AV_val))
+        kw = dict(num_warmup=num_warmup, num_samples=num_samples, max_tree_depth=max_tree_depth, seed=seed,
+                  warps_per_chain=warps_per_chain)
+        rank, world = 0, 1
+        if group is not None:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        lo, hi = shard_bounds(N, rank, world)
+        sl = lambda a, i0, i1: None if a is None else a[i0:i1]
+        devices = self._fit_devices(hi - lo) if (group is None and not return_device and q_init is None) else [self._device_index()]
+        runs = []
+        for d, dv in enumerate(devices):
+            l0, l1 = shard_bounds(hi - lo, d, len(devices))
+            l0, l1 = lo + l0, lo + l1
+            with torch.cuda.device(dv):
+                if len(devices) > 1:
+                    self._device = f'cuda:{dv}'
+                try:
+                    ctx = self.prepare(obs[:, :, l0:l1], sl(weights, l0, l1), band_inds, rv_mode, **fix)
+                finally:
+                    if len(devices) > 1:
+                        self._device = None
+                qi = q_init if q_init is not None else ctx.init_to_median(num_chains, seed=seed, sn_offset=sn_offset + l0)
+                out = ctx.nuts(qi, sn_offset=sn_offset + l0, **kw)           # asynchronous: the devices run concurrently
+            runs.append((ctx, out))
+        for ctx, out in runs:
+            torch.cuda.synchronize(ctx.device)
         if return_device:
-            return cons, out
+            ctx, out = runs[0]
+            return self.constrain(out['samples'], rv_mode), out
+        keys = None
+        parts = []
+        for ctx, out in runs:
+            cons = self.constrain(out['samples'], rv_mode)                   # (n, C, S[, dim]) on the device
+            cons['_stats'] = out['stats']
+            cons['_info'] = out['chain_info']
+            parts.append({k: v for k, v in cons.items()})
+        merged = {k: (torch.cat([p[k].to(parts[0][k].device) for p in parts], dim=0) if len(parts) > 1 else parts[0][k])
+                  for k in parts[0]}
+        if group is not None and world > 1 and gather:
+            merged = {k: gather_rows(v.contiguous(), N, group) for k, v in merged.items()}
+        stats_all = merged.pop('_stats').cpu().numpy()
+        info = merged.pop('_info').cpu().numpy()
         samples = {}
-        for k, v in cons.items():
+        for k, v in merged.items():
             v = v.cpu().numpy().astype(np.float64)
-            if v.ndim == 4:
-                samples[k] = v.transpose(1, 2, 3, 0) if k == 'eps' else v.transpose(1, 2, 0, 3)
-            else:
-                samples[k] = v.transpose(1, 2, 0)
-        stats = out['stats'][:, :, num_warmup:].cpu().numpy()
+            # reference :1846-1849: 4-D sites (N, C, S, dim) -> (C, S, dim, N), 3-D sites -> (C, S, N)
+            samples[k] = v.transpose(1, 2, 3, 0) if v.ndim == 4 else v.transpose(1, 2, 0)
+        stats = stats_all[:, :, num_warmup:]
         samples['diverging'] = stats[..., 2].transpose(1, 2, 0) > 0
         extras = {'accept_prob': stats[..., 0].transpose(1, 2, 0), 'num_steps': stats[..., 1].transpose(1, 2, 0),
                   'potential_energy': stats[..., 3].transpose(1, 2, 0),
-                  'chain_info': out['chain_info'].cpu().numpy(), 'launches': ctx.launches(),
-                  'all_stats': out['stats'].cpu().numpy()}
+                  'chain_info': info, 'launches': sum(c.launches() for c, _ in runs),
+                  'all_stats': stats_all, 'devices': [c.device for c, _ in runs], 'shard': (lo, hi)}
         return samples, extras
+
+    # ------------------------------------------------------------------ log densities (numpyro models of the reference)
+    def fit_model_globalRV(self, obs, weights, fix_tmax=False, fix_theta=False, theta_val=0, fix_AV=False, AV_val=0,
+                           band_inds=None):
+        """Reference :883-945.  The reference's method is a numpyro model (a callable the sampler traces); its
+        counterpart here is the bound log density: an object with ``logp_grad(q)`` ((N, C, D) unconstrained
+        positions -> log joint density incl. Jacobians (N, C) and its gradient), ``init_to_median(n_chains)``,
+        ``constrain(q)`` and ``nuts(q_init, ...)`` - what ``fit`` / ``fit_batch`` hand to the device sampler."""
+        return FitLogDensity(self, obs, weights, band_inds, native.RV_FIXED, fix_tmax, fix_theta, theta_val, fix_AV, AV_val)
+
+    def fit_model_popRV(self, obs, weights, fix_tmax=False, fix_theta=False, theta_val=0, fix_AV=False, AV_val=0,
+                        band_inds=None):
+        """Reference :996-1060 (R_V ~ truncated N(mu_R, sigma_R) per SN)."""
+        return FitLogDensity(self, obs, weights, band_inds, native.RV_POP, fix_tmax, fix_theta, theta_val, fix_AV, AV_val)
+
+    def fit_model_uniformRV(self, obs, weights, fix_tmax=False, fix_theta=False, theta_val=0, fix_AV=False, AV_val=0,
+                            band_inds=None):
+        """Reference :818-881 (R_V ~ U(1, 6) per SN)."""
+        return FitLogDensity(self, obs, weights, band_inds, native.RV_UNIFORM, fix_tmax, fix_theta, theta_val, fix_AV, AV_val)
+
+    def train_model_globalRV(self, obs, weights, band_inds=None):
+        """Reference :1115-1182: the joint training density; ``logp_grad(qg, ql[, group])`` evaluates it (and
+        its gradient) for unconstrained globals (C, G) and per-SN latents (N, C, Dl)."""
+        return TrainLogDensity(self, obs, weights, band_inds)
 
     def fit(self, t, flux, flux_err, filters, z, ebv_mw=0, peak_mjd=None, filt_map={}, print_summary=True,
             file_prefix=None, drop_bands=[], fix_tmax=False, fix_theta=False, fix_AV=False, RV=False, mu_R=False,
-            sigma_R=False, mag=False, seed=0):
-        """Reference :1994-2168 (4 chains x (250 + 250), max_tree_depth 10)."""
+            sigma_R=False, mag=False, seed=0, warps_per_chain='auto'):
+        """Reference :1994-2168 (4 chains x (250 + 250), max_tree_depth 10).  A single object is four chains on
+        a whole GPU: the sampler runs in latency mode (``warps_per_chain='auto'``)."""
         data, band_weights, band_inds = self.build_fit_data(t, flux, flux_err, filters, z, ebv_mw, peak_mjd,
                                                             filt_map, drop_bands, mag)
         rv_arg = None
@@ -420,8 +499,11 @@ class SEDmodel(object):
         samples, extras = self.fit_batch(data, band_weights, band_inds, num_chains=4, num_warmup=250,
                                          num_samples=250, max_tree_depth=10, seed=seed, RV=rv_arg,
                                          fix_tmax=fix_tmax, fix_theta=fix_theta, theta_val=theta_val, fix_AV=fix_AV,
-                                         AV_val=AV_val)
+                                         AV_val=AV_val, warps_per_chain=warps_per_chain)
         samples.pop('diverging')
+        # the plate of a single-object fit keeps eps_tform as (chains, draws, 1, n_eps) (example_fits.ipynb:166-197);
+        # the vmapped batch layout is (chains, draws, n_eps, N)
+        samples['eps_tform'] = samples['eps_tform'].transpose(0, 1, 3, 2)
         samples['potential_energy'] = extras['potential_energy'][..., 0]
         if print_summary:
             summary.print_summary({k: v for k, v in samples.items() if k not in ('potential_energy', 'eps')},
@@ -588,48 +670,117 @@ class SEDmodel(object):
         obs[9] = 1
         return obs, sim['band_weights'], sim['band_inds']
 
+    def chain_flux_device(self, t, band_lists, theta, AV, tmax, Ds, eps, zs, ebv_mws, RV=None, mag=False):
+        """Device core of ``get_flux_from_chains``: ONE kernel launch over (SN x draw x phase x band).
+        ``theta, AV, tmax, Ds`` (N, S) and ``eps`` (N, S, n_eps) are torch tensors on the model's device
+        (``Ds = mu + delM``, float64 welcome), ``band_lists`` one list of filter names per SN (or one list for
+        all).  Returns a (N, S, max_bands, len(t)) float32 device tensor."""
+        import torch
+        ctx = self._ctxs.get(('fwd',))
+        if ctx is None:
+            ctx = self._ctxs[('fwd',)] = self._context(native.RV_FIXED)
+        dev = f'cuda:{ctx.device}'
+        N = theta.shape[0]
+        if not isinstance(band_lists[0], (list, tuple, np.ndarray)):
+            band_lists = [list(band_lists)] * N
+        for bl in band_lists:
+            for b in bl:
+                if b not in self.band_dict:
+                    raise ValueError(f'{b} is not present in filters yaml file')
+        glob = [np.array([self.band_dict[b] for b in bl], dtype=np.int64) for bl in band_lists]
+        band_inds = np.unique(np.concatenate(glob))
+        max_bands = max(len(g) for g in glob)
+        local = np.full((N, max_bands), -1, dtype=np.int32)
+        used = np.zeros((N, len(band_inds)), dtype=bool)
+        for i, g in enumerate(glob):
+            loc = np.searchsorted(band_inds, g)
+            local[i, :len(g)] = loc
+            used[i, loc] = True
+        # distance: fold the SN's mean distance into its tile (float64), the kernel multiplies by 10^(-0.4 dD)
+        Ds = torch.as_tensor(Ds, device=dev).double()
+        fold = Ds.mean(dim=1)
+        dD = (Ds - fold[:, None]).float()
+        builder = packing.DeviceTileBuilder(ctx, self.filters, band_inds, self.RV_MW)
+        bscale = packing.band_log10_scale(self.zps[band_inds], self.offsets[band_inds])
+        zs = np.broadcast_to(np.atleast_1d(np.asarray(zs, dtype=np.float64)), (N,))
+        ebv_mws = np.broadcast_to(np.atleast_1d(np.asarray(ebv_mws, dtype=np.float64)), (N,))
+        sup, wt, store, wt_stride = packing.device_tiles(builder, zs, ebv_mws, used, fold.cpu().numpy() + self.M0,
+                                                         bscale, dev)
+        to = lambda a: torch.as_tensor(a, device=dev)
+        out = ctx.chain_flux(to(np.asarray(t, dtype=np.float32)), to(theta), to(AV), to(tmax), dD, to(eps),
+                             to(local), wt, sup, wt_stride, RV=None if RV is None else to(RV), mag=mag)
+        torch.cuda.synchronize()
+        del store
+        return out
+
     def get_flux_from_chains(self, t, bands, chains, zs, ebv_mws, mag=True, num_samples=None, mean=False):
         """Reference :3426-3524: model photometry for posterior samples,
-        (N_sne, num_samples, n_bands, len(t))."""
+        (N_sne, num_samples, n_bands, len(t)).  The reference loops over SNe through
+        ``simulate_light_curve`` (4.91 s per SN in its notebook); here all (SN, draw, phase, band) cells are
+        one kernel launch (``bayesn_chain_flux``).  Draw order and slicing follow the reference:
+        ``chains[k][..., i].flatten(order='F')[:num_samples]``; ``mean=True`` sets ``num_samples = 1`` BEFORE the
+        slice (:3474-3475, :3507-3511), so - like the reference - it evaluates the first draw."""
         if type(chains) == str:
             with open(chains, 'rb') as file:
                 chains = pickle.load(file)
-        N_sne = chains['theta'].shape[2]
+        th = np.asarray(chains['theta'])
+        C_, S_, N_sne = th.shape
+        tot = C_ * S_
         if num_samples is None:
-            num_samples = chains['theta'].shape[0] * chains['theta'].shape[1]
-        zs = np.atleast_1d(np.asarray(zs, dtype=float))
-        ebv_mws = np.atleast_1d(np.asarray(ebv_mws, dtype=float))
+            num_samples = tot
         if mean:
             num_samples = 1
-        band_list = isinstance(bands[0], list)
-        max_bands = max(len(b) for b in bands) if band_list else len(bands)
+        fl = lambda k: np.asarray(chains[k], dtype=np.float64).transpose(1, 0, 2).reshape(tot, N_sne)[:num_samples].T
+        eps = np.asarray(chains['eps'], dtype=np.float32)
+        eps = eps.transpose(1, 0, 2, 3).reshape(tot, eps.shape[2], N_sne)[:num_samples].transpose(2, 0, 1)
+        RV = fl('RV') if 'RV' in chains.keys() else None
         t = np.asarray(t, dtype=float)
-        flux_grid = np.zeros((N_sne, num_samples, max_bands, len(t)))
-        L, T = len(self.l_knots), len(self.tau_knots)
-        state = np.random.get_state()
-        for i in range(N_sne):
-            fit_bands = bands[i] if band_list else bands
-            fl = lambda k: chains[k][..., i].flatten(order='F')
-            theta, AV, tmax, mu, del_M = fl('theta'), fl('AV'), fl('tmax'), fl('mu'), fl('delM')
-            RV = fl('RV') if 'RV' in chains.keys() else None
-            eps = chains['eps'][..., i]
-            eps = eps.reshape((eps.shape[0] * eps.shape[1], eps.shape[2]), order='F')
-            eps = eps.reshape((eps.shape[0], L - 2, T), order='F')
-            eps_full = np.zeros((eps.shape[0], L, T))
-            eps_full[:, 1:-1, :] = eps
-            eps = eps_full
-            sl = slice(0, num_samples)
-            theta, AV, mu, eps, del_M, tmax = theta[sl], AV[sl], mu[sl], eps[sl], del_M[sl], tmax[sl]
-            if RV is not None:
-                RV = RV[sl]
-            if mean:
-                theta, AV, mu, eps, del_M, tmax = theta.mean()[None], AV.mean()[None], mu.mean()[None], \
-                    eps.mean(axis=0)[None], del_M.mean()[None], tmax.mean()[None]
-                if RV is not None:
-                    RV = RV.mean()[None]
-            lc, _, _ = self.simulate_light_curve(t, theta.shape[0], fit_bands, theta=theta, AV=AV, mu=mu, tmax=tmax,
-                                                 del_M=del_M, eps=eps, RV=RV, z=zs[i], write_to_files=False,
-                                                 ebv_mw=ebv_mws[i], yerr=0, mag=mag)
-            flux_grid[i, :, :len(fit_bands), :] = lc.T.reshape(num_samples, len(fit_bands), len(t))
-        np.random.set_state(state)
-        return flux_grid
+        out = self.chain_flux_device(t, bands, fl('theta'), fl('AV'), fl('tmax'), fl('mu') + fl('delM'),
+                                     np.ascontiguousarray(eps), zs, ebv_mws, RV=RV, mag=mag)
+        return out.cpu().numpy().astype(np.float64)
+
+
+class FitLogDensity:
+    """Bound per-object log density (see ``SEDmodel.fit_model_globalRV``)."""
+
+    def __init__(self, model, obs, weights, band_inds, rv_mode, fix_tmax, fix_theta, theta_val, fix_AV, AV_val):
+        self.model, self.rv_mode = model, rv_mode
+        self.ctx = model.prepare(obs, weights, band_inds, rv_mode, fix_tmax=bool(fix_tmax), fix_theta=bool(fix_theta),
+                                 theta_val=float(theta_val), fix_AV=bool(fix_AV), AV_val=float(AV_val))
+        self.N, self.D = self.ctx.N, self.ctx.D
+
+    def init_to_median(self, n_chains=4, seed=0, sn_offset=0):
+        return self.ctx.init_to_median(n_chains, seed=seed, sn_offset=sn_offset)
+
+    def logp_grad(self, q):
+        import torch
+        q = torch.as_tensor(q, dtype=torch.float32, device=f'cuda:{self.ctx.device}').contiguous()
+        return self.ctx.logp_grad(q)
+
+    def __call__(self, q):
+        return self.logp_grad(q)[0]
+
+    def constrain(self, q):
+        return self.model.constrain(q, self.rv_mode)
+
+    def nuts(self, q_init, **kw):
+        return self.ctx.nuts(q_init, **kw)
+
+
+class TrainLogDensity:
+    """Bound training log density (see ``SEDmodel.train_model_globalRV``)."""
+
+    def __init__(self, model, obs, weights, band_inds):
+        self.model = model
+        self.ctx = model.prepare_training(obs, weights, band_inds)
+        self.G, self.Dl, self.R = self.ctx.train_dims()
+
+    def logp_grad(self, qg, ql, group=None):
+        import torch
+        dev = f'cuda:{self.ctx.device}'
+        qg = torch.as_tensor(qg, dtype=torch.float32, device=dev).contiguous()
+        ql = torch.as_tensor(ql, dtype=torch.float32, device=dev).contiguous()
+        return self.ctx.train_logp_grad(qg, ql, group=group)
+
+    def __call__(self, qg, ql, group=None):
+        return self.logp_grad(qg, ql, group)[0]

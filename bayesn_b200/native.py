@@ -45,7 +45,8 @@ class NutsCfg(C.Structure):
     _fields_ = [('num_warmup', C.c_int32), ('num_samples', C.c_int32), ('num_chains', C.c_int32),
                 ('max_tree_depth', C.c_int32), ('target_accept', C.c_float), ('init_step_size', C.c_float),
                 ('adapt_step_size', C.c_int32), ('adapt_mass_matrix', C.c_int32),
-                ('regularize_mass_matrix', C.c_int32), ('seed', C.c_uint64), ('unit_offset', C.c_uint64)]
+                ('regularize_mass_matrix', C.c_int32), ('seed', C.c_uint64), ('unit_offset', C.c_uint64),
+                ('warps_per_chain', C.c_int32), ('reserved', C.c_int32)]
 
 
 EXPORTS = ['bayesn_abi_version', 'bayesn_ctx_create', 'bayesn_ctx_destroy', 'bayesn_last_error',
@@ -53,7 +54,8 @@ EXPORTS = ['bayesn_abi_version', 'bayesn_ctx_create', 'bayesn_ctx_destroy', 'bay
            'bayesn_flux_batch', 'bayesn_nuts_workspace_bytes', 'bayesn_nuts_fit', 'bayesn_launch_count',
            'bayesn_init_to_median', 'bayesn_ffma_peak', 'bayesn_train_dims', 'bayesn_train_begin',
            'bayesn_train_finish', 'bayesn_train_nuts_init', 'bayesn_train_nuts_sn', 'bayesn_train_nuts_ctl',
-           'bayesn_train_nuts_status', 'bayesn_tiles_support', 'bayesn_tiles_fill', 'bayesn_train_set_exchange', 'bayesn_spectra_batch']
+           'bayesn_train_nuts_status', 'bayesn_tiles_support', 'bayesn_tiles_fill', 'bayesn_train_set_exchange', 'bayesn_spectra_batch', 'bayesn_chain_flux',
+           'bayesn_logp_grad_fit_team']
 
 _lib = None
 
@@ -77,6 +79,7 @@ def load_library():
     lib.bayesn_bind_dataset.argtypes = [C.c_void_p, C.POINTER(DatasetDesc)]
     lib.bayesn_param_dim.argtypes = [C.c_void_p]
     lib.bayesn_logp_grad_fit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bayesn_logp_grad_fit_team.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bayesn_flux_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 12 + [
         C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
     lib.bayesn_nuts_workspace_bytes.argtypes = [C.c_void_p, C.POINTER(NutsCfg)]
@@ -87,6 +90,7 @@ def load_library():
     lib.bayesn_ffma_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.bayesn_launch_count.restype = C.c_longlong
     lib.bayesn_spectra_batch.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 10
+    lib.bayesn_chain_flux.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p] * 10 + [C.c_int, C.c_void_p, C.c_void_p]
     lib.bayesn_tiles_support.argtypes = [C.c_void_p, C.POINTER(TilesDesc), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bayesn_tiles_fill.argtypes = [C.c_void_p, C.POINTER(TilesDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.bayesn_train_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
@@ -198,7 +202,7 @@ class Context:
         self._check(self.lib.bayesn_ffma_peak(self.h, C.byref(v)), 'bayesn_ffma_peak')
         return float(v.value)
 
-    def logp_grad(self, q):
+    def logp_grad(self, q, warps_per_chain=1):
         """q: (N, C, D) float32 CUDA tensor -> (logp (N, C), grad (N, C, D))."""
         import torch
         assert q.is_cuda and q.dtype == torch.float32 and q.is_contiguous()
@@ -206,21 +210,42 @@ class Context:
         assert N == self.N and D == self.D
         logp = torch.empty((N, Cn), dtype=torch.float32, device=q.device)
         grad = torch.empty_like(q)
-        self._check(self.lib.bayesn_logp_grad_fit(self.h, Cn, q.data_ptr(), logp.data_ptr(), grad.data_ptr(),
-                                                  self._stream()), 'bayesn_logp_grad_fit')
+        self._check(self.lib.bayesn_logp_grad_fit_team(self.h, Cn, int(warps_per_chain), q.data_ptr(), logp.data_ptr(),
+                                                       grad.data_ptr(), self._stream()), 'bayesn_logp_grad_fit_team')
         return logp, grad
+
+    def resident_warps(self):
+        """Warp slots of the device for the sampler kernel (16 warps per SM at 128 registers)."""
+        import torch
+        return 16 * torch.cuda.get_device_properties(self.device).multi_processor_count
+
+    def auto_warps_per_chain(self, n_units):
+        """Latency mode width: the largest K in (8, 4, 2, 1) whose K * n_units warps still fit the device in
+        one resident wave - more warps per chain only pay while there are idle warp slots."""
+        slots = self.resident_warps()
+        for k in (8, 4, 2):
+            if n_units * k <= slots:
+                return k
+        return 1
 
     def nuts(self, q_init, num_warmup=250, num_samples=250, max_tree_depth=10, target_accept=0.8,
              init_step_size=1.0, adapt_step_size=True, adapt_mass_matrix=True, regularize_mass_matrix=True, seed=0,
-             out=None, sn_offset=0):
-        """Run the device NUTS for every (SN, chain).  Returns dict of CUDA tensors."""
+             out=None, sn_offset=0, warps_per_chain=1):
+        """Run the device NUTS for every (SN, chain).  Returns dict of CUDA tensors.  ``warps_per_chain``: 1
+        (throughput layout), 2 / 4 / 8 (latency mode) or 'auto'."""
         import torch
         assert q_init.is_cuda and q_init.dtype == torch.float32 and q_init.is_contiguous()
         N, Cn, D = q_init.shape
         assert N == self.N and D == self.D
+        if warps_per_chain == 'auto':
+            warps_per_chain = self.auto_warps_per_chain(N * Cn)
         cfg = NutsCfg(int(num_warmup), int(num_samples), int(Cn), int(max_tree_depth), float(target_accept),
                       float(init_step_size), int(adapt_step_size), int(adapt_mass_matrix),
-                      int(regularize_mass_matrix), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sn_offset) * int(Cn))
+                      int(regularize_mass_matrix), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sn_offset) * int(Cn),
+                      int(warps_per_chain), 0)
+        if out is None:
+            out = {}
+        out['warps_per_chain'] = int(warps_per_chain)
         wb = int(self.lib.bayesn_nuts_workspace_bytes(self.h, C.byref(cfg)))
         dev = q_init.device
         if out is None:
@@ -359,7 +384,7 @@ class Context:
         dev = qg0.device
         cfg = NutsCfg(int(num_warmup), int(num_samples), int(Cn), int(max_tree_depth), float(target_accept),
                       float(init_step_size), int(adapt_step_size), int(adapt_mass_matrix),
-                      int(regularize_mass_matrix), int(seed) & 0xFFFFFFFFFFFFFFFF, 0)
+                      int(regularize_mass_matrix), int(seed) & 0xFFFFFFFFFFFFFFFF, 0, 1, 0)
         out = dict(samples_g=torch.zeros((Cn, num_samples, G), dtype=torch.float32, device=dev),
                    samples_l=torch.zeros((N, Cn, num_samples, Dl), dtype=torch.float32, device=dev),
                    stats=torch.zeros((Cn, num_warmup + num_samples, 5), dtype=torch.float32, device=dev))
@@ -452,6 +477,27 @@ class Context:
                                                   W1.data_ptr(), eps.data_ptr(), RV.data_ptr(), J_t.data_ptr(),
                                                   hsiao_interp.data_ptr(), out.data_ptr(), self._stream()),
                     'bayesn_spectra_batch')
+        return out
+
+    def chain_flux(self, t, theta, AV, tmax, dD, eps, bands, weights, support, wt_stride, RV=None, mag=False):
+        """Model photometry of posterior draws (``get_flux_from_chains``, reference :3426-3524) in one
+        launch.  All arguments are CUDA tensors: ``t`` (n_t,), ``theta/AV/tmax/dD[/RV]`` (N, S), ``eps``
+        (N, S, n_eps), ``bands`` (N, max_bands) int32 tile rows (-1 = padding), ``weights`` / ``support`` the
+        compact tiles.  Returns (N, S, max_bands, n_t) float32."""
+        import torch
+        f32 = lambda a: a.to(torch.float32).contiguous()
+        t, theta, AV, tmax, dD, eps = map(f32, (t, theta, AV, tmax, dD, eps))
+        RVt = f32(RV) if RV is not None else None
+        bands = bands.to(torch.int32).contiguous()
+        N, S = theta.shape
+        assert eps.shape == (N, S, self.n_eps) and bands.shape[0] == N and support.shape[0] == N
+        n_t, max_bands, n_b = t.shape[0], bands.shape[1], support.shape[1]
+        out = torch.empty((N, S, max_bands, n_t), dtype=torch.float32, device=theta.device)
+        self._check(self.lib.bayesn_chain_flux(
+            self.h, N, S, n_t, max_bands, n_b, int(bool(mag)), int(RVt is not None), t.data_ptr(), theta.data_ptr(),
+            AV.data_ptr(), tmax.data_ptr(), dD.data_ptr(), RVt.data_ptr() if RVt is not None else None, eps.data_ptr(),
+            bands.data_ptr(), weights.data_ptr(), support.data_ptr(), int(wt_stride), out.data_ptr(), self._stream()),
+            'bayesn_chain_flux')
         return out
 
     def flux_batch(self, M0, theta, AV, W0, W1, eps, Ds, RV, band_indices, mask, J_t, hsiao_interp, weights,

@@ -29,24 +29,44 @@ def split_rhat_device(x):
     return torch.sqrt(var_plus / W)
 
 
-def device_fit_summary(model, cons, muhat, seed=0):
-    """``cons``: dict of constrained device tensors (N, C, S) from ``SEDmodel.constrain`` /
-    ``fit_batch(return_device=True)``.  Draws ``mu`` like the reference (:2250-2254; torch RNG on
-    the device instead of the unseeded numpy global) and returns a dict of (N,) numpy arrays:
-    MU_LCFIT, MUERR_LCFIT, THETA, THETAERR, AV, AVERR, MEANRHAT, MAXRHAT (+ TMAX, TMAXERR)."""
+MU_CHUNK = 1024
+
+
+def draw_mu_device(model, cons, muhat, seed=0, sn_offset=0):
+    """Distance-modulus draws of the reference's ``postprocess`` (:2248-2254): ``mu ~ N((Ds 25 + muhat sigma0^2) /
+    (25 + sigma0^2), sigma0^2 25 / (25 + sigma0^2))`` for every draw, ``delM = Ds - mu``; added to ``cons`` as
+    (N, C, S) device tensors.  The reference uses the unseeded global numpy RNG; here the noise is drawn on the
+    device in blocks of ``MU_CHUNK`` SNe keyed by (seed, global block index), so a shard of the data set
+    (``sn_offset``) gets the same draws as the whole."""
     import torch
     Ds = cons['Ds']
-    dev = Ds.device
-    mu_hat = torch.as_tensor(np.asarray(muhat, dtype=np.float32), device=dev)[:, None, None]
-    muhat_err = 5.0
-    s0 = float(model.sigma0)
-    Ds_err2 = muhat_err ** 2 + s0 ** 2
+    dev, (n, C, S) = Ds.device, Ds.shape
+    noise = torch.empty((n, C, S), dtype=torch.float32, device=dev)
     g = torch.Generator(device=dev)
-    g.manual_seed(int(seed))
-    mean = (Ds * muhat_err ** 2 + mu_hat * s0 ** 2) / Ds_err2
-    sd = math.sqrt(s0 ** 2 * muhat_err ** 2 / Ds_err2)
-    mu = mean + sd * torch.randn(Ds.shape, generator=g, device=dev, dtype=Ds.dtype)
-    sites = {'mu': mu, 'delM': Ds - mu, 'theta': cons['theta'], 'AV': cons['AV'], 'Ds': Ds}
+    first, last = sn_offset // MU_CHUNK, (sn_offset + max(n, 1) - 1) // MU_CHUNK
+    for b in range(first, last + 1):
+        g.manual_seed((int(seed) << 24) + b)
+        blk = torch.randn((MU_CHUNK, C, S), generator=g, device=dev, dtype=torch.float32)
+        lo, hi = max(b * MU_CHUNK, sn_offset), min((b + 1) * MU_CHUNK, sn_offset + n)
+        noise[lo - sn_offset:hi - sn_offset] = blk[lo - b * MU_CHUNK:hi - b * MU_CHUNK]
+    mu_hat = torch.as_tensor(np.asarray(muhat, dtype=np.float64), device=dev)[:, None, None]
+    s0, e2 = float(model.sigma0), 25.0
+    Dd = Ds.double()
+    cons['mu'] = ((Dd * e2 + mu_hat * s0 ** 2) / (e2 + s0 ** 2) + math.sqrt(s0 ** 2 * e2 / (e2 + s0 ** 2)) * noise.double())
+    cons['delM'] = Dd - cons['mu']
+    return cons
+
+
+def device_fit_summary(model, cons, muhat, seed=0, sn_offset=0):
+    """``cons``: dict of constrained device tensors (N, C, S) from ``SEDmodel.constrain`` /
+    ``fit_batch(return_device=True)``.  Uses the ``mu`` / ``delM`` draws in ``cons`` (``draw_mu_device`` adds them
+    when missing) and returns a dict of (N,) numpy arrays:
+    MU_LCFIT, MUERR_LCFIT, THETA, THETAERR, AV, AVERR, MEANRHAT, MAXRHAT (+ TMAX, TMAXERR)."""
+    import torch
+    if 'mu' not in cons:
+        draw_mu_device(model, cons, muhat, seed=seed, sn_offset=sn_offset)
+    mu, Ds = cons['mu'], cons['Ds']
+    sites = {'mu': mu, 'delM': cons['delM'], 'theta': cons['theta'], 'AV': cons['AV'], 'Ds': Ds}
     if 'tmax' in cons:
         sites['tmax'] = cons['tmax']
     # arviz.summary drops the *_tform sites for the FITRES r-hat columns (:2314-2316) but keeps eps
@@ -65,6 +85,16 @@ def device_fit_summary(model, cons, muhat, seed=0):
         out['TMAX'] = flat(cons['tmax']).mean(dim=1)
         out['TMAXERR'] = flat(cons['tmax']).std(dim=1, unbiased=False)
     return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def host_samples(cons):
+    """Device draws (N, C, S[, dim]) -> the reference's sample dict: (chains, draws, N) and, for the vector sites,
+    (chains, draws, dim, N) (:1839-1848)."""
+    out = {}
+    for k, v in cons.items():
+        v = v.cpu().numpy().astype(np.float64)
+        out[k] = v.transpose(1, 2, 3, 0) if v.ndim == 4 else v.transpose(1, 2, 0)
+    return out
 
 
 def write_fitres(path, sn_names, columns, version_photometry='NULL', snana_version='NULL'):
@@ -86,13 +116,14 @@ def write_fitres(path, sn_names, columns, version_photometry='NULL', snana_versi
 
 
 def postprocess_fits(model, cons, obs, sn_names=None, outputdir='.', outfile_prefix='output', seed=0,
-                     save_chains=False, extra_columns=None):
-    """Fitting branch of the reference's ``postprocess``: FITRES table (+ optionally ``chains.pkl``
-    with the full draws, which is the only step that copies them to the host)."""
+                     save_chains=False, extra_columns=None, sn_offset=0):
+    """Fitting branch of the reference's ``postprocess``: ``mu`` / ``delM`` draws, FITRES table (+ optionally
+    ``chains.pkl`` / ``fit_summary.csv`` with the full draws in the reference layout, which is the only step that
+    copies them to the host)."""
     obs = np.asarray(obs)
     N = obs.shape[-1]
     sn_names = [str(i) for i in range(N)] if sn_names is None else list(sn_names)
-    summ = device_fit_summary(model, cons, obs[-3, 0, :], seed=seed)
+    summ = device_fit_summary(model, cons, obs[-3, 0, :], seed=seed, sn_offset=sn_offset)
     cols = {'zHEL': obs[-5, 0, :], 'MWEBV': obs[-2, 0, :], 'MUHAT': obs[-3, 0, :]}
     if extra_columns:
         cols.update(extra_columns)
@@ -100,7 +131,14 @@ def postprocess_fits(model, cons, obs, sn_names=None, outputdir='.', outfile_pre
     os.makedirs(outputdir, exist_ok=True)
     dropped = write_fitres(os.path.join(outputdir, f'{outfile_prefix}.FITRES.TEXT'), sn_names, cols)
     if save_chains:
-        host = {k: v.cpu().numpy() for k, v in cons.items()}
-        with open(os.path.join(outputdir, 'chains.pkl'), 'wb') as fh:
-            pickle.dump(host, fh)
+        write_chains(host_samples(cons), outputdir)
     return cols, dropped
+
+
+def write_chains(samples, outputdir):
+    """``chains.pkl`` + ``fit_summary.csv`` (reference :2358-2364; arviz.summary -> bayesn_b200.summary)."""
+    from . import summary
+    keep = {k: v for k, v in samples.items() if k not in ('diverging', '_auto_latent')}
+    summary.summary_table(keep).to_csv(os.path.join(outputdir, 'fit_summary.csv'))
+    with open(os.path.join(outputdir, 'chains.pkl'), 'wb') as fh:
+        pickle.dump(samples, fh)

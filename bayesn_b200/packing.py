@@ -66,17 +66,25 @@ class DeviceTileBuilder:
         self.model_wave = np.ascontiguousarray(filters.grid.model_wave, dtype=np.float64)
         self.band_spacing = float(filters.grid.band_spacing)
         self.RV_MW = float(RV_MW)
+        self.max_redshift = float(getattr(filters.grid, 'max_redshift', 4))
         yk, _ = f99_yk(np.float64(RV_MW))
         self.xk, self.yk, self.mk = F99_XK.copy(), np.asarray(yk), inv_kd(F99_XK) @ yk
 
 
-def _tiles_on_device(builder, obs, used, fold, bscale, device):
-    """Compact tiles straight from (z, E(B-V)) on the GPU: no (N, 300, n_b) array anywhere."""
+def device_tiles(builder, z, ebv, used, fold, bscale, device):
+    """Compact tiles straight from (z, E(B-V)) on the GPU: no (N, 300, n_b) array anywhere.  ``used`` (N, n_b)
+    bool marks the band rows to build, ``fold`` (N,) is the per-SN exponent (magnitudes) folded into the rows
+    together with the band scale.  Returns (support (N, n_b, 4) int32 device tensor, tiles (N, wt_stride) view,
+    backing storage, wt_stride)."""
     import torch
     N, n_b = used.shape
+    z = np.asarray(z, dtype=np.float64)
+    if np.any(z > builder.max_redshift) or np.any(z <= -1):
+        raise ValueError(f'redshift outside the range covered by the band master curves (z <= {builder.max_redshift}, '
+                         f'reference :290)')
     f64 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
     bits = (used.astype(np.uint64) << np.arange(n_b, dtype=np.uint64)[None, :]).sum(axis=1).astype(np.uint32)
-    dev = dict(master=f64(builder.master), z=f64(obs[-5, 0, :]), ebv=f64(obs[-2, 0, :]), fold=f64(fold),
+    dev = dict(master=f64(builder.master), z=f64(z), ebv=f64(ebv), fold=f64(fold),
                bscale=f64(bscale), used=torch.as_tensor(bits.view(np.int32), device=device),
                model_wave=f64(builder.model_wave))
     sup = torch.zeros((N, n_b, 4), dtype=torch.int32, device=device)
@@ -88,6 +96,11 @@ def _tiles_on_device(builder, obs, used, fold, bscale, device):
     wt = wt_store[:N * wt_stride].view(N, wt_stride)
     builder.ctx.tiles_fill(desc, sup, wt_stride, wt)
     torch.cuda.synchronize()
+    return sup, wt, wt_store, wt_stride
+
+
+def _tiles_on_device(builder, obs, used, fold, bscale, device):
+    sup, wt, wt_store, wt_stride = device_tiles(builder, obs[-5, 0, :], obs[-2, 0, :], used, fold, bscale, device)
     return sup.cpu().numpy(), wt, wt_store, wt_stride
 
 

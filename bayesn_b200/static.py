@@ -16,6 +16,7 @@ from . import datafiles
 SPECTRUM_BINS = 300          # reference :295
 BAND_OVERSAMPLING = 51       # reference :296
 MAX_REDSHIFT = 4             # reference :297
+UV_LIMIT_AA = 2700.0         # below this rest wavelength the reference switches to the FM90 UV law (:627-638)
 C_AA_PER_S = 2.99792458e18   # astropy.constants.c in Angstrom/s (reference :391)
 C_KM_S = 299792.458
 ZPT = 27.5                   # reference :489
@@ -194,6 +195,14 @@ class ModelGrid:
     def __init__(self, l_knots, tau_knots):
         self.l_knots = np.asarray(l_knots, dtype=np.float64)
         self.tau_knots = np.asarray(tau_knots, dtype=np.float64)
+        self.max_redshift = MAX_REDSHIFT
+        if self.l_knots[0] < UV_LIMIT_AA:
+            # the FM90 UV branch of the host-dust law (reference get_spectra :627-638, rest wavelengths below
+            # 2700 A) is not built into the kernels: every shipped model starts at 2800 A or redder.  Refuse
+            # instead of silently applying the optical spline where the reference would not.
+            raise ValueError(f'l_knots[0] = {self.l_knots[0]:.1f} A is below {UV_LIMIT_AA:.0f} A: the Fitzpatrick99 UV '
+                             f'branch (reference bayesn_model.py:627-638) is not implemented in the sm_100a kernels; '
+                             f'models must start at >= {UV_LIMIT_AA:.0f} A rest frame')
         lo, hi = np.log10(self.l_knots[0]), np.log10(self.l_knots[-1])
         self.model_log_wave = np.linspace(lo, hi, SPECTRUM_BINS)
         self.model_spacing = self.model_log_wave[1] - self.model_log_wave[0]
@@ -273,6 +282,9 @@ class FilterSet:
         (reference ``_calculate_band_weights`` :499-554)."""
         z = np.atleast_1d(np.asarray(redshifts, dtype=np.float64))
         ebv = np.broadcast_to(np.atleast_1d(np.asarray(ebv, dtype=np.float64)), z.shape)
+        if np.any(z > MAX_REDSHIFT) or np.any(z <= -1):
+            raise ValueError(f'redshift outside the range covered by the band master curves (z <= {MAX_REDSHIFT}, '
+                             f'reference :290)')
         if band_inds is None:
             band_inds = np.arange(self.master.shape[0])
         band_inds = np.asarray(band_inds)

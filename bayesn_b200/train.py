@@ -97,12 +97,56 @@ def unconstrain(model, init, n_sne, rng=None):
     return qg, ql
 
 
+def prior_draw(model, obs, rng, sigma_pec=150 / 3e5):
+    """One draw of every site of ``train_model_globalRV`` from its prior (reference :1131-1177), constrained
+    values in the layout of :func:`initial_values` (the AV and Ds priors are conditional on the drawn tau_A /
+    sigma0, as a forward run of the numpyro model draws them).  L_Omega ~ LKJCholesky(eta = 1) through the C-vine:
+    the partial correlation of column j is 2 Beta(b_j, b_j) - 1 with b_j = 1 + (n - 2 - j) / 2, and those are
+    exactly the tanh(y) of the signed stick breaking."""
+    d = dims(model)
+    L, T, ne, n = d['L'], d['T'], d['n_eps'], obs.shape[-1]
+    tauA_t, sigma0_t = rng.uniform(0, HALF_PI), rng.uniform(0, HALF_PI)
+    tauA, sigma0 = math.tan(tauA_t), 0.1 * math.tan(sigma0_t)
+    ii, jj = np.tril_indices(ne, -1)
+    b = 1.0 + (ne - 2 - jj) / 2.0
+    r = 2.0 * rng.beta(b, b) - 1.0
+    zs, zerr = obs[-5, 0, :], obs[-4, 0, :]
+    muerr = 5 / (zs * math.log(10)) * np.sqrt(zerr ** 2 + sigma_pec ** 2)
+    return {'W0': rng.normal(0, 1, L * T), 'W1': rng.normal(0, 1, L * T), 'RV': rng.uniform(1, 5),
+            'tauA_tform': tauA_t, 'sigma0_tform': sigma0_t, 'theta': rng.normal(0, 1, n),
+            'AV': rng.exponential(tauA, n), 'sigmaepsilon_tform': rng.uniform(0, HALF_PI, ne),
+            '_y_corr': np.arctanh(np.clip(r, -1 + 1e-7, 1 - 1e-7)), 'eps_tform': rng.normal(0, 1, (n, ne)),
+            'Ds': rng.normal(obs[-3, 0, :], np.sqrt(muerr ** 2 + sigma0 ** 2))}
+
+
+def prior_position(model, obs, rng, how):
+    """``initialisation: median | sample`` (reference :1756-1759): numpyro's ``init_to_median`` (median of 15 prior
+    draws per site, taken in the constrained space - for L_Omega on the partial correlations, whose prior median is
+    the identity) or ``init_to_sample`` (one prior draw) -> (qg (G,), ql (N, Dl))."""
+    n = obs.shape[-1]
+    draws = [prior_draw(model, obs, rng) for _ in range(15 if how == 'median' else 1)]
+    init = {k: np.median(np.stack([np.asarray(dr[k], dtype=np.float64) for dr in draws]), axis=0) for k in draws[0]}
+    y = np.arctanh(np.median(np.stack([np.tanh(dr['_y_corr']) for dr in draws]), axis=0))
+    init['L_Omega'] = np.eye(dims(model)['n_eps'])
+    qg, ql = unconstrain(model, init, n, rng)
+    d = dims(model)
+    qg[2 * d['L'] * d['T'] + d['n_eps']:d['G'] - 3] = y
+    return qg, ql
+
+
 def initial_position(model, obs, num_chains=4, reference_model='M20_model', seed=0, device='cuda'):
-    """Same starting point for every chain (the reference notes numpyro cannot initialise chains
-    separately, :1572-1573): returns float32 CUDA tensors qg (C, G), ql (N, C, Dl)."""
+    """Starting point of the training chains: float32 CUDA tensors qg (C, G), ql (N, C, Dl).  A model name / yaml
+    path starts every chain from ``initial_guess`` (the reference notes numpyro cannot initialise chains
+    separately, :1572-1573); ``median`` / ``sample`` start every chain from its own prior median / draw
+    (:1756-1759)."""
     import torch
     rng = np.random.RandomState(seed)
     n = obs.shape[-1]
+    if reference_model in ('median', 'sample'):
+        pos = [prior_position(model, obs, np.random.RandomState(seed * 1000 + c), reference_model) for c in range(num_chains)]
+        qg_t = torch.tensor(np.stack([p[0] for p in pos]), dtype=torch.float32, device=device).contiguous()
+        ql_t = torch.tensor(np.stack([p[1] for p in pos], axis=1), dtype=torch.float32, device=device).contiguous()
+        return qg_t, ql_t
     qg, ql = unconstrain(model, initial_values(model, obs, reference_model, rng), n, rng)
     qg_t = torch.tensor(np.repeat(qg[None], num_chains, axis=0), dtype=torch.float32, device=device).contiguous()
     ql_t = torch.tensor(np.repeat(ql[:, None], num_chains, axis=1), dtype=torch.float32, device=device).contiguous()

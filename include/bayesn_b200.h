@@ -101,6 +101,12 @@ typedef struct {
     uint64_t unit_offset;   /* index of this data set's first (SN, chain) unit in the whole job (first SN *
                              * num_chains): random streams are keyed by the global unit, so sharding
                              * SNe over GPUs reproduces the single-GPU draws bit for bit */
+    int32_t warps_per_chain; /* latency mode: 0 / 1 = one warp per (SN, chain) (throughput layout); 2, 4, 8 = that
+                              * many warps share one chain's observation pairs and exchange their partial sums
+                              * through shared memory once per evaluation.  For few chains on a whole GPU (a single
+                              * fit(), small shards of a strong-scaled job).  Draws depend on the value (summation
+                              * order) but not on the sharding. */
+    int32_t reserved;
 } bayesn_nuts_cfg;
 
 int bayesn_ctx_create(int device, bayesn_ctx** out);
@@ -122,6 +128,9 @@ int bayesn_param_dim(bayesn_ctx* ctx);
  *   logp [N][n_chains]     device, out
  *   grad [N][n_chains][D]  device, out */
 int bayesn_logp_grad_fit(bayesn_ctx* ctx, int n_chains, const float* q, float* logp, float* grad, void* stream);
+/* The same evaluation in latency mode (warps_per_chain as in bayesn_nuts_cfg). */
+int bayesn_logp_grad_fit_team(bayesn_ctx* ctx, int n_chains, int warps_per_chain, const float* q, float* logp,
+                              float* grad, void* stream);
 
 /* Forward model only: SEDmodel.get_flux_batch (bayesn/bayesn_model.py:645-709) when mag == 0,
  * SEDmodel.get_mag_batch (:711-759) when mag != 0.  Same argument meaning and array layouts as
@@ -141,6 +150,22 @@ int bayesn_flux_batch(bayesn_ctx* ctx, int N, int N_obs, int n_b, int mag, float
 int bayesn_spectra_batch(bayesn_ctx* ctx, int N, int N_obs, const float* theta, const float* AV, const float* W0,
                          const float* W1, const float* eps, const float* RV, const float* J_t, const float* hsiao_interp,
                          float* out, void* stream);
+
+/* SEDmodel.get_flux_from_chains (bayesn/bayesn_model.py:3426-3524; called by postprocess :2269-2272 for the
+ * LCPLOT file): model photometry of posterior draws on a rest-frame phase grid, ONE launch over
+ * (SN x draw x phase x band) instead of the reference's per-SN loop through simulate_light_curve.
+ *   t        [n_t]            device, in   rest-frame phases
+ *   theta, AV, tmax, dD [N][S] device, in  per draw; dD = (mu + delM) - fold_s, the distance relative to the
+ *                                          exponent 10^(-0.4 (M0 + fold_s)) folded into the SN's weight tile
+ *   RV       [N][S]           device, in   per-draw R_V (rv_per_draw != 0: popRV / uniformRV chains), else NULL
+ *   eps      [N][S][n_eps]    device, in   the 'eps' site (L_Sigma eps_tform), element (l-1) + (L-2) m
+ *   bands    [N][max_bands]   device, in   for each SN the tile rows (band columns) to integrate, -1 = padding
+ *   weights, support, wt_stride            compact band-weight tiles as in bayesn_dataset_desc
+ *   out      [N][S][max_bands][n_t] device, out  FLUXCAL, or magnitudes when mag != 0 (0 for padded bands) */
+int bayesn_chain_flux(bayesn_ctx* ctx, int N, int S, int n_t, int max_bands, int n_b, int mag, int rv_per_draw,
+                      const float* t, const float* theta, const float* AV, const float* tmax, const float* dD,
+                      const float* RV, const float* eps, const int32_t* bands, const float* weights,
+                      const int32_t* support, int wt_stride, float* out, void* stream);
 
 /* Device-resident batched NUTS over every (SN, chain) of the bound data set: replaces the
  * numpyro MCMC(NUTS(fit_model_*)) runs at bayesn/bayesn_model.py:1830-1837 and :2128-2141.

@@ -4,6 +4,8 @@ itself pinned against the reference's only published numbers (``tests/test_oracl
 
     python tests/golden/make_golden.py            # logp/grad + flux vectors (seconds)
     python tests/golden/make_golden.py posterior  # C1 posterior with the oracle NUTS (~10-20 min)
+    python tests/golden/make_golden.py posterior_w22 [threads]   # 16 W22 ugrizYJH SNe (C3 recipe), ~1 h
+    python tests/golden/make_golden.py posterior_lsst [threads]  # 8 W22 ugrizy LSST SNe (C5 recipe), ~1 h
 """
 import json
 import os
@@ -75,6 +77,36 @@ def golden_posterior():
     print('done', res['seconds'], res['evals'])
 
 
+W22_POSTERIOR = {
+    'w22': dict(model_name='W22_model',
+                bands=['u_LSST', 'g_PS1', 'r_PS1', 'i_PS1', 'z_PS1', 'Y_WFCAM', 'J_WFCAM', 'H_WFCAM'],
+                t=np.array([-8.0, 2.0, 12.0, 22.0, 32.0]), N=16, seed=20241020, mask_some=False),
+    'lsst': dict(model_name='W22_model', bands=['u_LSST', 'g_LSST', 'r_LSST', 'i_LSST', 'z_LSST', 'y_LSST'],
+                 t=np.arange(-8, 40, 5.0), N=8, seed=20241021, mask_some=False, zrange=(0.02, 0.09)),
+}
+
+
+def golden_posterior_w22(which, threads=None):
+    """Oracle-sampler posteriors on the W22 model: the C3 recipe (ugrizYJH, 40 obs) and the C5 recipe
+    (LSST ugrizy, 60 obs), 4 x (250 + 250) each - the float64 counterpart of the shapes where the FP32
+    sampler needed its safeguard."""
+    from oracle import ref_fit
+    kw = W22_POSTERIOR[which]
+    case = make_case(**kw)
+    res = ref_fit.fit_cpu(case['ref'], case['obs'], case['weights'], n_chains=4, num_warmup=250, num_samples=250,
+                          seed=0, threads=threads)
+    c = ref_fit.constrain(case['ref'], res['samples'])
+    np.savez_compressed(os.path.join(HERE, f'{which}_oracle_posterior.npz'), obs=case['obs'],
+                        weights=case['weights'].astype(np.float32), z=case['z'], band_names=np.array(case['band_names']),
+                        theta=c['theta'].astype(np.float32), AV=c['AV'].astype(np.float32),
+                        tmax=c['tmax'].astype(np.float32), Ds=c['Ds'], n_steps=res['n_steps'], accept=res['accept'],
+                        diverging=res['diverging'], all_steps=res['all_steps'], seconds=res['seconds'],
+                        evals=res['evals'], ticks=res['ticks'], threads=threads or 0,
+                        true_theta=case['params']['theta'], true_AV=case['params']['AV'],
+                        true_mu=case['params']['mu'], true_delM=case['params']['del_M'])
+    print('done', which, res['seconds'], res['evals'])
+
+
 def golden_train():
     """Training log density (train_model_globalRV, unconstrained) and gradient at a seeded point."""
     from tests.test_gpu_train import training_point
@@ -93,6 +125,9 @@ def golden_train():
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'train':
         golden_train()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] in ('posterior_w22', 'posterior_lsst'):
+        golden_posterior_w22(sys.argv[1].split('_')[1], int(sys.argv[2]) if len(sys.argv) > 2 else None)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'posterior':
         golden_posterior()

@@ -19,7 +19,7 @@ def test_library_exports_every_symbol_in_header(built_library):
     assert {'bayesn_logp_grad_fit', 'bayesn_nuts_fit', 'bayesn_flux_batch', 'bayesn_set_model'} <= declared
     for name in declared:
         assert hasattr(built_library, name), name
-    assert built_library.bayesn_abi_version() == 1
+    assert built_library.bayesn_abi_version() == 2
     from bayesn_b200 import native
     assert set(native.EXPORTS) == declared
 
@@ -28,6 +28,15 @@ def test_library_is_sm100a_with_tma_and_no_tensor_fallback(built_library):
     from bayesn_b200 import native
     out = subprocess.run(['cuobjdump', '-lelf', native.LIB_PATH], capture_output=True, text=True).stdout
     assert 'sm_100a' in out
+    # the sampler kernel stages its tables with TMA bulk copies completed on an mbarrier (SASS: UBLKCP + SYNCS),
+    # and nothing in the library falls back to tensor-core MMA paths (the contractions are K <= 12: FP32 SIMT)
+    fns = re.findall(r'Function : (\S+)', subprocess.run(['cuobjdump', '-sass', native.LIB_PATH], capture_output=True,
+                                                           text=True).stdout)
+    fn = [f for f in fns if 'nuts_kernelILi11ELi6ELi2ELb0ELb1' in f][0]
+    sass = subprocess.run(['cuobjdump', '-sass', '-fun', fn, native.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'UBLKCP' in sass and 'SYNCS' in sass
+    assert 'BAR.SYNC' in sass or 'BAR.SYNC.DEFER_BLOCKING' in sass          # team barrier of the latency mode
+    assert not re.search(r'\b(HMMA|IMMA|UTCHMMA|UTCIMMA|WGMMA)\b', sass)
 
 
 def _sass_loops(path, mangled_substr):
