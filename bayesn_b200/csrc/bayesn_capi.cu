@@ -30,6 +30,7 @@ struct bayesn_ctx {
     XchgDev X{};                // peer-memory exchange of the training sums (world 1 = off)
     std::vector<void*> tn_owned;
     bool have_tn = false;
+    int train_kw = 1;           // warps per (SN, chain) unit of the last training SN launch
 };
 
 namespace {
@@ -272,17 +273,29 @@ template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
 int launch_train_nuts_sn(bayesn_ctx* ctx, cudaStream_t st) {
     if (RVFREE) return fail(ctx, -1, "training needs a fixed-RV model context (rv_mode = BAYESN_RV_FIXED)");
     const int C = ctx->T.C;
-    const int ntile = ntile_for(C);
-    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, false, STAGE, true);
+    const long long units = (long long)ctx->D.N * C;
+    // latency mode: when this rank's (SN, chain) units leave warp slots idle (SNe sharded over GPUs), kw warps
+    // share the observation pairs of each unit's one evaluation per pass; BAYESN_TRAIN_KW overrides (tests)
+    int kw = 1, sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    for (int k = WPB; k >= 2; k >>= 1)
+        if (units * k <= 16LL * sms) { kw = k; break; }
+    if (const char* e = getenv("BAYESN_TRAIN_KW")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= WPB && !(v & (v - 1))) kw = v;
+    }
+    ctx->train_kw = kw;
+    const int upc = WPB / kw;
+    const int ntile = ntile_for(C, upc);
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, false, STAGE, true, kw);
     const size_t bytes = (size_t)P.totalFloats * 4;
     constexpr int TVPL = (LP * TP - 2 * TP + 3 + 31) / 32;
     auto kern = train_nuts_sn_kernel<LP, TP, TVPL, STAGE>;
     if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
     if (ctx->TN.VPL != TVPL) return fail(ctx, -1, "internal: latent vector width mismatch");
     CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    const long long units = (long long)ctx->D.N * C;
-    const unsigned grid = (unsigned)((units + WPB - 1) / WPB);
-    kern<<<grid, WPB * 32, bytes, st>>>(ctx->M, ctx->D, ctx->T, ctx->TN, ntile);
+    const unsigned grid = (unsigned)((units + upc - 1) / upc);
+    kern<<<grid, WPB * 32, bytes, st>>>(team_model(ctx->M, kw, P), ctx->D, ctx->T, ctx->TN, ntile);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -369,6 +382,8 @@ const char* bayesn_last_error(bayesn_ctx* ctx) { return ctx ? ctx->err.c_str() :
 long long bayesn_launch_count(bayesn_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int bayesn_param_dim(bayesn_ctx* ctx) { return (ctx && ctx->have_model) ? ctx->M.D : -1; }
+
+int bayesn_train_warps_per_unit(bayesn_ctx* ctx) { return ctx ? ctx->train_kw : -1; }
 
 int bayesn_set_model(bayesn_ctx* ctx, const bayesn_model_desc* m) {
     if (!ctx || !m) return -1;

@@ -477,6 +477,25 @@ __device__ __forceinline__ void spline_row(float t, int T, const float* tau, con
     }
 }
 
+// sum_{j0 <= j < j1} col[(j - j0) * stride] * v[j]: one lane's share of a triangular L_Sigma mat-vec (lanes over
+// rows, the walk down a column is coalesced across the lanes).  Eight loads in flight and four independent FMA
+// chains: a lone warp (latency mode, small batches) no longer waits a full load latency per term - the single
+// chain cost ~30 cycles per multiply-add, 2 x 2 300 cycles per evaluation of a W22 fit (scripts/phase_timing.py).
+// j0 is a multiple of 4 and v 16-byte aligned.
+__device__ __forceinline__ float column_dot(const float* __restrict__ col, int stride, const float* __restrict__ v, int j0, int j1) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int j = j0;
+    for (; j + 8 <= j1; j += 8, col += 8 * stride) {
+        const float l0 = __ldg(col), l1 = __ldg(col + stride), l2 = __ldg(col + 2 * stride), l3 = __ldg(col + 3 * stride);
+        const float l4 = __ldg(col + 4 * stride), l5 = __ldg(col + 5 * stride), l6 = __ldg(col + 6 * stride), l7 = __ldg(col + 7 * stride);
+        const float4 e0 = *reinterpret_cast<const float4*>(v + j), e1 = *reinterpret_cast<const float4*>(v + j + 4);
+        a0 = fmaf(l0, e0.x, a0); a1 = fmaf(l1, e0.y, a1); a2 = fmaf(l2, e0.z, a2); a3 = fmaf(l3, e0.w, a3);
+        a0 = fmaf(l4, e1.x, a0); a1 = fmaf(l5, e1.y, a1); a2 = fmaf(l6, e1.z, a2); a3 = fmaf(l7, e1.w, a3);
+    }
+    for (; j < j1; ++j, col += stride) a0 = fmaf(__ldg(col), v[j], a0);
+    return (a0 + a1) + (a2 + a3);
+}
+
 // element i of a lane-strided vector (element i lives in lane i%32, slot i/32), broadcast
 template <int VPL>
 __device__ __forceinline__ float vget(const float (&v)[VPL], int i) {
@@ -550,13 +569,10 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     for (int i0 = 0; i0 < ne; i0 += 32) {
         const int i = i0 + lane;
         const int jend = (TRAIN || M.ls_lower) ? min(ne, i0 + 32) : ne;      // eps_i = sum_{j <= i} L[i][j] e_j
-        float acc = 0.f;
         if (i < ne) {
             // pointer walk: with the compile-time stride the unrolled loads use immediate offsets
             // (a 32-bit index j * lss cost two integer instructions per load)
-            const float* pc = c.LsT + i;
-            for (int j = 0; j < jend; ++j, pc += lss) acc = fmaf(__ldg(pc), c.ev[j], acc);
-            c.eps[i] = acc;
+            c.eps[i] = column_dot(c.LsT + i, lss, c.ev, 0, jend);
         }
     }
     __syncwarp();
@@ -909,11 +925,8 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         int i = lane + 32 * s;
         float gi = 0.f;
         if (i < ne) {
-            float acc = 0.f;
             const int j0 = (TRAIN || M.ls_lower) ? 32 * s : 0;
-            const float* pc = c.Ls + i + (size_t)j0 * lss;
-            for (int j = j0; j < ne; ++j, pc += lss) acc = fmaf(__ldg(pc), c.ev[j], acc);
-            gi = acc - q[s];
+            gi = column_dot(c.Ls + i + (size_t)j0 * lss, lss, c.ev, j0, ne) - q[s];
             ss = fmaf(q[s], q[s], ss);
         }
         grad[s] = gi;

@@ -90,6 +90,21 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) train_nuts_sn_kernel(
 #pragma unroll
     for (int s = 0; s < VPL; ++s) own[s] = (lane + 32 * s) < Dl;
     float z[VPL], r[VPL], g[VPL], im[VPL], t1[VPL], t2[VPL];
+    // Latency mode (M.kw > 1, used when the rank's SNe leave warp slots idle - a sharded training run): the
+    // team's first warp owns the latent slice (all vector bookkeeping below), hands the new position to its
+    // teammates through shared memory, and all kw warps share the observation pairs of the ONE evaluation of
+    // this pass (eval_logp_grad exchanges the partial sums); the teammates then leave.
+    const int tk = (threadIdx.x >> 5) & (M.kw - 1);
+    constexpr int XW = xchg_words(LP, TP);
+    const float eps = ctl.eps_dir;
+    float ke0 = 0.f;
+    if (tk != 0) {
+        if (act & ACT_DONE) return;
+        team_sync((threadIdx.x >> 5) >> M.kwl, M.kw);
+        const float* zs = c.sc - tk * M.xstride + M.xoff + XW;       // the leader's spare exchange buffer
+#pragma unroll
+        for (int s = 0; s < VPL; ++s) z[s] = own[s] ? zs[lane + 32 * s] : 0.f;
+    } else {
     io.ld(TV_IM, im);
 
     // ---- vector actions decided at the end of the previous pass ---------------------------------
@@ -136,7 +151,6 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) train_nuts_sn_kernel(
         }
     }
     if (act & ACT_DONE) return;
-    float ke0 = 0.f;
     if (act & ACT_NEW_TRANS) {
         // momentum refresh r ~ N(0, M) for this SN's latents; the stream is keyed by the global SN index
         const uint2 key = make_uint2(Nt.cfg.seed_lo, Nt.cfg.seed_hi);
@@ -164,12 +178,19 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) train_nuts_sn_kernel(
 
     // ---- one leapfrog step of the latent slice (its gradient only needs this SN) ----------------
     io.ld(TV_CZ, z); io.ld(TV_CR, r); io.ld(TV_CG, g);
-    const float eps = ctl.eps_dir;
 #pragma unroll
     for (int s = 0; s < VPL; ++s) {
         r[s] = fmaf(-0.5f * eps, g[s], r[s]);
         z[s] = fmaf(eps * im[s], r[s], z[s]);
     }
+    if (M.kw > 1) {
+        float* zs = c.sc + M.xoff + XW;
+#pragma unroll
+        for (int s = 0; s < VPL; ++s)
+            if (own[s]) zs[lane + 32 * s] = z[s];
+        team_sync((threadIdx.x >> 5) >> M.kwl, M.kw);
+    }
+    }   // tk == 0
     c.sW0 = Tr.W0 + (size_t)chain * Tr.LPTP;
     c.sW1 = Tr.W1 + (size_t)chain * Tr.LPTP;
     c.Ls = Tr.Ls + (size_t)chain * ne * ne;
@@ -183,6 +204,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) train_nuts_sn_kernel(
     c.part = part;
     double lp;
     eval_logp_grad<LP, TP, VPL, false, STAGE, true>(M, c, M.hs, z, lp, g, lane);
+    if (tk != 0) return;
 #pragma unroll
     for (int s = 0; s < VPL; ++s) {
         g[s] = -g[s];

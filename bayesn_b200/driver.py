@@ -207,6 +207,77 @@ def survey_id(survey):
     return 0
 
 
+def fit_dataset(model, ds, args, group=None):
+    """The array-level core of ``run(mode='fitting')`` (reference :1809-1849 + ``postprocess`` :2247-2364): NUTS fits of
+    every SN of ``ds`` (``obs`` (10, N_obs, N), ``band_inds``, ``sn_names``, ``peak_mjds``, optional ``lcplot`` /
+    ``fitres`` frames), device-side summaries, FITRES / LCPLOT / chains files written by rank 0.
+
+    With ``group`` the SNe are sharded over the ranks.  ``ds['obs']`` is either the whole data set on every rank
+    (each takes ``shard_bounds(N, rank, world)``) or - ``ds['shard'] = (lo, hi, N)`` - already this rank's block
+    (LSST-sized jobs simulate / read only their own block).  Returns (samples, rows dropped from FITRES)."""
+    import torch
+    from . import outputs
+    from .distributed import shard_bounds, gather_rows
+    rank, world = 0, 1
+    if group is not None:
+        rank, world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
+    if 'shard' in ds:
+        lo, hi, N = ds['shard']
+        obs_loc = ds['obs']
+    else:
+        N = ds['obs'].shape[-1]
+        lo, hi = shard_bounds(N, rank, world)
+        obs_loc = ds['obs'][:, :, lo:hi]
+    t_fit = time.time()
+    cons, raw = model.fit_batch(obs_loc, None, ds['band_inds'], num_chains=args['num_chains'],
+                                num_warmup=args['num_warmup'], num_samples=args['num_samples'], max_tree_depth=10,
+                                seed=args.get('seed', 0), return_device=True, sn_offset=lo,
+                                warps_per_chain=args.get('warps_per_chain', 'auto'))
+    ds['timing'] = {'fit_batch_s': time.time() - t_fit, 'leapfrogs': float(raw['chain_info'][..., 2].sum()),
+                    'divergences': float(raw['chain_info'][..., 3].sum()), 'warps_per_chain': raw.get('warps_per_chain', 1)}
+    muhat = obs_loc[7, 0, :]
+    outputs.draw_mu_device(model, cons, muhat, seed=args.get('seed', 0), sn_offset=lo)          # reference :2250-2254
+    summ = outputs.device_fit_summary(model, cons, muhat)
+    keys = list(summ.keys())
+    rows = np.stack([summ[k] for k in keys], axis=1)
+    meta = np.stack([obs_loc[5, 0, :], obs_loc[8, 0, :], obs_loc[7, 0, :]], axis=1)      # zHEL, MWEBV, MUHAT
+    # the LCPLOT table needs the photometry frames of process_dataset (not kept for pre-sharded array input)
+    want_lcplot = args.get('lcplot', True) and ds.get('lcplot') is not None and 'shard' not in ds
+    if want_lcplot:
+        t, fm, fe = lcplot_curves(model, ds, cons, lo, hi, args.get('save_fit_errors', False))
+    if world > 1:
+        dev = cons['Ds'].device
+        g = lambda a: gather_rows(torch.as_tensor(np.ascontiguousarray(a), device=dev), N, group).cpu().numpy()
+        rows, meta = g(rows), g(meta)
+        if want_lcplot:
+            fm, fe = g(fm), g(fe)
+    want_chains = args.get('save_chains', True) and not args.get('snana', False)
+    if want_chains or world == 1:
+        full = {k: (gather_rows(v.contiguous(), N, group) if world > 1 else v) for k, v in cons.items()}
+        samples = outputs.host_samples(full) if (want_chains or args.get('return_samples', True)) else {}
+        if 'tmax' in samples and ds.get('peak_mjds') is not None and len(ds['peak_mjds']) == N:
+            samples['peak_MJD'] = ds['peak_mjds'][None, None, :] + samples['tmax'] * (1 + meta[:, 0][None, None, :])
+    else:
+        samples = outputs.host_samples(cons) if args.get('return_samples', True) else {}      # this rank's block only
+    drop_count = 0
+    if rank == 0:
+        cols = {'zHEL': meta[:, 0], 'MWEBV': meta[:, 1], 'MUHAT': meta[:, 2]}
+        cols.update({k: v for k, v in (ds.get('fitres') or {}).items() if k not in ('zHEL', 'MWEBV')})
+        cols.update({k: rows[:, i] for i, k in enumerate(keys)})
+        pre = args['outfile_prefix']
+        base = pre if os.path.isabs(pre) else os.path.join(args['outputdir'], pre)
+        os.makedirs(os.path.dirname(base) or '.', exist_ok=True)
+        names = ds.get('sn_names') or [str(i) for i in range(N)]
+        drop_count = outputs.write_fitres(base + '.FITRES.TEXT', names, cols,
+                                          version_photometry=args.get('version_photometry', 'NULL'))
+        if want_lcplot:
+            write_lcplot(model, base + '.LCPLOT', ds, t, fm, fe)
+        if want_chains:
+            outputs.write_chains(samples, args['outputdir'])
+        ds['fitres_columns'] = cols
+    return samples, drop_count
+
+
 def run(model, args, cmd_args=None, group=None):
     """Reference ``SEDmodel.run`` for ``mode: fitting`` (per-object NUTS fits of every SN in the data
     set, :1809-1849) and ``mode: training_globalRV`` (:1766-1770, :1913-1924).  Returns the samples
@@ -220,8 +291,6 @@ def run(model, args, cmd_args=None, group=None):
     LSST-sized jobs: 100k SNe are 23 GB of draws)."""
     import torch
     import yaml
-    from . import outputs
-    from .distributed import shard_bounds, gather_rows
     args = parse_yaml_input(model, args, cmd_args)
     mode = args['mode'].lower()
     rank, world = 0, 1
@@ -240,42 +309,7 @@ def run(model, args, cmd_args=None, group=None):
     start = time.time()
     drop_count = 0
     if mode == 'fitting':
-        N = ds['obs'].shape[-1]
-        lo, hi = shard_bounds(N, rank, world)
-        cons, raw = model.fit_batch(ds['obs'][:, :, lo:hi], None, ds['band_inds'], num_chains=args['num_chains'],
-                                    num_warmup=args['num_warmup'], num_samples=args['num_samples'], max_tree_depth=10,
-                                    seed=0, return_device=True, sn_offset=lo, warps_per_chain=args['warps_per_chain'])
-        muhat = ds['obs'][7, 0, lo:hi]
-        outputs.draw_mu_device(model, cons, muhat, seed=0, sn_offset=lo)          # reference :2250-2254
-        summ = outputs.device_fit_summary(model, cons, muhat)
-        t, fm, fe = lcplot_curves(model, ds, cons, lo, hi, args['save_fit_errors'])
-        keys = list(summ.keys())
-        rows = np.stack([summ[k] for k in keys], axis=1)
-        if world > 1:
-            dev = cons['Ds'].device
-            g = lambda a: gather_rows(torch.as_tensor(np.ascontiguousarray(a), device=dev), N, group).cpu().numpy()
-            rows, fm, fe = g(rows), g(fm), g(fe)
-        samples = None
-        want_chains = args['save_chains'] and not args['snana']
-        if want_chains or world == 1:
-            full = {k: (gather_rows(v.contiguous(), N, group) if world > 1 else v) for k, v in cons.items()}
-            samples = outputs.host_samples(full)
-            if 'tmax' in samples:
-                samples['peak_MJD'] = ds['peak_mjds'][None, None, :] + samples['tmax'] * (1 + ds['obs'][5, 0, :][None, None, :])
-        else:
-            samples = outputs.host_samples(cons)           # this rank's shard only
-        if rank == 0:
-            cols = {'zHEL': ds['obs'][5, 0, :], 'MWEBV': ds['obs'][8, 0, :], 'MUHAT': ds['obs'][7, 0, :]}
-            cols.update({k: v for k, v in ds['fitres'].items() if k not in ('zHEL', 'MWEBV')})
-            cols.update({k: rows[:, i] for i, k in enumerate(keys)})
-            pre = args['outfile_prefix']
-            base = pre if os.path.isabs(pre) else os.path.join(args['outputdir'], pre)
-            os.makedirs(os.path.dirname(base) or '.', exist_ok=True)
-            drop_count = outputs.write_fitres(base + '.FITRES.TEXT', ds['sn_names'], cols,
-                                              version_photometry=args.get('version_photometry', 'NULL'))
-            write_lcplot(model, base + '.LCPLOT', ds, t, fm, fe)
-            if want_chains:
-                outputs.write_chains(samples, args['outputdir'])
+        samples, drop_count = fit_dataset(model, ds, args, group)
     elif mode == 'training_globalrv':
         init = args['initialisation']
         samples, _ = model.train(ds['obs'], None, ds['band_inds'], num_chains=args['num_chains'],

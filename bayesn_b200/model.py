@@ -435,16 +435,21 @@ class SEDmodel(object):
         stats_all = merged.pop('_stats').cpu().numpy()
         info = merged.pop('_info').cpu().numpy()
         samples = {}
+        d2h = stats_all.nbytes + info.nbytes
         for k, v in merged.items():
-            v = v.cpu().numpy().astype(np.float64)
-            # reference :1846-1849: 4-D sites (N, C, S, dim) -> (C, S, dim, N), 3-D sites -> (C, S, N)
-            samples[k] = v.transpose(1, 2, 3, 0) if v.ndim == 4 else v.transpose(1, 2, 0)
+            # reference :1846-1849: 4-D sites (N, C, S, dim) -> (C, S, dim, N), 3-D sites -> (C, S, N); the
+            # transposition and the float64 widening run on the device, the host receives the final layout
+            v = v.permute(1, 2, 3, 0) if v.ndim == 4 else v.permute(1, 2, 0)
+            samples[k] = v.contiguous().double().cpu().numpy()
+            d2h += samples[k].nbytes
         stats = stats_all[:, :, num_warmup:]
         samples['diverging'] = stats[..., 2].transpose(1, 2, 0) > 0
         extras = {'accept_prob': stats[..., 0].transpose(1, 2, 0), 'num_steps': stats[..., 1].transpose(1, 2, 0),
                   'potential_energy': stats[..., 3].transpose(1, 2, 0),
                   'chain_info': info, 'launches': sum(c.launches() for c, _ in runs),
-                  'all_stats': stats_all, 'devices': [c.device for c, _ in runs], 'shard': (lo, hi)}
+                  'all_stats': stats_all, 'devices': [c.device for c, _ in runs], 'shard': (lo, hi),
+                  'warps_per_chain': runs[0][1].get('warps_per_chain', 1), 'd2h_bytes': int(d2h),
+                  'h2d_bytes': int(sum(c._keep['data']['h2d_bytes'][0] for c, _ in runs))}
         return samples, extras
 
     # ------------------------------------------------------------------ log densities (numpyro models of the reference)

@@ -55,7 +55,7 @@ EXPORTS = ['bayesn_abi_version', 'bayesn_ctx_create', 'bayesn_ctx_destroy', 'bay
            'bayesn_init_to_median', 'bayesn_ffma_peak', 'bayesn_train_dims', 'bayesn_train_begin',
            'bayesn_train_finish', 'bayesn_train_nuts_init', 'bayesn_train_nuts_sn', 'bayesn_train_nuts_ctl',
            'bayesn_train_nuts_status', 'bayesn_tiles_support', 'bayesn_tiles_fill', 'bayesn_train_set_exchange', 'bayesn_spectra_batch', 'bayesn_chain_flux',
-           'bayesn_logp_grad_fit_team']
+           'bayesn_logp_grad_fit_team', 'bayesn_train_warps_per_unit']
 
 _lib = None
 
@@ -99,6 +99,7 @@ def load_library():
     lib.bayesn_train_nuts_init.argtypes = [C.c_void_p, C.POINTER(NutsCfg), C.c_int] + [C.c_void_p] * 6
     lib.bayesn_train_nuts_sn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bayesn_train_nuts_ctl.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bayesn_train_warps_per_unit.argtypes = [C.c_void_p]
     lib.bayesn_train_nuts_status.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
     lib.bayesn_train_set_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                               C.c_void_p]
@@ -459,6 +460,7 @@ class Context:
         out['info'] = np.ctypeslib.as_array(status).reshape(Cn, 8).copy()
         out['passes'] = passes
         out['finished'] = bool(done)
+        out['warps_per_unit'] = int(self.lib.bayesn_train_warps_per_unit(self.h))
         if peer:
             if self.train_exchange_error():
                 raise RuntimeError('peer-memory exchange timed out waiting for a rank')

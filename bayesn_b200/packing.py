@@ -82,7 +82,12 @@ def device_tiles(builder, z, ebv, used, fold, bscale, device):
     if np.any(z > builder.max_redshift) or np.any(z <= -1):
         raise ValueError(f'redshift outside the range covered by the band master curves (z <= {builder.max_redshift}, '
                          f'reference :290)')
-    f64 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
+    nbytes = [0]
+
+    def f64(a):
+        a = np.array(a, dtype=np.float64, order='C')          # a writable copy (inputs may be broadcast views)
+        nbytes[0] += a.nbytes
+        return torch.as_tensor(a, device=device)
     bits = (used.astype(np.uint64) << np.arange(n_b, dtype=np.uint64)[None, :]).sum(axis=1).astype(np.uint32)
     dev = dict(master=f64(builder.master), z=f64(z), ebv=f64(ebv), fold=f64(fold),
                bscale=f64(bscale), used=torch.as_tensor(bits.view(np.int32), device=device),
@@ -96,6 +101,7 @@ def device_tiles(builder, z, ebv, used, fold, bscale, device):
     wt = wt_store[:N * wt_stride].view(N, wt_stride)
     builder.ctx.tiles_fill(desc, sup, wt_stride, wt)
     torch.cuda.synchronize()
+    builder.h2d_bytes = nbytes[0] + bits.nbytes
     return sup, wt, wt_store, wt_stride
 
 
@@ -181,9 +187,14 @@ def pack_dataset(obs, weights, zps, offsets, M0, Ds_prior_sd, tauA, n_eps, devic
     else:
         lconst += -half_l2pi * (1 + n_eps) - math.log(tauA) - math.log(Ds_prior_sd) - half_l2pi
         muhat_err2 = None
-    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    h2d = [int(getattr(builder, 'h2d_bytes', 0)) if weights is None else int(wt.numel() * 4)]
+
+    def to(a):
+        a = np.ascontiguousarray(a)
+        h2d[0] += a.nbytes
+        return torch.from_numpy(a).to(device)
     return dict(N=N, N_obs=N_obs, n_b=n_b, wt_stride=wt_stride, obs4=to(obs4), n_valid=to(n_valid), weights=wt,
                 support=to(np.ascontiguousarray(sup_h)),
                 muhat=to(muhat.astype(np.float32)), lconst=to(lconst.astype(np.float32)),
                 muhat64=muhat, order=order, _weights_storage=wt_store,
-                muhat_err2=None if muhat_err2 is None else to(muhat_err2.astype(np.float32)))
+                muhat_err2=None if muhat_err2 is None else to(muhat_err2.astype(np.float32)), h2d_bytes=h2d)

@@ -225,6 +225,9 @@ int bayesn_train_finish(bayesn_ctx* ctx, int n_chains, const float* qg, double* 
 int bayesn_train_nuts_init(bayesn_ctx* ctx, const bayesn_nuts_cfg* cfg, int sn_offset, const float* qg0,
                            const float* ql0, float* samples_g, float* samples_l, float* stats, void* stream);
 int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream);
+/* warps per (SN, chain) unit the last bayesn_train_nuts_sn launch used (latency mode of the training SN kernel:
+ * chosen from the number of units on this rank, 1 when they fill the GPU) */
+int bayesn_train_warps_per_unit(bayesn_ctx* ctx);
 int bayesn_train_nuts_ctl(bayesn_ctx* ctx, double* red, void* stream);
 
 /* Fused exchange of the per-leapfrog training sums over NVLink peer memory, replacing the caller's

@@ -444,7 +444,7 @@ def test_run_fitting_from_snana_text_directory(tmp_path):
     interp = np.interp(dat.MJD.values, fit.MJD.values, fit.FLUXCAL.values)
     assert np.median(np.abs(interp / dat.FLUXCAL.values - 1)) < 0.06
     chains = pickle.load(open(out / 'chains.pkl', 'rb'))
-    assert chains['AV'].shape == (N, 4, 100)
+    assert chains['AV'].shape == (4, 100, N) and chains['mu'].shape == (4, 100, N)
 
 
 def test_get_flux_from_chains_shapes_and_values():

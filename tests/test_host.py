@@ -302,3 +302,48 @@ def test_parse_yaml_input_defaults_and_errors(tmp_path):
         driver.parse_yaml_input(m, {'mode': 'fitting', 'fit_method': 'VI', 'outputdir': str(tmp_path)})
     with pytest.raises(ValueError):
         driver.process_dataset(m, {'mode': 'fitting'})
+
+
+def test_mu_draws_do_not_depend_on_the_sharding():
+    """postprocess draws mu ~ N(.., ..) per posterior draw (reference :2250-2254); the noise is keyed by
+    (seed, global block of SNe), so a rank's block of a sharded job gets exactly the draws of the unsharded run."""
+    from bayesn_b200 import outputs
+
+    class M:
+        sigma0 = 0.1
+    g = torch.Generator().manual_seed(0)
+    N, C, S = 2500, 2, 5
+    Ds = 35 + torch.randn((N, C, S), generator=g)
+    muhat = 35 + np.arange(N) * 1e-3
+    full = outputs.draw_mu_device(M, {'Ds': Ds}, muhat, seed=3)
+    for lo, hi in ((0, 700), (700, 1100), (1100, 2500)):
+        part = outputs.draw_mu_device(M, {'Ds': Ds[lo:hi]}, muhat[lo:hi], seed=3, sn_offset=lo)
+        assert torch.equal(part['mu'], full['mu'][lo:hi]) and torch.equal(part['delM'], full['delM'][lo:hi])
+    # the conditional of mu given Ds: mean (25 Ds + s0^2 muhat) / (25 + s0^2), sd s0 5 / sqrt(25 + s0^2)
+    resid = (full['mu'] - (25 * Ds.double() + 0.01 * torch.as_tensor(muhat)[:, None, None]) / 25.01)
+    assert abs(float(resid.std()) - 0.1 * 5 / np.sqrt(25.01)) < 2e-3 and abs(float(resid.mean())) < 2e-3
+
+
+def test_training_prior_initialisation_modes():
+    """initialisation: median | sample for training (reference :1756-1759): finite unconstrained positions, a
+    different one per chain, L_Omega at the identity for the median."""
+    from bayesn_b200 import train as btrain
+
+    class M:
+        l_knots = np.linspace(3000., 18000., 6)
+        tau_knots = np.linspace(-10., 40., 6)
+    d = btrain.dims(M)
+    rng = np.random.RandomState(0)
+    obs = np.zeros((10, 4, 7))
+    obs[-5] = rng.uniform(0.02, 0.08, 7)[None]
+    obs[-4] = 1e-4
+    obs[-3] = 35.0
+    for how in ('median', 'sample'):
+        qg, ql = btrain.prior_position(M, obs, np.random.RandomState(1), how)
+        assert qg.shape == (d['G'],) and ql.shape == (7, d['Dl']) and np.all(np.isfinite(qg)) and np.all(np.isfinite(ql))
+        qg2, _ = btrain.prior_position(M, obs, np.random.RandomState(2), how)
+        assert not np.allclose(qg, qg2)
+    qg, _ = btrain.prior_position(M, obs, np.random.RandomState(1), 'median')
+    ne = d['n_eps']
+    y = qg[2 * 36 + ne:d['G'] - 3]
+    assert np.max(np.abs(y)) < 0.6 and np.max(np.abs(qg[:72])) < 1.0          # medians of 15 draws sit near the prior medians
