@@ -294,8 +294,8 @@ def run(model, args, cmd_args=None, group=None):
     args = parse_yaml_input(model, args, cmd_args)
     mode = args['mode'].lower()
     rank, world = 0, 1
-    if group is None and torch.distributed.is_available() and torch.distributed.is_initialized() \
-            and torch.distributed.get_world_size() > 1:
+    if group is None and args.get('distributed', True) and torch.distributed.is_available() \
+            and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
         group = torch.distributed.group.WORLD
     if group is not None:
         rank, world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)

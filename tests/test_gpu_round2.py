@@ -406,3 +406,17 @@ def test_in_process_multi_device_fit_matches_single_device():
     assert e2['devices'] == [0, 1]
     for k in s1:
         assert np.array_equal(s1[k], s2[k]), k
+
+
+def test_sharded_run_under_torchrun_matches_single_gpu(tmp_path):
+    """SEDmodel.run(mode='fitting') with the SNe sharded over 2 ranks (torchrun, NCCL) against one GPU: identical
+    draws, FITRES, chains.pkl (needs >= 2 GPUs; scripts/sharded_run_check.py)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(HERE)
+    p = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+                        '127.0.0.1', '--master-port', '29519', os.path.join(root, 'scripts', 'sharded_run_check.py'), str(tmp_path)],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and 'SHARDED_RUN_CHECK OK' in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]

@@ -203,3 +203,25 @@ def test_training_recovers_the_generating_model():
     assert np.sqrt((z ** 2).mean()) < 2.5 and np.abs(z).max() < 5, z
     assert samples['theta'].shape == (4, S, 100) and samples['eps'].shape == (4, S, m.n_eps, 100)
     assert samples['L_Omega'].shape == (4, S, m.n_eps, m.n_eps)
+
+
+@pytest.mark.parametrize('K', [2, 4, 8])
+def test_train_sn_kernel_latency_mode_matches_one_warp_per_unit(K, monkeypatch):
+    """Latency mode of the training SN kernel (K warps share the observation pairs of a unit's evaluation; used
+    when a rank's SNe leave warp slots idle): same trees as one warp per unit for the first transitions, finite
+    draws, and the whole run agrees statistically (acceptance)."""
+    case, ref, m, ctx, qg32, ql32 = _small_training_problem(N=5, C=2, seed=9)
+    kw = dict(num_warmup=0, num_samples=6, max_tree_depth=5, init_step_size=0.004, adapt_step_size=False,
+              adapt_mass_matrix=False, seed=11, passes_per_graph=8)
+    monkeypatch.setenv('BAYESN_TRAIN_KW', '1')
+    o1 = ctx.train_nuts(qg32, ql32, **kw)
+    assert o1['warps_per_unit'] == 1
+    monkeypatch.setenv('BAYESN_TRAIN_KW', str(K))
+    ok = ctx.train_nuts(qg32, ql32, **kw)
+    assert ok['warps_per_unit'] == K and ok['finished']
+    for k in ('samples_g', 'samples_l', 'stats'):
+        assert torch.isfinite(ok[k]).all(), k
+    s1, sk = o1['stats'].cpu().numpy(), ok['stats'].cpu().numpy()
+    assert np.array_equal(s1[:, :3, 1], sk[:, :3, 1]), (s1[:, :, 1], sk[:, :, 1])       # leapfrogs per transition
+    assert np.allclose(s1[:, :3, 3], sk[:, :3, 3], rtol=1e-5)                            # potential energy
+    assert float((o1['samples_g'][:, :3] - ok['samples_g'][:, :3]).abs().max()) < 5e-3
