@@ -227,7 +227,8 @@ int dispatch(bayesn_ctx* ctx, bool stage, F&& f) {
     BAYESN_CASE(10, 9, 3)
     BAYESN_CASE(12, 10, 4)
 #undef BAYESN_CASE
-    return fail(ctx, -4, "no kernel instantiation for this model shape");
+    return fail(ctx, -4, "no kernel instantiation for this model shape (compiled: L<=6,T<=6,D<=32 | L<=9,T<=6,D<=64 | "
+                         "L<=11,T<=6,D<=64 | L<=10,T<=9,D<=96 | L<=12,T<=10,D<=128)");
 }
 
 template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
@@ -396,7 +397,9 @@ int bayesn_set_model(bayesn_ctx* ctx, const bayesn_model_desc* m) {
     ctx->LP = 0;
     for (const Combo& c : kCombos)
         if (c.LP >= L && c.TP >= T && 32 * c.VPL >= D) { ctx->LP = c.LP; ctx->TP = c.TP; ctx->VPL = c.VPL; break; }
-    if (!ctx->LP) return fail(ctx, -4, "model shape not supported");
+    if (!ctx->LP)
+        return fail(ctx, -4, "model shape not supported: " + std::to_string(L) + " wavelength x " + std::to_string(T) +
+                                 " time knots (compiled: L<=6,T<=6 | L<=9,T<=6 | L<=11,T<=6 | L<=10,T<=9 | L<=12,T<=10)");
     free_owned(ctx);
     ctx->have_model = false;
     const int LP = ctx->LP, TP = ctx->TP;
@@ -775,6 +778,12 @@ int bayesn_train_nuts_status(bayesn_ctx* ctx, float* out, void* stream) {
     if (!ctx->have_tn) return fail(ctx, -1, "bayesn_train_nuts_init first");
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
     const int C = ctx->T.C;
+    if (ctx->X.world > 1) {
+        unsigned xerr = 0;
+        CU_CHECK(ctx, cudaMemcpyAsync(&xerr, ctx->X.err, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        CU_CHECK(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+        if (xerr) return fail(ctx, -5, "peer-memory exchange timed out waiting for a rank: the training chains were stopped");
+    }
     std::vector<TrainCtl> h(C);
     CU_CHECK(ctx, cudaMemcpyAsync(h.data(), ctx->TN.ctl, C * sizeof(TrainCtl), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU_CHECK(ctx, cudaStreamSynchronize((cudaStream_t)stream));

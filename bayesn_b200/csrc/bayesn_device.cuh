@@ -35,7 +35,8 @@ namespace bayesn {
 
 // -DBAYESN_PHASE_TIMING: clock64() deltas of the evaluator's phases, accumulated for warp 0 of CTA 0 (diagnostic
 // build, scripts/phase_timing.py): 0 scalars, 1 eps + W (+ dust basis), 2 per-observation setup, 3 pair loop,
-// 4 combine / team exchange, 5 reverse + priors, 6 sampler bookkeeping between evaluations, 7 evaluations.
+// 4 combine / team exchange, 5 reverse + priors, 6 sampler bookkeeping between evaluations, 7 evaluations;
+// sub-phases: 8 eps = L_Sigma e (then 1 = W assembly), 9 dtheta (then 10 = L_Sigma^T dW, then 5 = priors).
 #ifdef BAYESN_PHASE_TIMING
 __device__ unsigned long long g_phase[16];
 #define BAYESN_PHASE_BEGIN long long _pt = clock64();
@@ -576,6 +577,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         }
     }
     __syncwarp();
+    BAYESN_PHASE(8);
     for (int p = lane; p < LP * TP; p += 32) {
         int l = p / TP, m = p - l * TP;
         float w = 0.f;
@@ -916,6 +918,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     }
     gth = wsum(gth);
     __syncwarp();
+    BAYESN_PHASE(9);
 
     // ---- priors, Jacobians, assemble gradient in the unconstrained space ---------------------
     double lp = logL + (double)c.lconst;
@@ -932,6 +935,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         grad[s] = gi;
     }
     ss = wsum(ss);
+    BAYESN_PHASE(10);
     lp += -0.5f * ss;
     // theta ~ N(0,1)
     lp += -0.5f * theta_s * theta_s;
@@ -1018,7 +1022,20 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
 
     float* sJl = smem + P.oJl;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P.oBar);
-    if (tid == 0) mbar_init(bar, 1);
+    // Lanes that have run past their band's support keep reading (and discarding) words beyond it: table padding,
+    // neighbouring regions, slots of SN data that are staged later.  The products they form are multiplied by an
+    // exact zero, so the only requirement is that no such word is a NaN / Inf pattern left behind by an earlier
+    // kernel: clear the CTA's whole allocation once (generic-proxy stores, fenced before the TMA writes).
+    {
+        float4* z4 = reinterpret_cast<float4*>(smem);
+        for (int i = tid; i < P.totalFloats / 4; i += blockDim.x) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = (P.totalFloats & ~3) + tid; i < P.totalFloats; i += blockDim.x) smem[i] = 0.f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __syncthreads();
     if (tid == 0) {
         constexpr uint32_t kJlBytes = JROWS * Dims<LP, TP>::RS * 4;

@@ -398,19 +398,25 @@ __global__ void __launch_bounds__(256) train_reduce_final_kernel(TrainDev Tr, in
 }
 
 // consumer side: wait for every rank's sums of the current pass, add them in rank order into red[c]
-__device__ __forceinline__ void xchg_gather(const XchgDev& X, const TrainDev& Tr, int c, double* __restrict__ red) {
-    if (X.world <= 1) return;
+// Returns false when a rank's sums did not arrive in time (or an earlier pass already failed): the caller must
+// stop the chain - adding stale slots would let the ranks' replicated sampler states diverge.
+__device__ __forceinline__ bool xchg_gather(const XchgDev& X, const TrainDev& Tr, int c, double* __restrict__ red) {
+    if (X.world <= 1) return true;
+    __shared__ int xchg_bad;
+    if (threadIdx.x == 0) xchg_bad = (*reinterpret_cast<volatile unsigned*>(X.err) != 0u);
+    __syncthreads();
     const unsigned cur = *X.seq;
-    if ((int)threadIdx.x < X.world) {
+    if ((int)threadIdx.x < X.world && !xchg_bad) {
         const unsigned* f = X.my_flag + (cur & 1u) * X.world + threadIdx.x;
         const long long t0 = clock64();
         unsigned v;
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if (clock64() - t0 > 4000000000LL) { *X.err = 1u; break; }      // ~2 s: never hang the GPU
+            if (clock64() - t0 > 4000000000LL) { *X.err = 1u; xchg_bad = 1; break; }      // ~2 s: never hang the GPU
         } while (v != cur);
     }
     __syncthreads();
+    if (xchg_bad) return false;
     const double* src = X.my_buf + ((size_t)(cur & 1u) * X.world * Tr.C + c) * Tr.R;
     for (int r = threadIdx.x; r < Tr.R; r += blockDim.x) {
         double acc = 0.0;
@@ -418,6 +424,7 @@ __device__ __forceinline__ void xchg_gather(const XchgDev& X, const TrainDev& Tr
         red[(size_t)c * Tr.R + r] = acc;
     }
     __syncthreads();
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -499,7 +506,10 @@ __global__ void __launch_bounds__(128) train_finish_kernel(ModelDev M, TrainDev 
                                                            const float* __restrict__ qg_all, double* __restrict__ red_all,
                                                            double* __restrict__ logp, float* __restrict__ grad_g, XchgDev X) {
     const int c = blockIdx.x;
-    xchg_gather(X, Tr, c, red_all);
+    if (!xchg_gather(X, Tr, c, red_all)) {
+        if (threadIdx.x == 0) logp[c] = nan("");          // the exchange failed: bayesn_train_finish reports it
+        return;
+    }
     const double* red = red_all + (size_t)c * Tr.R;
     extern __shared__ __align__(16) float tmat[];
     if (threadIdx.x == 0) logp[c] = red[0] + Tr.lpg[c];

@@ -324,7 +324,11 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
         return;
     }
     // sums of the other ranks' SN shards (fused peer-memory exchange; no-op on one GPU / with NCCL)
-    xchg_gather(X, Tr, c, red_all);
+    if (!xchg_gather(X, Tr, c, red_all)) {
+        // a rank's sums never arrived: stop this chain here (the host sees the error flag at its next status poll)
+        if (tid == 0) { sctl.phase = 2; sctl.act = ACT_DONE; Nt.ctl[c] = sctl; }
+        return;
+    }
     const int nvec = train_nuts_num_vectors(cfg.max_depth);
     GVec W{Nt.work_g + (size_t)c * nvec * G, G};
     for (int r = tid; r < Tr.R; r += blockDim.x) red_s[r] = red_all[(size_t)c * Tr.R + r];

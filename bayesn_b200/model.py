@@ -536,14 +536,14 @@ class SEDmodel(object):
 
     def fit_from_file(self, path, filt_map={}, peak_mjd_key='SEARCH_PEAKMJD', print_summary=True, file_prefix=None,
                       drop_bands=[], fix_tmax=False, fix_theta=False, fix_AV=False, RV=False, mu_R=False,
-                      sigma_R=False, mag=False, seed=0):
+                      sigma_R=False, mag=False, seed=0, warps_per_chain='auto'):
         """Reference :1926-1992 (SNANA text file)."""
         meta, lc = snana.read_snana_ascii(path)
         return self.fit(lc['MJD'], lc['FLUXCAL'], lc['FLUXCALERR'], lc['FLT'], meta['REDSHIFT_HELIO'],
                         ebv_mw=meta['MWEBV'], peak_mjd=meta[peak_mjd_key], filt_map=filt_map,
                         print_summary=print_summary, file_prefix=file_prefix, drop_bands=drop_bands,
                         fix_tmax=fix_tmax, fix_theta=fix_theta, fix_AV=fix_AV, RV=RV, mu_R=mu_R, sigma_R=sigma_R,
-                        mag=mag, seed=seed)
+                        mag=mag, seed=seed, warps_per_chain=warps_per_chain)
 
     # ------------------------------------------------------------------ simulation (reference :3103-3424)
     def sample_del_M(self, N):

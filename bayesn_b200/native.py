@@ -341,6 +341,11 @@ class Context:
         import torch
         assert qg.is_cuda and qg.dtype == torch.float32 and qg.is_contiguous()
         assert ql.is_cuda and ql.dtype == torch.float32 and ql.is_contiguous()
+        if 'xchg' in self._keep:
+            # with the fused peer exchange switched on the reduction kernel publishes into the peers' buffers and
+            # `red` stays stale: an NCCL all-reduce of it here would be wrong
+            raise RuntimeError('train_logp_grad: the peer-memory exchange of a running train_nuts is enabled on this '
+                               'context; call disable_train_exchange() first')
         Cn, G = qg.shape
         N, C2, Dl = ql.shape
         Gd, Dld, R = self.train_dims()
@@ -368,7 +373,7 @@ class Context:
     def train_nuts(self, qg0, ql0, num_warmup=500, num_samples=500, max_tree_depth=10, target_accept=0.8,
                    init_step_size=0.1, adapt_step_size=True, adapt_mass_matrix=True, regularize_mass_matrix=False,
                    seed=0, group=None, sn_offset=0, passes_per_graph=32, use_graph=True, max_passes=None,
-                   progress=None, exchange='nccl'):
+                   progress=None, exchange='auto'):
         """Device-resident NUTS over the joint training posterior (numpyro call at reference
         :1767-1770, :1913-1919).  ``qg0`` (C, G), ``ql0`` (N, C, Dl) float32 CUDA tensors.  One pass =
         one leapfrog of every chain = SN kernel + reduction -> [all-reduce over ``group``] -> control
@@ -397,7 +402,12 @@ class Context:
                                                     self._stream()), 'bayesn_train_nuts_init')
         if group is not None:
             import torch.distributed as dist
-        peer = group is not None and exchange == 'peer' and dist.get_world_size(group) > 1
+        world = dist.get_world_size(group) if group is not None else 1
+        if exchange == 'auto':
+            # measured on 8 x B200 (profiles/README.md): NCCL's LL all-reduce of the 61 KB buffer wins at two ranks,
+            # the one-hop peer stores win from four ranks on (ring latency grows with the rank count)
+            exchange = 'peer' if world >= 4 else 'nccl'
+        peer = group is not None and exchange == 'peer' and world > 1
         if peer:
             self.enable_train_exchange(group, Cn)        # fused NVLink peer-memory exchange instead of NCCL
         else:
@@ -461,6 +471,8 @@ class Context:
         out['passes'] = passes
         out['finished'] = bool(done)
         out['warps_per_unit'] = int(self.lib.bayesn_train_warps_per_unit(self.h))
+        out['exchange'] = ('peer' if peer else 'nccl') if world > 1 else 'none'
+        out['launches_per_pass'] = 4
         if peer:
             if self.train_exchange_error():
                 raise RuntimeError('peer-memory exchange timed out waiting for a rank')

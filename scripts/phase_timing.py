@@ -31,7 +31,8 @@ obs, w, bi = m.simulated_obs_array(data, yerr, params)
 ctx = m.prepare(obs, None, bi)
 l = native.load_library()
 l.bayesn_debug_phase.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
-names = ['scalars', 'eps+W', 'obs setup', 'pair loop', 'combine/exchange', 'reverse+priors', 'sampler bookkeeping']
+names = ['scalars', 'W assembly', 'obs setup', 'pair loop', 'combine/exchange', 'priors', 'sampler bookkeeping']
+sub = {8: 'eps=L e', 9: 'dtheta', 10: 'L^T dW'}
 res = {}
 for K in (1, 2, 4, 8):
     q0 = ctx.init_to_median(4, seed=1)
@@ -44,11 +45,11 @@ for K in (1, 2, 4, 8):
     torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * 16)()
     l.bayesn_debug_phase(buf, 0)
-    v = np.array(buf[:8], dtype=np.float64)
+    v = np.array(buf[:16], dtype=np.float64)
     ne = max(v[7], 1)
     lf = float(out['chain_info'][..., 2].sum())
-    res[K] = dict(cycles_per_eval={k: round(v[i] / ne, 1) for i, k in enumerate(names)}, total_cycles_per_eval=round(v[:7].sum() / ne, 1),
+    res[K] = dict(cycles_per_eval={k: round(v[i] / ne, 1) for i, k in enumerate(names)}, total_cycles_per_eval=round((v[:7].sum() + v[8:11].sum()) / ne, 1), sub_phases={k: round(v[i] / ne, 1) for i, k in sub.items()},
                   evals_warp0=int(ne), kernel_ms=e0.elapsed_time(e1), leapfrogs_all=lf)
     print(f'{which} n={n} K={K}: {res[K]["total_cycles_per_eval"]:.0f} cycles/eval  ' +
-          '  '.join(f'{k} {v[i] / ne:.0f}' for i, k in enumerate(names)) + f'   kernel {res[K]["kernel_ms"]:.2f} ms, {lf:.0f} leapfrogs')
+          '  '.join(f'{k} {v[i] / ne:.0f}' for i, k in enumerate(names)) + '  ' + '  '.join(f'{k} {v[i] / ne:.0f}' for i, k in sub.items()) + f'   kernel {res[K]["kernel_ms"]:.2f} ms, {lf:.0f} leapfrogs')
 print(json.dumps({'config': which, 'n_sne': n, 'phases': res}))

@@ -249,7 +249,9 @@ def test_distance_rescue_population():
     out = ctx.nuts(q0, 250, 250, 10, seed=0)
     torch.cuda.synchronize()
     st = out['stats'][:, :, :250, 4]                                  # step size of every warm-up transition
-    rescued = (st < 1e-6).any(dim=2).cpu().numpy()                     # (N, 4)
+    # the rescue fires when the adapted step falls below 1e-6 and restarts the adaptation at the initial step, so
+    # the collapsed step itself is never used; the steps recorded on the way down are (healthy chains stay > 1e-3)
+    rescued = (st < 1e-4).any(dim=2).cpu().numpy()                     # (N, 4)
     ci = out['chain_info'].cpu().numpy()
     Ds = out['samples'][..., m.n_eps + 3].mean(dim=2).cpu().numpy()    # (N, 4) posterior mean distance per chain
     sd = out['samples'][..., m.n_eps + 3].std(dim=2).cpu().numpy()
@@ -312,7 +314,8 @@ def test_chain_flux_kernel_matches_oracle_forward(model, per_draw_rv):
     # num_samples / mean follow the reference's slicing (:3474-3511)
     one = m.get_flux_from_chains(t, band_lists, chains, zs, ebv, mag=False, mean=True)
     full = m.get_flux_from_chains(t, band_lists, chains, zs, ebv, mag=False)
-    assert one.shape[1] == 1 and np.array_equal(one[:, 0], full[:, 0])
+    # (the tile of an SN folds in the mean distance of the draws that are evaluated: last-bit differences)
+    assert one.shape[1] == 1 and np.allclose(one[:, 0], full[:, 0], rtol=2e-6)
 
 
 def test_chains_pkl_round_trips_through_get_flux_from_chains(tmp_path):
