@@ -346,6 +346,12 @@ constexpr int OVERRUN = BAYESN_OVERRUN;     // bins a lane may read past the end
 // instructions per load: 4 % of the evaluator's instructions in the r01i profile).  Training keeps
 // per-chain tables with stride n_eps.
 __host__ __device__ constexpr int ls_row_stride(int LP, int TP) { return ((LP - 2) * TP + 3) & ~3; }
+// The fit kernels keep ONE copy of L_Sigma in shared memory with an ODD row stride: lanes over rows walking along
+// their row (eps = L e) and lanes over columns walking down theirs (L^T dW) are both bank-conflict free.  Rows are
+// padded to a multiple of 8 (zeros) so the 8-wide mat-vec loops need no remainder.  Through L1 the same walks cost a
+// lone warp ~27 cycles per multiply-add even with eight loads in flight (scripts/phase_timing.py, r02c).
+__host__ __device__ constexpr int ls_smem_stride(int LP, int TP) { return ((LP - 2) * TP) | 1; }
+__host__ __device__ constexpr int ls_smem_rows(int LP, int TP) { return ((LP - 2) * TP + 7) & ~7; }
 __host__ __device__ constexpr int jl_row_stride(int LP) { return ((((LP + 3) & ~3) / 4) % 2 == 1) ? ((LP + 3) & ~3) : ((LP + 3) & ~3) + 4; }
 __host__ __device__ constexpr int rec_stride(int LP, int TP, bool train = false) {
     int raw = ((((LP + 3) & ~3) + (train ? 1 : 2) * TP + 3) & ~3) + 4;
@@ -354,7 +360,7 @@ __host__ __device__ constexpr int rec_stride(int LP, int TP, bool train = false)
 
 struct SmemPlan {
     // CTA-shared (float offsets)
-    int oJl, oAd, oMf, oW0, oW1, oKD, oTau, oWt, oSup, oObs, oBar;
+    int oJl, oAd, oMf, oW0, oW1, oKD, oTau, oLs, oWt, oSup, oObs, oBar;
     int oWarp, warpStride;     // per-warp region
     // inside the per-warp region
     int wWs, wEv, wEps, wRec, wSc, wAd, wDad, wX;
@@ -377,6 +383,7 @@ __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b
     p.oW1 = take(LP * TP);
     p.oKD = take(TP * TP);
     p.oTau = take(TP);
+    p.oLs = take(train ? 0 : ls_smem_rows(LP, TP) * ls_smem_stride(LP, TP) + 8);      // fit: L_Sigma, odd row stride
     p.oWt = take(stage ? ntile * wt_stride : 0);
     p.oSup = take(ntile * n_b * 4);
     p.oObs = take(ntile * N_obs * 4);
@@ -385,7 +392,7 @@ __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b
     int w = 0;
     auto wtake = [&](int n) { int r = w; w += (n + 3) & ~3; return r; };
     p.wWs = wtake(LP * TP);
-    p.wEv = wtake(n_eps);
+    p.wEv = wtake((n_eps + 7) & ~7);     // zero beyond n_eps: the 8-wide mat-vec loops read the padding
     p.wEps = wtake(n_eps);
     p.wRec = wtake((((N_obs + 1) & ~1) < OBS_CHUNK ? ((N_obs + 1) & ~1) : OBS_CHUNK) * rec);    // one chunk of observations (pairs)
     p.wSc = wtake(8);
@@ -404,7 +411,7 @@ __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b
 
 // Everything one warp needs to evaluate log p and its gradient.
 struct WarpCtx {
-    const float *sJl, *sAd, *sMf, *sW0, *sW1, *sKD, *sTau;
+    const float *sJl, *sAd, *sMf, *sW0, *sW1, *sKD, *sTau, *sLs;
     const float* wt_s;    // this SN's weight tile staged in shared memory (STAGE) ...
     const float* wt_g;    // ... or in global memory (read through L1)
     const int4* sup;      // this SN's band supports (shared)
@@ -497,6 +504,20 @@ __device__ __forceinline__ float column_dot(const float* __restrict__ col, int s
     return (a0 + a1) + (a2 + a3);
 }
 
+// The same walk over the shared-memory copy of L_Sigma: n8 terms (a multiple of 8; table and vector are zero padded).
+template <int STRIDE>
+__device__ __forceinline__ float smem_dot(const float* col, const float* v, int n8) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int j = 0; j < n8; j += 8, col += 8 * STRIDE) {
+        const float l0 = col[0], l1 = col[STRIDE], l2 = col[2 * STRIDE], l3 = col[3 * STRIDE];
+        const float l4 = col[4 * STRIDE], l5 = col[5 * STRIDE], l6 = col[6 * STRIDE], l7 = col[7 * STRIDE];
+        const float4 e0 = *reinterpret_cast<const float4*>(v + j), e1 = *reinterpret_cast<const float4*>(v + j + 4);
+        a0 = fmaf(l0, e0.x, a0); a1 = fmaf(l1, e0.y, a1); a2 = fmaf(l2, e0.z, a2); a3 = fmaf(l3, e0.w, a3);
+        a0 = fmaf(l4, e1.x, a0); a1 = fmaf(l5, e1.y, a1); a2 = fmaf(l6, e1.z, a2); a3 = fmaf(l7, e1.w, a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
 // element i of a lane-strided vector (element i lives in lane i%32, slot i/32), broadcast
 template <int VPL>
 __device__ __forceinline__ float vget(const float (&v)[VPL], int i) {
@@ -571,9 +592,13 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         const int i = i0 + lane;
         const int jend = (TRAIN || M.ls_lower) ? min(ne, i0 + 32) : ne;      // eps_i = sum_{j <= i} L[i][j] e_j
         if (i < ne) {
-            // pointer walk: with the compile-time stride the unrolled loads use immediate offsets
-            // (a 32-bit index j * lss cost two integer instructions per load)
-            c.eps[i] = column_dot(c.LsT + i, lss, c.ev, 0, jend);
+            if constexpr (TRAIN) {
+                // per-chain tables in global memory; pointer walk down the column (coalesced over the lanes)
+                c.eps[i] = column_dot(c.LsT + i, lss, c.ev, 0, jend);
+            } else {
+                // lane i walks along row i of the shared-memory copy (odd row stride: conflict free)
+                c.eps[i] = smem_dot<1>(c.sLs + i * ls_smem_stride(LP, TP), c.ev, (jend + 7) & ~7);
+            }
         }
     }
     __syncwarp();
@@ -929,7 +954,8 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         float gi = 0.f;
         if (i < ne) {
             const int j0 = (TRAIN || M.ls_lower) ? 32 * s : 0;
-            gi = column_dot(c.Ls + i + (size_t)j0 * lss, lss, c.ev, j0, ne) - q[s];
+            if constexpr (TRAIN) gi = column_dot(c.Ls + i + (size_t)j0 * lss, lss, c.ev, j0, ne) - q[s];
+            else gi = smem_dot<ls_smem_stride(LP, TP)>(c.sLs + i + j0 * ls_smem_stride(LP, TP), c.ev + j0, (ne - j0 + 7) & ~7) - q[s];
             ss = fmaf(q[s], q[s], ss);
         }
         grad[s] = gi;
@@ -1056,6 +1082,14 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
     }
     for (int i = tid; i < TP * TP; i += blockDim.x) smem[P.oKD + i] = M.KD[i];
     for (int i = tid; i < TP; i += blockDim.x) smem[P.oTau + i] = M.tau[i];
+    if constexpr (!TRAIN) {
+        const int ne = M.n_eps;
+        constexpr int SS = ls_smem_stride(LP, TP), LSS = ls_row_stride(LP, TP);
+        for (int e = tid; e < ne * ne; e += blockDim.x) {
+            const int i = e / ne, j = e - i * ne;
+            smem[P.oLs + i * SS + j] = M.Ls[i * LSS + j];
+        }
+    }
     int4* sSup = reinterpret_cast<int4*>(smem + P.oSup);
     for (int i = tid; i < nt * Dd.n_b; i += blockDim.x) sSup[i] = Dd.sup[(size_t)s_first * Dd.n_b + i];
     mbar_wait(bar, 0);
@@ -1081,6 +1115,7 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
     c.sW1 = smem + P.oW1;
     c.sKD = smem + P.oKD;
     c.sTau = smem + P.oTau;
+    c.sLs = at(P.oLs);
     c.wt_s = at(P.oWt + slot * Dd.wt_stride);
     c.wt_g = Dd.wt + (size_t)sn * Dd.wt_stride;
     c.sup = reinterpret_cast<const int4*>(at(P.oSup + slot * Dd.n_b * 4));

@@ -651,6 +651,8 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
             // coordinate in closed form (two evaluations), restart the step-size adaptation, carry on.
             if (it < cfg.num_warmup && cfg.adapt_step && step < 1e-6f && n_rescue < 3) {
                 ++n_rescue;
+                // recorded with the transition that ended here: stats[2] = diverging + 2 (warm-up rows only)
+                if (lane == 0 && writer) stats[(unit * (size_t)n_iter + (it - 1)) * 5 + 2] += 2.f;
                 const float dD1 = vget<VPL>(z, iD);
                 rs_S1 = exp2f(-C2 * dD1);
                 rs_h1 = vget<VPL>(g, iD) / (KAPPA * rs_S1);

@@ -367,6 +367,20 @@ class SEDmodel(object):
         n = max(1, min(int(self.num_devices or 1), torch.cuda.device_count(), int(N)))
         return list(range(n))
 
+    def _to_host(self, t):
+        """Device tensor -> fresh numpy array through a page-locked staging buffer kept on the model (a pageable
+        cudaMemcpy of the ~1 GB of draws of a 1000-SN fit runs at ~3 GB/s; pinned DMA + a host memcpy is 3x faster)."""
+        import torch
+        n = t.numel() * t.element_size()
+        if n < (1 << 20):
+            return t.cpu().numpy()
+        buf = getattr(self, '_pinned', None)
+        if buf is None or buf.numel() < n:
+            buf = self._pinned = torch.empty(n, dtype=torch.uint8).pin_memory()
+        view = buf[:n].view(t.dtype).view(t.shape)
+        view.copy_(t)
+        return view.numpy().copy()
+
     def fit_batch(self, obs, weights, band_inds=None, num_chains=4, num_warmup=250, num_samples=250,
                   max_tree_depth=10, seed=0, RV=None, fix_tmax=False, fix_theta=False, theta_val=0.0, fix_AV=False,
                   AV_val=0.0, init='median', return_device=False, q_init=None, sn_offset=0, group=None,
@@ -440,7 +454,7 @@ class SEDmodel(object):
             # reference :1846-1849: 4-D sites (N, C, S, dim) -> (C, S, dim, N), 3-D sites -> (C, S, N); the
             # transposition and the float64 widening run on the device, the host receives the final layout
             v = v.permute(1, 2, 3, 0) if v.ndim == 4 else v.permute(1, 2, 0)
-            samples[k] = v.contiguous().double().cpu().numpy()
+            samples[k] = self._to_host(v.contiguous().double())
             d2h += samples[k].nbytes
         stats = stats_all[:, :, num_warmup:]
         samples['diverging'] = stats[..., 2].transpose(1, 2, 0) > 0

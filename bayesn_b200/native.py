@@ -79,7 +79,7 @@ def load_library():
     lib.bayesn_bind_dataset.argtypes = [C.c_void_p, C.POINTER(DatasetDesc)]
     lib.bayesn_param_dim.argtypes = [C.c_void_p]
     lib.bayesn_logp_grad_fit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.bayesn_logp_grad_fit_team.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    _optional(lambda: setattr(lib.bayesn_logp_grad_fit_team, 'argtypes', [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]))
     lib.bayesn_flux_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 12 + [
         C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
     lib.bayesn_nuts_workspace_bytes.argtypes = [C.c_void_p, C.POINTER(NutsCfg)]
@@ -90,7 +90,7 @@ def load_library():
     lib.bayesn_ffma_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.bayesn_launch_count.restype = C.c_longlong
     lib.bayesn_spectra_batch.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 10
-    lib.bayesn_chain_flux.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p] * 10 + [C.c_int, C.c_void_p, C.c_void_p]
+    _optional(lambda: setattr(lib.bayesn_chain_flux, 'argtypes', [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p] * 10 + [C.c_int, C.c_void_p, C.c_void_p]))
     lib.bayesn_tiles_support.argtypes = [C.c_void_p, C.POINTER(TilesDesc), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bayesn_tiles_fill.argtypes = [C.c_void_p, C.POINTER(TilesDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.bayesn_train_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
@@ -99,12 +99,22 @@ def load_library():
     lib.bayesn_train_nuts_init.argtypes = [C.c_void_p, C.POINTER(NutsCfg), C.c_int] + [C.c_void_p] * 6
     lib.bayesn_train_nuts_sn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bayesn_train_nuts_ctl.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.bayesn_train_warps_per_unit.argtypes = [C.c_void_p]
+    _optional(lambda: setattr(lib.bayesn_train_warps_per_unit, 'argtypes', [C.c_void_p]))
     lib.bayesn_train_nuts_status.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
     lib.bayesn_train_set_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                               C.c_void_p]
     _lib = lib
     return lib
+
+
+def _optional(fn):
+    """Bind a symbol that older builds of the library do not have (A/B measurements against an earlier build through
+    BAYESN_B200_LIB); the product build exports everything (tests/test_host.py)."""
+    try:
+        fn()
+    except AttributeError:
+        if 'BAYESN_B200_LIB' not in os.environ:
+            raise
 
 
 def _f32(a):
@@ -211,8 +221,12 @@ class Context:
         assert N == self.N and D == self.D
         logp = torch.empty((N, Cn), dtype=torch.float32, device=q.device)
         grad = torch.empty_like(q)
-        self._check(self.lib.bayesn_logp_grad_fit_team(self.h, Cn, int(warps_per_chain), q.data_ptr(), logp.data_ptr(),
-                                                       grad.data_ptr(), self._stream()), 'bayesn_logp_grad_fit_team')
+        if int(warps_per_chain) <= 1:
+            self._check(self.lib.bayesn_logp_grad_fit(self.h, Cn, q.data_ptr(), logp.data_ptr(), grad.data_ptr(),
+                                                      self._stream()), 'bayesn_logp_grad_fit')
+        else:
+            self._check(self.lib.bayesn_logp_grad_fit_team(self.h, Cn, int(warps_per_chain), q.data_ptr(), logp.data_ptr(),
+                                                           grad.data_ptr(), self._stream()), 'bayesn_logp_grad_fit_team')
         return logp, grad
 
     def resident_warps(self):

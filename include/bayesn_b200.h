@@ -172,7 +172,8 @@ int bayesn_chain_flux(bayesn_ctx* ctx, int N, int S, int n_t, int max_bands, int
  *   q_init  [N][C][D]           device, in   initial unconstrained positions
  *   samples [N][C][S][D]        device, out  unconstrained draws after warm-up
  *   stats   [N][C][W+S][5]      device, out  per transition incl. warm-up: {accept_prob, n_leapfrog,
- *                                              diverging, potential_energy, step_size}
+ *                                              diverging, potential_energy, step_size}; warm-up rows carry
+ *                                              diverging + 2 when the float32 distance rescue fired after them
  *   chain_info [N][C][4+D]      device, out  {final step size, mean accept (sampling), total
  *                                              leapfrogs, divergences, inverse mass diag[D]}
  *   work, work_bytes            device scratch of at least bayesn_nuts_workspace_bytes(): the tree
