@@ -31,6 +31,7 @@ struct bayesn_ctx {
     std::vector<void*> tn_owned;
     bool have_tn = false;
     int train_kw = 1;           // warps per (SN, chain) unit of the last training SN launch
+    bool fuse_ctl = false;      // training pass: second reduction stage (+ peer exchange) inside the control kernel
 };
 
 namespace {
@@ -138,7 +139,8 @@ template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
 int launch_logp(bayesn_ctx* ctx, int C, int kw, const float* q, float* logp, float* grad, cudaStream_t st) {
     const int upc = WPB / kw;
     const int ntile = ntile_for(C, upc);
-    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE, false, kw);
+    // one evaluation per warp: staging L_Sigma in shared memory (12 KB per CTA) costs more than the L1 walks it saves
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE, false, kw, false);
     const size_t bytes = (size_t)P.totalFloats * 4;
     auto kern = logp_grad_kernel<LP, TP, VPL, RVFREE, STAGE>;
     if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
@@ -158,7 +160,7 @@ int launch_nuts(bayesn_ctx* ctx, const NutsDev& cfg, int kw, unsigned long long*
     const int C = cfg.num_chains;
     const int upc = WPB / kw;
     const int ntile = use_queue ? upc : ntile_for(C, upc);      // queue: one slot of SN data per team
-    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE, false, kw);
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE, false, kw, true);
     const size_t bytes = (size_t)P.totalFloats * 4;
     auto kern = nuts_kernel<LP, TP, VPL, RVFREE, STAGE>;
     if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
@@ -191,7 +193,7 @@ void choose_nuts_schedule(bayesn_ctx* ctx, int C, int kw, bool* use_queue, bool*
     const bool rvfree = ctx->M.rv_mode != BAYESN_RV_FIXED;
     const int upc = WPB / kw;
     auto occ = [&](int ntile, bool st) {
-        const SmemPlan P = make_plan(ctx->LP, ctx->TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, rvfree, st, false, kw);
+        const SmemPlan P = make_plan(ctx->LP, ctx->TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, rvfree, st, false, kw, true);
         const long long bytes = (long long)P.totalFloats * 4;
         if (bytes > 227 * 1024) return 0;
         return (int)std::min<long long>(16 / WPB, (228LL * 1024) / (bytes + 1024));    // 128 registers x 16 warps fill the SM
@@ -251,15 +253,15 @@ int launch_train_sn(bayesn_ctx* ctx, const float* ql, float* grad_l, cudaStream_
 
 // two-stage deterministic reduction of the per-SN rows (bayesn_train.cuh T3)
 int launch_train_reduce(bayesn_ctx* ctx, const float* lat, size_t chain_stride, size_t sn_stride, double* red,
-                        cudaStream_t st) {
+                        cudaStream_t st, bool final_stage = true) {
     const TrainDev& T = ctx->T;
     const int nchunk = (ctx->D.N + TRAIN_RCHUNK - 1) / TRAIN_RCHUNK;
     const size_t smem = (size_t)TRAIN_RCHUNK * (T.PR + ctx->M.n_eps + 2) * sizeof(float);
     CU_CHECK(ctx, cudaFuncSetAttribute(train_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     train_reduce_kernel<<<dim3(nchunk, T.C, (T.R + 255) / 256), 256, smem, st>>>(ctx->M, T, ctx->D.N, ctx->LP, ctx->TP, lat, chain_stride,
                                                               sn_stride, T.rpart);
-    train_reduce_final_kernel<<<dim3((T.R + 255) / 256, T.C), 256, 0, st>>>(T, nchunk, T.rpart, red, ctx->X);
-    ctx->launches += 2;
+    if (final_stage) train_reduce_final_kernel<<<dim3((T.R + 255) / 256, T.C), 256, 0, st>>>(T, nchunk, T.rpart, red, ctx->X);
+    ctx->launches += final_stage ? 2 : 1;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
 }
@@ -385,6 +387,12 @@ long long bayesn_launch_count(bayesn_ctx* ctx) { return ctx ? ctx->launches : 0;
 int bayesn_param_dim(bayesn_ctx* ctx) { return (ctx && ctx->have_model) ? ctx->M.D : -1; }
 
 int bayesn_train_warps_per_unit(bayesn_ctx* ctx) { return ctx ? ctx->train_kw : -1; }
+
+int bayesn_train_fuse_reduction(bayesn_ctx* ctx, int on) {
+    if (!ctx) return -1;
+    ctx->fuse_ctl = on != 0;
+    return 0;
+}
 
 int bayesn_set_model(bayesn_ctx* ctx, const bayesn_model_desc* m) {
     if (!ctx || !m) return -1;
@@ -755,7 +763,9 @@ int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream) {
     TrainNutsSnCall call{ctx, st};
     if (int rc = dispatch(ctx, /*stage=*/ctx->T.C >= 2, call)) return rc;
     const size_t vec = (size_t)32 * ctx->TN.VPL, nvec = train_nuts_num_vectors(ctx->TN.cfg.max_depth);
-    if (int rc = launch_train_reduce(ctx, ctx->TN.work_l + TV_CZ * vec, nvec * vec, (size_t)ctx->T.C * nvec * vec, red, st))
+    // fused mode: the control kernel adds the chunk partials (and exchanges them) itself
+    if (int rc = launch_train_reduce(ctx, ctx->TN.work_l + TV_CZ * vec, nvec * vec, (size_t)ctx->T.C * nvec * vec, red, st,
+                                     !ctx->fuse_ctl))
         return rc;
     return 0;
 }
@@ -767,7 +777,8 @@ int bayesn_train_nuts_ctl(bayesn_ctx* ctx, double* red, void* stream) {
     const size_t csm = (size_t)ctx->T.R * sizeof(double) +
                        ((size_t)ctx->M.n_eps * ctx->M.n_eps + ctx->T.G) * sizeof(float);
     CU_CHECK(ctx, cudaFuncSetAttribute(train_nuts_ctl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-    train_nuts_ctl_kernel<<<ctx->T.C, 256, csm, (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->TN, ctx->LP, ctx->TP, red, ctx->X);
+    train_nuts_ctl_kernel<<<ctx->T.C, 256, csm, (cudaStream_t)stream>>>(ctx->M, ctx->T, ctx->TN, ctx->LP, ctx->TP, red, ctx->X,
+                                                                        ctx->fuse_ctl ? 1 : 0, (ctx->D.N + TRAIN_RCHUNK - 1) / TRAIN_RCHUNK);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;

@@ -165,13 +165,14 @@ __device__ __forceinline__ float treduce16(float (&v)[16], int lane) {
 }
 
 // Packed FP32 arithmetic (Blackwell FFMA2 / FADD2: one issue slot for two IEEE fp32 operations on an
-// aligned register pair).  -DBAYESN_FFMA2=1 uses it for the two knot contractions of the band-pass loop
-// and the adds of the transposed reduction: 36 instead of 47 instructions per bin round and bit-identical
-// results (each half is an ordinary round-to-nearest FMA in the same order), but NOT faster on B200
-// (logp+grad 65.2 vs 67.5 M evals/s, NUTS unchanged; profiles/README.md): the loop is co-limited by the
-// shared-memory pipe (48 B of J_l row per bin and lane), not by issue slots alone.  Off by default.
+// aligned register pair), used for the two knot contractions of the band-pass loop and the adds of the transposed
+// reduction: 36 instead of 47 instructions per bin round and bit-identical results (each half is an ordinary
+// round-to-nearest FMA in the same order).  Round 1 measured it neutral (the loop was co-limited by the
+// shared-memory pipe); on the round-2 build the same-box A/B (scripts/ab_compare.py, profiles/README.md) gives the
+// sampler +3.5 % on C3 and +6.3 % on the dense C5 bands, the one-shot log p kernel -1 %: on by default,
+// -DBAYESN_FFMA2=0 restores the scalar loop.
 #ifndef BAYESN_FFMA2
-#define BAYESN_FFMA2 0
+#define BAYESN_FFMA2 1
 #endif
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
@@ -371,7 +372,7 @@ struct SmemPlan {
 __host__ __device__ constexpr int xchg_words(int LP, int TP) { return ((LP * TP + 6) + 3) & ~3; }
 
 __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b, int N_obs, int wt_stride, int ntile,
-                                              bool rvfree, bool stage, bool train = false, int kw = 1) {
+                                              bool rvfree, bool stage, bool train = false, int kw = 1, bool ls_smem = false) {
     SmemPlan p;
     const int rec = rec_stride(LP, TP, train);
     int o = 0;
@@ -383,7 +384,7 @@ __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b
     p.oW1 = take(LP * TP);
     p.oKD = take(TP * TP);
     p.oTau = take(TP);
-    p.oLs = take(train ? 0 : ls_smem_rows(LP, TP) * ls_smem_stride(LP, TP) + 8);      // fit: L_Sigma, odd row stride
+    p.oLs = take((train || !ls_smem) ? 0 : ls_smem_rows(LP, TP) * ls_smem_stride(LP, TP) + 8);      // L_Sigma, odd row stride
     p.oWt = take(stage ? ntile * wt_stride : 0);
     p.oSup = take(ntile * n_b * 4);
     p.oObs = take(ntile * N_obs * 4);
@@ -537,7 +538,9 @@ __device__ __forceinline__ float vget(const float (&v)[VPL], int i) {
 //   (W0, W1, L_Sigma, sigma0, R_V, tau_A), q = [eps_tform, theta, log A_V, Ds - muhat]; t_max is
 //   fixed at 0, the likelihood is Gaussian in magnitudes, and besides the latent gradient the
 //   un-reduced contributions to the global gradient are written to c.part.
-template <int LP, int TP, int VPL, bool RVFREE, bool STAGE, bool TRAIN = false>
+// LSMEM: L_Sigma is staged in shared memory (the persistent sampler); a one-shot evaluation and the training kernels
+//   (per-chain tables) walk it in global memory through L1.
+template <int LP, int TP, int VPL, bool RVFREE, bool STAGE, bool TRAIN = false, bool LSMEM = false>
 __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx& c, const float* __restrict__ hs,
                                                const float (&q)[VPL], double& logp_out, float (&grad)[VPL], int lane) {
     using DM = Dims<LP, TP, TRAIN>;
@@ -592,8 +595,9 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         const int i = i0 + lane;
         const int jend = (TRAIN || M.ls_lower) ? min(ne, i0 + 32) : ne;      // eps_i = sum_{j <= i} L[i][j] e_j
         if (i < ne) {
-            if constexpr (TRAIN) {
-                // per-chain tables in global memory; pointer walk down the column (coalesced over the lanes)
+            if constexpr (TRAIN || !LSMEM) {
+                // tables in global memory (per chain in training); pointer walk down the column, coalesced over the
+                // lanes, immediate offsets thanks to the compile-time stride
                 c.eps[i] = column_dot(c.LsT + i, lss, c.ev, 0, jend);
             } else {
                 // lane i walks along row i of the shared-memory copy (odd row stride: conflict free)
@@ -954,7 +958,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         float gi = 0.f;
         if (i < ne) {
             const int j0 = (TRAIN || M.ls_lower) ? 32 * s : 0;
-            if constexpr (TRAIN) gi = column_dot(c.Ls + i + (size_t)j0 * lss, lss, c.ev, j0, ne) - q[s];
+            if constexpr (TRAIN || !LSMEM) gi = column_dot(c.Ls + i + (size_t)j0 * lss, lss, c.ev, j0, ne) - q[s];
             else gi = smem_dot<ls_smem_stride(LP, TP)>(c.sLs + i + j0 * ls_smem_stride(LP, TP), c.ev + j0, (ne - j0 + 7) & ~7) - q[s];
             ss = fmaf(q[s], q[s], ss);
         }
@@ -1029,10 +1033,10 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
 // ------------------------------------------------------------------------------------------
 // CTA prologue shared by the log p kernel and the NUTS kernel: stage tables with TMA, carve smem
 // ------------------------------------------------------------------------------------------
-template <int LP, int TP, bool RVFREE, bool STAGE, bool TRAIN = false>
+template <int LP, int TP, bool RVFREE, bool STAGE, bool TRAIN = false, bool LSMEM = false>
 __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, int n_chains, int ntile, float* smem,
                                           WarpCtx& c, int& sn, int& chain, bool per_warp = false) {
-    const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE, TRAIN, M.kw);
+    const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE, TRAIN, M.kw, LSMEM);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int upc = WPB >> M.kwl;                  // (SN, chain) units per CTA: one per team of kw warps
     const int team = warp >> M.kwl;
@@ -1082,7 +1086,7 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
     }
     for (int i = tid; i < TP * TP; i += blockDim.x) smem[P.oKD + i] = M.KD[i];
     for (int i = tid; i < TP; i += blockDim.x) smem[P.oTau + i] = M.tau[i];
-    if constexpr (!TRAIN) {
+    if constexpr (!TRAIN && LSMEM) {
         const int ne = M.n_eps;
         constexpr int SS = ls_smem_stride(LP, TP), LSS = ls_row_stride(LP, TP);
         for (int e = tid; e < ne * ne; e += blockDim.x) {

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
     // does not matter, balance does.  queue == nullptr: CTA b runs units [b WPB, (b+1) WPB), their SN
     // data staged once per CTA (used when a per-warp slot of SN data would cost occupancy).
     const bool dyn = queue != nullptr;
-    const bool active = cta_setup<LP, TP, RVFREE, STAGE>(M, Dd, C, ntile, smem, c, sn, chain, dyn);
+    const bool active = cta_setup<LP, TP, RVFREE, STAGE, false, true>(M, Dd, C, ntile, smem, c, sn, chain, dyn);
     if (!active) return;
     const int lane = threadIdx.x & 31;
     // Latency mode (M.kw > 1): the kw warps of a team run this whole state machine redundantly on the same unit -
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
             if (u >= total_units) break;
             sn = (int)(u / (unsigned)C);
             chain = (int)(u - (unsigned long long)sn * C);
-            const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE, false, M.kw);
+            const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE, false, M.kw, true);
             warp_bind<STAGE>(M, Dd, P, smem, c, sn, lane);
         } else {
             if (!first_unit) break;
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
                 atomicAdd(&g_phase[7], 1ULL);
             }
 #endif
-            eval_logp_grad<LP, TP, VPL, RVFREE, STAGE>(M, c, M.hs, z, lp, g, lane);
+            eval_logp_grad<LP, TP, VPL, RVFREE, STAGE, false, true>(M, c, M.hs, z, lp, g, lane);
 #ifdef BAYESN_PHASE_TIMING
             t_prev_eval = clock64();
 #endif

@@ -50,6 +50,7 @@ struct TrainCtl {
     float step, u_main, w_main, w_sub, sum_acc, s_acc, da_x, da_xavg, da_gavg, da_prox, mean_acc;
     double pe, E0, prop_pe, sprop_pe, ke0_g;
     long long total_steps;
+    unsigned xseq;             // passes exchanged so far (fused reduction + peer exchange in the ctl kernel)
 };
 
 struct TrainNutsDev {
@@ -301,8 +302,59 @@ __device__ __forceinline__ void block_sums(float (&v)[NV], float* sh /* [8][NV] 
     __syncthreads();
 }
 
+// Fused second reduction stage + exchange (fused != 0): the chain's CTA adds the chunk partials of train_reduce_kernel
+// itself (fixed order) and - when SNe are sharded over ranks with the peer-memory exchange - stores its sums into its
+// slot of EVERY rank's symmetric buffer over NVLink, publishes the pass number with st.release.sys, waits for the
+// other ranks' numbers (ld.acquire.sys) and adds the slots in rank order: the same bits on every rank.  One kernel
+// less per pass and no NCCL launch; slots and flags are per (parity, rank, chain), so chains never wait for each other.
+// A rank runs at most one pass ahead of its peers (it needs their sums to finish a pass), which the two parities cover.
+__device__ __forceinline__ bool ctl_reduce_exchange(const TrainDev& Tr, const XchgDev& X, int c, int nchunk, unsigned seq,
+                                                    double* __restrict__ red_s) {
+    const int tid = threadIdx.x, R = Tr.R, C = Tr.C;
+    const unsigned par = seq & 1u;
+    for (int r = tid; r < R; r += blockDim.x) {
+        double acc = 0.0;
+        for (int k = 0; k < nchunk; ++k) acc += Tr.rpart[((size_t)k * C + c) * R + r];
+        if (X.world > 1) {
+            const size_t slot = (((size_t)par * X.world + X.rank) * C + c) * R + r;
+            for (int p = 0; p < X.world; ++p) X.peer_buf[p][slot] = acc;
+        } else {
+            red_s[r] = acc;
+        }
+    }
+    if (X.world <= 1) {
+        __syncthreads();
+        return true;
+    }
+    __shared__ int xbad;
+    if (tid == 0) xbad = (*reinterpret_cast<volatile unsigned*>(X.err) != 0u);
+    __threadfence_system();
+    __syncthreads();
+    if (tid < X.world) {
+        unsigned* f = X.peer_flag[tid] + ((size_t)par * X.world + X.rank) * C + c;          // my flag in rank tid's memory
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+        const unsigned* mine = X.my_flag + ((size_t)par * X.world + tid) * C + c;            // rank tid's flag in mine
+        const long long t0 = clock64();
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if (clock64() - t0 > 4000000000LL) { *X.err = 1u; xbad = 1; break; }      // ~2 s: never hang the GPU
+        } while (v != seq && !xbad);
+    }
+    __syncthreads();
+    if (xbad) return false;
+    const double* src = X.my_buf + ((size_t)par * X.world * C + c) * R;
+    for (int r = tid; r < R; r += blockDim.x) {
+        double acc = 0.0;
+        for (int p = 0; p < X.world; ++p) acc += __ldcg(src + (size_t)p * C * R + r);   // L2: the peers wrote it
+        red_s[r] = acc;
+    }
+    __syncthreads();
+    return true;
+}
+
 __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDev Tr, TrainNutsDev Nt, int LP, int TP,
-                                                             double* __restrict__ red_all, XchgDev X) {
+                                                             double* __restrict__ red_all, XchgDev X, int fused, int nchunk) {
     __shared__ TrainShared S;
     __shared__ float shsum[8 * TRAIN_NX];
     __shared__ TrainCtl sctl;
@@ -323,15 +375,25 @@ __global__ void __launch_bounds__(256) train_nuts_ctl_kernel(ModelDev M, TrainDe
         if (tid == 0) Nt.ctl[c].act = ACT_DONE;
         return;
     }
-    // sums of the other ranks' SN shards (fused peer-memory exchange; no-op on one GPU / with NCCL)
-    if (!xchg_gather(X, Tr, c, red_all)) {
+    const int nvec = train_nuts_num_vectors(cfg.max_depth);
+    GVec W{Nt.work_g + (size_t)c * nvec * G, G};
+    bool got;
+    if (fused) {
+        const unsigned seq = sctl.xseq + 1u;
+        got = ctl_reduce_exchange(Tr, X, c, nchunk, seq, red_s);
+        if (tid == 0) sctl.xseq = seq;
+    } else {
+        // sums of the other ranks' SN shards (peer-memory exchange after the separate second stage; no-op on one
+        // GPU / with NCCL)
+        got = xchg_gather(X, Tr, c, red_all);
+        if (got)
+            for (int r = tid; r < Tr.R; r += blockDim.x) red_s[r] = red_all[(size_t)c * Tr.R + r];
+    }
+    if (!got) {
         // a rank's sums never arrived: stop this chain here (the host sees the error flag at its next status poll)
         if (tid == 0) { sctl.phase = 2; sctl.act = ACT_DONE; Nt.ctl[c] = sctl; }
         return;
     }
-    const int nvec = train_nuts_num_vectors(cfg.max_depth);
-    GVec W{Nt.work_g + (size_t)c * nvec * G, G};
-    for (int r = tid; r < Tr.R; r += blockDim.x) red_s[r] = red_all[(size_t)c * Tr.R + r];
     for (int i = tid; i < G; i += blockDim.x) qg_s[i] = W.v(TV_CZ)[i];
     __syncthreads();
     const double* red = red_s;

@@ -55,7 +55,7 @@ EXPORTS = ['bayesn_abi_version', 'bayesn_ctx_create', 'bayesn_ctx_destroy', 'bay
            'bayesn_init_to_median', 'bayesn_ffma_peak', 'bayesn_train_dims', 'bayesn_train_begin',
            'bayesn_train_finish', 'bayesn_train_nuts_init', 'bayesn_train_nuts_sn', 'bayesn_train_nuts_ctl',
            'bayesn_train_nuts_status', 'bayesn_tiles_support', 'bayesn_tiles_fill', 'bayesn_train_set_exchange', 'bayesn_spectra_batch', 'bayesn_chain_flux',
-           'bayesn_logp_grad_fit_team', 'bayesn_train_warps_per_unit']
+           'bayesn_logp_grad_fit_team', 'bayesn_train_warps_per_unit', 'bayesn_train_fuse_reduction']
 
 _lib = None
 
@@ -100,6 +100,7 @@ def load_library():
     lib.bayesn_train_nuts_sn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bayesn_train_nuts_ctl.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     _optional(lambda: setattr(lib.bayesn_train_warps_per_unit, 'argtypes', [C.c_void_p]))
+    _optional(lambda: setattr(lib.bayesn_train_fuse_reduction, 'argtypes', [C.c_void_p, C.c_int]))
     lib.bayesn_train_nuts_status.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
     lib.bayesn_train_set_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                               C.c_void_p]
@@ -317,7 +318,7 @@ class Context:
             symm.enable_symm_mem_for_group(group.group_name)
         except Exception:
             pass
-        buf = symm.empty(n_data + 16, dtype=torch.float64, device=dev)       # data + 2 * world uint32 flags
+        buf = symm.empty(n_data + 128, dtype=torch.float64, device=dev)      # data + 2 * world * C uint32 flags
         hdl = symm.rendezvous(buf, group)
         buf.zero_()
         scratch = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -387,7 +388,7 @@ class Context:
     def train_nuts(self, qg0, ql0, num_warmup=500, num_samples=500, max_tree_depth=10, target_accept=0.8,
                    init_step_size=0.1, adapt_step_size=True, adapt_mass_matrix=True, regularize_mass_matrix=False,
                    seed=0, group=None, sn_offset=0, passes_per_graph=32, use_graph=True, max_passes=None,
-                   progress=None, exchange='auto'):
+                   progress=None, exchange='auto', fuse_reduction=True):
         """Device-resident NUTS over the joint training posterior (numpyro call at reference
         :1767-1770, :1913-1919).  ``qg0`` (C, G), ``ql0`` (N, C, Dl) float32 CUDA tensors.  One pass =
         one leapfrog of every chain = SN kernel + reduction -> [all-reduce over ``group``] -> control
@@ -426,6 +427,10 @@ class Context:
             self.enable_train_exchange(group, Cn)        # fused NVLink peer-memory exchange instead of NCCL
         else:
             self.disable_train_exchange()
+        # one GPU / peer exchange: the control kernel adds the chunk partials (and exchanges them) itself - three
+        # kernels per pass; with NCCL the reduced buffer has to exist between the two calls - four kernels + NCCL
+        fused = (group is None or world == 1 or peer) and fuse_reduction
+        self._check(self.lib.bayesn_train_fuse_reduction(self.h, int(fused)), 'bayesn_train_fuse_reduction')
 
         def one_pass():
             st = self._stream()
@@ -486,7 +491,8 @@ class Context:
         out['finished'] = bool(done)
         out['warps_per_unit'] = int(self.lib.bayesn_train_warps_per_unit(self.h))
         out['exchange'] = ('peer' if peer else 'nccl') if world > 1 else 'none'
-        out['launches_per_pass'] = 4
+        out['launches_per_pass'] = 3 if fused else 4
+        self.lib.bayesn_train_fuse_reduction(self.h, 0)
         if peer:
             if self.train_exchange_error():
                 raise RuntimeError('peer-memory exchange timed out waiting for a rank')

@@ -229,6 +229,12 @@ int bayesn_train_nuts_sn(bayesn_ctx* ctx, double* red, void* stream);
 /* warps per (SN, chain) unit the last bayesn_train_nuts_sn launch used (latency mode of the training SN kernel:
  * chosen from the number of units on this rank, 1 when they fill the GPU) */
 int bayesn_train_warps_per_unit(bayesn_ctx* ctx);
+/* Training pass with three kernels instead of four (+ no NCCL launch): with `on`, bayesn_train_nuts_sn leaves the sums
+ * over this rank's SNe as per-chunk partials and bayesn_train_nuts_ctl adds them in a fixed order itself; with the
+ * peer-memory exchange enabled (bayesn_train_set_exchange) the control kernel also stores them into every rank's
+ * buffer, publishes / waits for the pass number and adds the ranks' slots in rank order.  `red` is then unused.
+ * Switch it off when the caller all-reduces `red` itself (NCCL) between the two calls. */
+int bayesn_train_fuse_reduction(bayesn_ctx* ctx, int on);
 int bayesn_train_nuts_ctl(bayesn_ctx* ctx, double* red, void* stream);
 
 /* Fused exchange of the per-leapfrog training sums over NVLink peer memory, replacing the caller's
@@ -237,7 +243,7 @@ int bayesn_train_nuts_ctl(bayesn_ctx* ctx, double* red, void* stream);
  * buffer and publishes a pass number; the control kernel waits for all ranks' numbers and adds the
  * slots in rank order (bit-identical on every rank).
  *   peer_bufs[p]  device address, valid in THIS process, of rank p's buffer of 2 * world * C * R doubles
- *   peer_flags[p] same for rank p's 2 * world uint32 flags (zero-initialised)
+ *   peer_flags[p] same for rank p's 2 * world * C uint32 flags (zero-initialised)
  *   scratch       4 zero-initialised uint32 words in this rank's own memory (pass counter, CTA counter, error)
  * The buffers must be peer-mapped symmetric memory (e.g. torch.distributed._symmetric_memory); all
  * ranks must issue the same sequence of passes.  world = 1 switches the exchange off. */

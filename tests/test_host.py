@@ -66,9 +66,10 @@ def test_band_pass_loop_of_the_sampler_kernel_is_spill_free_and_vectorised(built
     assert len(ex2) >= 2
     inner, pair = ex2[0][1], ex2[1][1]
     rounds = sum('MUFU.EX2' in x for x in inner)
-    assert rounds >= 1 and len(inner) <= 60 * rounds, (rounds, len(inner))
+    assert rounds >= 1 and len(inner) <= 50 * rounds, (rounds, len(inner))
     assert sum(x.startswith('LDS.128') or ' LDS.128' in x for x in inner) >= 3 * rounds
-    assert sum('FFMA' in x for x in inner) >= 22 * rounds
+    # packed FP32 (FFMA2: two multiply-adds per issue slot) counts twice
+    assert sum(2 if 'FFMA2' in x else ('FFMA' in x) for x in inner) >= 22 * rounds
     for body in (inner, pair):
         assert not any(('LDL' in x) or ('STL' in x) for x in body)
     # the L_Sigma column walks use immediate-offset loads (compile-time row stride)
