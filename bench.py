@@ -136,8 +136,12 @@ def run_ours(args):
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
+    # keep stdout for the ONE JSON line: everything libraries print on file descriptor 1 (NCCL's version banner, ...)
+    # goes to stderr; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout for the one JSON line: NCCL's own banner ("NCCL version ...", NCCL_DEBUG >= VERSION) goes to stderr
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
     import __graft_entry__ as ge
@@ -309,7 +313,8 @@ def run_ours(args):
         if strong is not None:
             line['strong'] = strong
         line.update(extra)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
