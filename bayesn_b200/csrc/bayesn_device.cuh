@@ -270,19 +270,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// the same with a bound (~1 s): a byte-count mismatch must trap, never hang the GPU
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    const long long t0 = clock64();
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (!ok && clock64() - t0 > 2000000000LL) __trap();
-    }
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
     while (!ok) {
@@ -401,7 +388,7 @@ __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b
     p.oWt = take(stage ? ntile * wt_stride : 0);
     p.oSup = take(ntile * n_b * 4);
     p.oObs = take(ntile * N_obs * 4);
-    p.oBar = take(4 + 2 * WPB);      // the CTA's mbarrier + one per slot of SN data (work-queue schedule)
+    p.oBar = take(4);
     p.oWarp = o;
     int w = 0;
     auto wtake = [&](int n) { int r = w; w += (n + 3) & ~3; return r; };
@@ -1077,7 +1064,6 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
     __syncthreads();
     if (tid == 0) {
         mbar_init(bar, 1);
-        for (int k = 0; k < WPB; ++k) mbar_init(bar + 2 + k, 1);       // per-slot barriers of warp_bind
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
@@ -1167,25 +1153,26 @@ __device__ __forceinline__ bool cta_setup(const ModelDev& M, const DataDev& Dd, 
 // points its context at them.  A few KB of coalesced loads per chain, i.e. per ~10^5 evaluations.
 template <bool STAGE>
 __device__ __forceinline__ void warp_bind(const ModelDev& M, const DataDev& Dd, const SmemPlan& P, float* smem, WarpCtx& c,
-                                          int sn, int lane, uint32_t& phase) {
+                                          int sn, int lane) {
     const int warp = threadIdx.x >> 5;
     const int slot = warp >> M.kwl;                // one slot of SN data per team
     __syncwarp();
-    if ((warp & (M.kw - 1)) == 0) {
-        // The team's first warp stages the SN's observations, band supports and weight tile with 1-D TMA bulk copies
-        // completed on the slot's own mbarrier (the others wait at the team barrier below).  Every reader of the
-        // previous SN's data in this slot is past its last evaluation - nothing of the old data is in flight.
-        uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P.oBar) + 2 + slot;
-        if (lane == 0) {
-            const uint32_t b_obs = Dd.N_obs * 16u, b_sup = Dd.n_b * 16u, b_wt = STAGE ? Dd.wt_stride * 4u : 0u;
-            mbar_expect_tx(bar, b_obs + b_sup + b_wt);
-            tma_load_1d(reinterpret_cast<float4*>(smem + P.oObs) + slot * Dd.N_obs, Dd.obs4 + (size_t)sn * Dd.N_obs, b_obs, bar);
-            tma_load_1d(reinterpret_cast<int4*>(smem + P.oSup) + slot * Dd.n_b, Dd.sup + (size_t)sn * Dd.n_b, b_sup, bar);
-            if (STAGE) tma_load_1d(smem + P.oWt + slot * Dd.wt_stride, Dd.wt + (size_t)sn * Dd.wt_stride, b_wt, bar);
+    if ((warp & (M.kw - 1)) == 0) {                // the team's first warp stages, the others wait at the barrier
+        // Plain coalesced 128-bit loads: a few KB once per ~10^5 evaluations.  (A per-slot cp.async.bulk + mbarrier
+        // version of this staging faulted on B200 with staged tiles - r02f - and was backed out; the CTA-level
+        // tables and the static schedule's SN data are staged by TMA in cta_setup.)
+        float4* so = reinterpret_cast<float4*>(smem + P.oObs) + slot * Dd.N_obs;
+        const float4* go = Dd.obs4 + (size_t)sn * Dd.N_obs;
+        for (int i = lane; i < Dd.N_obs; i += 32) so[i] = go[i];
+        int4* ss = reinterpret_cast<int4*>(smem + P.oSup) + slot * Dd.n_b;
+        const int4* gs = Dd.sup + (size_t)sn * Dd.n_b;
+        for (int i = lane; i < Dd.n_b; i += 32) ss[i] = gs[i];
+        if (STAGE) {
+            float4* st = reinterpret_cast<float4*>(smem + P.oWt + slot * Dd.wt_stride);
+            const float4* gt = reinterpret_cast<const float4*>(Dd.wt + (size_t)sn * Dd.wt_stride);
+            for (int i = lane; i < Dd.wt_stride / 4; i += 32) st[i] = gt[i];
         }
-        mbar_wait_bounded(bar, phase & 1u);
     }
-    phase ^= 1u;
     __syncwarp();
     if (M.kw > 1) team_sync(slot, M.kw);
     c.wt_g = Dd.wt + (size_t)sn * Dd.wt_stride;

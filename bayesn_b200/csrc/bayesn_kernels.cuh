@@ -321,7 +321,6 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
     const int tk = (threadIdx.x >> 5) & (M.kw - 1);
     const bool writer = tk == 0;
     const unsigned long long total_units = (unsigned long long)Dd.N * C;
-    uint32_t bind_phase = 0;        // parity of this team's slot barrier (one TMA staging per unit)
     for (bool first_unit = true;; first_unit = false) {
         size_t unit;
         if (dyn) {
@@ -341,7 +340,7 @@ __global__ void __launch_bounds__(WPB * 32, NUTS_MIN_CTAS) nuts_kernel(ModelDev 
             sn = (int)(u / (unsigned)C);
             chain = (int)(u - (unsigned long long)sn * C);
             const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE, false, M.kw, true);
-            warp_bind<STAGE>(M, Dd, P, smem, c, sn, lane, bind_phase);
+            warp_bind<STAGE>(M, Dd, P, smem, c, sn, lane);
         } else {
             if (!first_unit) break;
         }
