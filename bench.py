@@ -270,16 +270,20 @@ def run_ours(args):
             with open(EXECUTED_PATH) as fh:
                 executed = json.load(fh)
         roofline = {'bound': 'fp32_fma', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                    'frac': achieved / peak, 'traffic': (executed or {}).get('dram_bytes_per_launch'),
+                    'frac': achieved / peak,
+                    'traffic': ((executed or {}).get('dram_bytes_per_eval') or 0) * leap_total / args.steps or None,
                     'kernel': 'nuts_kernel',
                     'executed_frac': (executed or {}).get('fma_pipe_frac'),
                     'executed_note': 'frac counts the DENSE algorithmic flops of SURVEY 8d; the kernel skips the exact-zero '
                                      'part of every band (C3 bands cover 22-62 of 300 bins), so the FMA pipe itself is busy '
                                      'executed_frac of the time (ncu sm__inst_executed_pipe_fma, ' +
                                      ((executed or {}).get('source', 'profiles/README.md')) + ')',
-                    'traffic_note': 'dram__bytes_read+write of a short launch of the same kernel under ncu --set full (ncu cannot '
-                                    'replay the multi-second launch); the algorithmic bytes are 11.8 KB per evaluation, the '
-                                    'kernel moves ~2 B: tiles, tables and sampler workspace stay in L2 / shared memory',
+                    'traffic_note': 'bytes per launch = (dram__bytes_read + dram__bytes_write) per evaluation of a short launch of '
+                                    'the same kernel under ncu --set full (2.5 B; ncu cannot replay the multi-second launch) x the '
+                                    'evaluations of this launch; the algorithmic bytes are 11.8 KB per evaluation: tiles, tables '
+                                    'and the sampler workspace stay in L2 / shared memory',
+                    'executed': {k: (executed or {}).get(k) for k in ('fma_pipe_frac', 'fma_inst_frac', 'issue_active_frac',
+                                                                      'lsu_pipe_frac', 'warp_instructions_per_eval')},
                     'peak_source': 'measured FFMA microbenchmark (bayesn_ffma_peak); MEASURED_PEAKS.json has no '
                                    'FP32 SIMT figure',
                     'algorithmic_flops_per_eval': F, 'evals_per_launch': leap_total / args.steps,

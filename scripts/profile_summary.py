@@ -2,15 +2,17 @@
 """Turn an ncu report of scripts/profile_target.py into the files kept under profiles/:
   <tag>_ncu_full_raw.csv             raw page (every metric of every captured launch)
   <tag>_nuts_kernel_hot_lines.csv    per-source-line stall samples / instructions / shared-memory wavefronts
-usage: python scripts/profile_summary.py gpurun_out/prof_X.ncu-rep TAG N_EVALS"""
+usage: python scripts/profile_summary.py gpurun_out/prof_X.ncu-rep TAG N_EVALS [LAUNCH]   (LAUNCH: which nuts_kernel launch
+of the report the per-line table is for, default 0)"""
 import csv, os, subprocess, sys
 rep, tag, nev = sys.argv[1], sys.argv[2], float(sys.argv[3])
+launch = sys.argv[4] if len(sys.argv) > 4 else '0'
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 raw = os.path.join(root, 'profiles', f'{tag}_ncu_full_raw.csv')
 with open(raw, 'w') as fh:
     subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], stdout=fh, stderr=subprocess.DEVNULL, check=True)
-src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-name', 'regex:nuts_kernel', '--print-source',
-                      'cuda,sass'], capture_output=True, text=True).stdout
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-name', 'regex:nuts_kernel', '--launch-skip', launch,
+                      '--launch-count', '1', '--print-source', 'cuda,sass'], capture_output=True, text=True).stdout
 out, hdr, sec = [], None, 0
 for r in csv.reader(src.splitlines()):
     if not r:
