@@ -139,10 +139,12 @@ template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
 int launch_logp(bayesn_ctx* ctx, int C, int kw, const float* q, float* logp, float* grad, cudaStream_t st) {
     const int upc = WPB / kw;
     const int ntile = ntile_for(C, upc);
-    // one evaluation per warp: staging L_Sigma in shared memory (12 KB per CTA) costs more than the L1 walks it saves
-    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE, false, kw, false);
+    // one evaluation per warp: staging L_Sigma in shared memory (12 KB per CTA) costs more than the L1 walks it saves;
+    // latency-mode launches take the sampler's shared-memory path
+    const bool lsmem = kw > 1;
+    const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE, false, kw, lsmem);
     const size_t bytes = (size_t)P.totalFloats * 4;
-    auto kern = logp_grad_kernel<LP, TP, VPL, RVFREE, STAGE>;
+    auto kern = lsmem ? logp_grad_kernel<LP, TP, VPL, RVFREE, STAGE, true> : logp_grad_kernel<LP, TP, VPL, RVFREE, STAGE, false>;
     if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
     CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     const long long units = (long long)ctx->D.N * C;

@@ -397,7 +397,9 @@ __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b
     p.wEps = wtake(n_eps);
     p.wRec = wtake((((N_obs + 1) & ~1) < OBS_CHUNK ? ((N_obs + 1) & ~1) : OBS_CHUNK) * rec);    // one chunk of observations (pairs)
     p.wSc = wtake(8);
-    p.wX = wtake(kw > 1 ? 2 * xchg_words(LP, TP) : 0);      // double-buffered exchange slot (latency mode)
+    // latency mode: double-buffered exchange slot of the evaluation + one slot each for the partial sums of the two
+    // team-split L_Sigma products
+    p.wX = wtake(kw > 1 ? 2 * xchg_words(LP, TP) + 2 * ((n_eps + 7) & ~7) : 0);
     p.wAd = wtake(rvfree ? JROWS : 0);
     p.wDad = wtake(rvfree ? JROWS : 0);
     p.warpStride = w;
@@ -549,6 +551,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     static_assert(!(RVFREE && TRAIN), "training samples one global R_V");
     const int L = M.L, T = M.T, ne = M.n_eps;
     const int lss = TRAIN ? ne : ls_row_stride(LP, TP);     // row stride of c.Ls / c.LsT
+    const int tk_ = (threadIdx.x >> 5) & (M.kw - 1);        // rank in the team (latency mode), 0 otherwise
     BAYESN_PHASE_BEGIN
 
     // ---- scalars ------------------------------------------------------------------------
@@ -591,7 +594,34 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         if (i < ne) c.ev[i] = q[s];
     }
     __syncwarp();
-    for (int i0 = 0; i0 < ne; i0 += 32) {
+    // Latency mode, sampler: the two L_Sigma products are split over the team as well - every warp sums a slice of the
+    // terms of every row / column (the table carries the zeros above the diagonal), publishes the partials in its slot,
+    // one team barrier, and all warps add the slices in rank order (identical results everywhere).
+    const bool team_mv = LSMEM && !TRAIN && M.kw > 1;
+    const int ne8 = (ne + 7) & ~7;
+    const int mv_w = (((ne8 >> M.kwl) + 7) & ~7);                 // terms per warp, a multiple of 8
+    const int mv_lo = min(ne8, tk_ * mv_w), mv_n = min(ne8, mv_lo + mv_w) - mv_lo;
+    if (team_mv) {
+        constexpr int XWc = xchg_words(LP, TP);
+        float* fx = c.sc + M.xoff + 2 * XWc;
+#pragma unroll
+        for (int s = 0; s < VPL; ++s) {
+            const int i = lane + 32 * s;
+            if (i < ne) fx[i] = smem_dot<1>(c.sLs + i * ls_smem_stride(LP, TP) + mv_lo, c.ev + mv_lo, mv_n);
+        }
+        team_sync((threadIdx.x >> 5) >> M.kwl, M.kw);
+        const float* base = fx - tk_ * M.xstride;
+#pragma unroll
+        for (int s = 0; s < VPL; ++s) {
+            const int i = lane + 32 * s;
+            if (i < ne) {
+                float acc = 0.f;
+                for (int kk = 0; kk < M.kw; ++kk) acc += base[kk * M.xstride + i];
+                c.eps[i] = acc;
+            }
+        }
+    }
+    for (int i0 = 0; i0 < (team_mv ? 0 : ne); i0 += 32) {
         const int i = i0 + lane;
         const int jend = (TRAIN || M.ls_lower) ? min(ne, i0 + 32) : ne;      // eps_i = sum_{j <= i} L[i][j] e_j
         if (i < ne) {
@@ -726,8 +756,16 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
             const int4 spo = c.sup[band];
             int nro = (spo.y - spo.x + 15) >> 4;
             nro = max(nro, __shfl_xor_sync(act, nro, 1));
+            // Mixed-band pairs: the even lanes read J_l rows first_A + hl, the odd lanes first_B + hl, and a row is three
+            // 16-byte words, so within each 8-lane phase of the LDS.128 the two sets of four rows hit the same bank
+            // groups unless first_B - first_A = 4 (mod 8) (39 % extra wavefronts on these loads in the r02i profile).
+            // The second observation therefore starts its lanes `rot` bins into its support (lane hl takes bin
+            // first + ((hl + rot) & 15)): the same bins, another lane order.  Same-band pairs keep rot = 0 (broadcast).
+            const int pband = __shfl_xor_sync(act, band, 1), pfirst = __shfl_xor_sync(act, spo.x, 1);
+            const int rot = ((lane & 1) && pband != band) ? ((4 - (spo.x - pfirst)) & 7) : 0;
             *reinterpret_cast<float4*>(rc + DM::R_SC) =
-                make_float4(interp ? (t - fl) : 0.f, __int_as_float(i0 | (interp ? 256 : 0) | (nro << 9) | (band << 16)),
+                make_float4(interp ? (t - fl) : 0.f,
+                            __int_as_float(i0 | (interp ? 256 : 0) | (nro << 9) | (band << 16) | (rot << 24)),
                             dummy ? 0.f : ob.y, dummy ? 0.f : ob.z);
         }
         __syncwarp();
@@ -754,12 +792,13 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
             const float f = scal.x;
             const int pk = __float_as_int(scal.y);
             const float yo = scal.z, iso = scal.w;
-            const int4 sp = c.sup[pk >> 16];
+            const int4 sp = c.sup[(pk >> 16) & 0xff];
             const int nr = (pk >> 9) & 0x7f;          // <= 19 rounds of 16 bins
             // running pointers: one add per array per round instead of rebuilding addresses
-            const int b_first = sp.x + hl;
+            const int boff = (hl + (pk >> 24)) & 15;  // this lane's first bin in the support (rotated for mixed pairs)
+            const int b_first = sp.x + boff;
             const float* p0 = hs + (pk & 0xff) * BP + b_first;
-            const float* pw = wtile + sp.z + hl;
+            const float* pw = wtile + sp.z + boff;
             const float4* pj = reinterpret_cast<const float4*>(c.sJl) + b_first * (RS / 4);
             const float* pa = adv + b_first;
             const float* pda = RVFREE ? (c.wdad + b_first) : (TRAIN ? c.dad_g + b_first : nullptr);
@@ -952,6 +991,30 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     // ---- priors, Jacobians, assemble gradient in the unconstrained space ---------------------
     double lp = logL + (double)c.lconst;
     float ss = 0.f;
+    if (team_mv) {
+        // d e_j = sum_i L[i][j] d eps_i - e_j: this warp's slice of the rows i, every column j
+        constexpr int XWc = xchg_words(LP, TP);
+        float* rx = c.sc + M.xoff + 2 * XWc + ne8;
+#pragma unroll
+        for (int s = 0; s < VPL; ++s) {
+            const int j = lane + 32 * s;
+            if (j < ne) rx[j] = smem_dot<ls_smem_stride(LP, TP)>(c.sLs + j + mv_lo * ls_smem_stride(LP, TP), c.ev + mv_lo, mv_n);
+        }
+        team_sync((threadIdx.x >> 5) >> M.kwl, M.kw);
+        const float* base = rx - tk_ * M.xstride;
+#pragma unroll
+        for (int s = 0; s < VPL; ++s) {
+            const int j = lane + 32 * s;
+            float gi = 0.f;
+            if (j < ne) {
+                float acc = 0.f;
+                for (int kk = 0; kk < M.kw; ++kk) acc += base[kk * M.xstride + j];
+                gi = acc - q[s];
+                ss = fmaf(q[s], q[s], ss);
+            }
+            grad[s] = gi;
+        }
+    } else {
 #pragma unroll
     for (int s = 0; s < VPL; ++s) {
         int i = lane + 32 * s;
@@ -963,6 +1026,7 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
             ss = fmaf(q[s], q[s], ss);
         }
         grad[s] = gi;
+    }
     }
     ss = wsum(ss);
     BAYESN_PHASE(10);

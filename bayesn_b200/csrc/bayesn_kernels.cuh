@@ -7,7 +7,9 @@ namespace bayesn {
 // ------------------------------------------------------------------------------------------
 // (1) fused log-density + gradient for every (SN, chain)
 // ------------------------------------------------------------------------------------------
-template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
+// LSMEM: the evaluator's shared-memory L_Sigma path (what the sampler runs); used for the latency-mode launches so that
+// the parity tests of K > 1 exercise the sampler's code, while the one-shot throughput launch walks the global tables.
+template <int LP, int TP, int VPL, bool RVFREE, bool STAGE, bool LSMEM = false>
 __global__ void __launch_bounds__(WPB * 32) logp_grad_kernel(ModelDev M, DataDev Dd, int n_chains, int ntile,
                                                              const float* __restrict__ q_in,
                                                              float* __restrict__ logp_out,
@@ -15,7 +17,7 @@ __global__ void __launch_bounds__(WPB * 32) logp_grad_kernel(ModelDev M, DataDev
     extern __shared__ __align__(16) float smem[];
     WarpCtx c;
     int sn, chain;
-    const bool active = cta_setup<LP, TP, RVFREE, STAGE>(M, Dd, n_chains, ntile, smem, c, sn, chain);
+    const bool active = cta_setup<LP, TP, RVFREE, STAGE, false, LSMEM>(M, Dd, n_chains, ntile, smem, c, sn, chain);
     if (!active) return;
     const int lane = threadIdx.x & 31;
     const size_t unit = (size_t)sn * n_chains + chain;
@@ -27,7 +29,7 @@ __global__ void __launch_bounds__(WPB * 32) logp_grad_kernel(ModelDev M, DataDev
         if (i == M.n_eps + 3) q[s] -= c.muhat;     // the evaluator works with Ds - muhat
     }
     double lp;
-    eval_logp_grad<LP, TP, VPL, RVFREE, STAGE>(M, c, M.hs, q, lp, g, lane);
+    eval_logp_grad<LP, TP, VPL, RVFREE, STAGE, false, LSMEM>(M, c, M.hs, q, lp, g, lane);
     if (((threadIdx.x >> 5) & (M.kw - 1)) != 0) return;       // latency mode: the team's warps hold identical results
     if (lane == 0) logp_out[unit] = (float)lp;
 #pragma unroll
