@@ -397,9 +397,7 @@ __host__ __device__ inline SmemPlan make_plan(int LP, int TP, int n_eps, int n_b
     p.wEps = wtake(n_eps);
     p.wRec = wtake((((N_obs + 1) & ~1) < OBS_CHUNK ? ((N_obs + 1) & ~1) : OBS_CHUNK) * rec);    // one chunk of observations (pairs)
     p.wSc = wtake(8);
-    // latency mode: double-buffered exchange slot of the evaluation + one slot each for the partial sums of the two
-    // team-split L_Sigma products
-    p.wX = wtake(kw > 1 ? 2 * xchg_words(LP, TP) + 2 * ((n_eps + 7) & ~7) : 0);
+    p.wX = wtake(kw > 1 ? 2 * xchg_words(LP, TP) : 0);      // double-buffered exchange slot (latency mode)
     p.wAd = wtake(rvfree ? JROWS : 0);
     p.wDad = wtake(rvfree ? JROWS : 0);
     p.warpStride = w;
@@ -551,7 +549,6 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     static_assert(!(RVFREE && TRAIN), "training samples one global R_V");
     const int L = M.L, T = M.T, ne = M.n_eps;
     const int lss = TRAIN ? ne : ls_row_stride(LP, TP);     // row stride of c.Ls / c.LsT
-    const int tk_ = (threadIdx.x >> 5) & (M.kw - 1);        // rank in the team (latency mode), 0 otherwise
     BAYESN_PHASE_BEGIN
 
     // ---- scalars ------------------------------------------------------------------------
@@ -594,34 +591,10 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
         if (i < ne) c.ev[i] = q[s];
     }
     __syncwarp();
-    // Latency mode, sampler: the two L_Sigma products are split over the team as well - every warp sums a slice of the
-    // terms of every row / column (the table carries the zeros above the diagonal), publishes the partials in its slot,
-    // one team barrier, and all warps add the slices in rank order (identical results everywhere).
-    const bool team_mv = LSMEM && !TRAIN && M.kw > 1;
-    const int ne8 = (ne + 7) & ~7;
-    const int mv_w = (((ne8 >> M.kwl) + 7) & ~7);                 // terms per warp, a multiple of 8
-    const int mv_lo = min(ne8, tk_ * mv_w), mv_n = min(ne8, mv_lo + mv_w) - mv_lo;
-    if (team_mv) {
-        constexpr int XWc = xchg_words(LP, TP);
-        float* fx = c.sc + M.xoff + 2 * XWc;
-#pragma unroll
-        for (int s = 0; s < VPL; ++s) {
-            const int i = lane + 32 * s;
-            if (i < ne) fx[i] = smem_dot<1>(c.sLs + i * ls_smem_stride(LP, TP) + mv_lo, c.ev + mv_lo, mv_n);
-        }
-        team_sync((threadIdx.x >> 5) >> M.kwl, M.kw);
-        const float* base = fx - tk_ * M.xstride;
-#pragma unroll
-        for (int s = 0; s < VPL; ++s) {
-            const int i = lane + 32 * s;
-            if (i < ne) {
-                float acc = 0.f;
-                for (int kk = 0; kk < M.kw; ++kk) acc += base[kk * M.xstride + i];
-                c.eps[i] = acc;
-            }
-        }
-    }
-    for (int i0 = 0; i0 < (team_mv ? 0 : ne); i0 += 32) {
+    // (Splitting the two L_Sigma products over the team as well - a slice of the terms per warp, partials exchanged behind
+    // one more barrier each - was measured slower than the replicated products: +0.7 k cycles per evaluation at K = 4,
+    // profiles/README.md r02k.  A team barrier costs more than the ~50 multiply-adds it saves.)
+    for (int i0 = 0; i0 < ne; i0 += 32) {
         const int i = i0 + lane;
         const int jend = (TRAIN || M.ls_lower) ? min(ne, i0 + 32) : ne;      // eps_i = sum_{j <= i} L[i][j] e_j
         if (i < ne) {
@@ -991,30 +964,6 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
     // ---- priors, Jacobians, assemble gradient in the unconstrained space ---------------------
     double lp = logL + (double)c.lconst;
     float ss = 0.f;
-    if (team_mv) {
-        // d e_j = sum_i L[i][j] d eps_i - e_j: this warp's slice of the rows i, every column j
-        constexpr int XWc = xchg_words(LP, TP);
-        float* rx = c.sc + M.xoff + 2 * XWc + ne8;
-#pragma unroll
-        for (int s = 0; s < VPL; ++s) {
-            const int j = lane + 32 * s;
-            if (j < ne) rx[j] = smem_dot<ls_smem_stride(LP, TP)>(c.sLs + j + mv_lo * ls_smem_stride(LP, TP), c.ev + mv_lo, mv_n);
-        }
-        team_sync((threadIdx.x >> 5) >> M.kwl, M.kw);
-        const float* base = rx - tk_ * M.xstride;
-#pragma unroll
-        for (int s = 0; s < VPL; ++s) {
-            const int j = lane + 32 * s;
-            float gi = 0.f;
-            if (j < ne) {
-                float acc = 0.f;
-                for (int kk = 0; kk < M.kw; ++kk) acc += base[kk * M.xstride + j];
-                gi = acc - q[s];
-                ss = fmaf(q[s], q[s], ss);
-            }
-            grad[s] = gi;
-        }
-    } else {
 #pragma unroll
     for (int s = 0; s < VPL; ++s) {
         int i = lane + 32 * s;
@@ -1026,7 +975,6 @@ __device__ __forceinline__ void eval_logp_grad(const ModelDev& M, const WarpCtx&
             ss = fmaf(q[s], q[s], ss);
         }
         grad[s] = gi;
-    }
     }
     ss = wsum(ss);
     BAYESN_PHASE(10);
