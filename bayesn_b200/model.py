@@ -379,7 +379,7 @@ class SEDmodel(object):
             buf = self._pinned = torch.empty(n, dtype=torch.uint8).pin_memory()
         view = buf[:n].view(t.dtype).view(t.shape)
         view.copy_(t)
-        return view.numpy().copy()
+        return torch.empty(t.shape, dtype=t.dtype).copy_(view).numpy()       # torch's host copy is multi-threaded
 
     def fit_batch(self, obs, weights, band_inds=None, num_chains=4, num_warmup=250, num_samples=250,
                   max_tree_depth=10, seed=0, RV=None, fix_tmax=False, fix_theta=False, theta_val=0.0, fix_AV=False,
