@@ -557,6 +557,19 @@ int bayesn_init_to_median(bayesn_ctx* ctx, int n_chains, uint64_t seed, uint64_t
     return 0;
 }
 
+int bayesn_debug_poison_smem(bayesn_ctx* ctx, void* stream) {
+    if (!ctx) return -1;
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    int sms = 148;
+    CU_CHECK(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    const int bytes = 110 * 1024;                     // two CTAs per SM cover ~220 KB of the 228 KB
+    CU_CHECK(ctx, cudaFuncSetAttribute(poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    poison_smem_kernel<<<2 * sms, 256, bytes, (cudaStream_t)stream>>>(bytes / 4);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
 int bayesn_ffma_peak(bayesn_ctx* ctx, double* tflops_out) {
     if (!ctx || !tflops_out) return -1;
     CU_CHECK(ctx, cudaSetDevice(ctx->device));

@@ -741,6 +741,16 @@ __global__ void init_median_kernel(InitArgs A) {
     A.q[idx] = out;
 }
 
+// Test aid: leave every SM's shared memory full of NaN bit patterns, as an unrelated earlier kernel might.  The
+// evaluator's lanes that run past a band's support read such words and multiply them by an exact zero; cta_setup clears
+// the CTA's allocation so that they can never be NaN (tests/test_gpu_round2.py::test_stale_shared_memory_is_harmless).
+__global__ void poison_smem_kernel(int nfloats) {
+    extern __shared__ __align__(16) float psm[];
+    for (int i = threadIdx.x; i < nfloats; i += blockDim.x) psm[i] = __int_as_float(0x7fc00000 | (i & 0xffff));
+    __syncthreads();
+    if (psm[(threadIdx.x * 7919) % nfloats] == 0.f) psm[0] = 1.f;      // keep the stores
+}
+
 // ------------------------------------------------------------------------------------------
 // (5) FP32 FMA peak microbenchmark: the roofline denominator for the SIMT kernels above
 //     (MEASURED_PEAKS.json has no FP32 figure).  8 independent FFMA chains per thread.

@@ -55,7 +55,7 @@ EXPORTS = ['bayesn_abi_version', 'bayesn_ctx_create', 'bayesn_ctx_destroy', 'bay
            'bayesn_init_to_median', 'bayesn_ffma_peak', 'bayesn_train_dims', 'bayesn_train_begin',
            'bayesn_train_finish', 'bayesn_train_nuts_init', 'bayesn_train_nuts_sn', 'bayesn_train_nuts_ctl',
            'bayesn_train_nuts_status', 'bayesn_tiles_support', 'bayesn_tiles_fill', 'bayesn_train_set_exchange', 'bayesn_spectra_batch', 'bayesn_chain_flux',
-           'bayesn_logp_grad_fit_team', 'bayesn_train_warps_per_unit', 'bayesn_train_fuse_reduction']
+           'bayesn_logp_grad_fit_team', 'bayesn_train_warps_per_unit', 'bayesn_train_fuse_reduction', 'bayesn_debug_poison_smem']
 
 _lib = None
 
@@ -101,6 +101,7 @@ def load_library():
     lib.bayesn_train_nuts_ctl.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     _optional(lambda: setattr(lib.bayesn_train_warps_per_unit, 'argtypes', [C.c_void_p]))
     _optional(lambda: setattr(lib.bayesn_train_fuse_reduction, 'argtypes', [C.c_void_p, C.c_int]))
+    _optional(lambda: setattr(lib.bayesn_debug_poison_smem, 'argtypes', [C.c_void_p, C.c_void_p]))
     lib.bayesn_train_nuts_status.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
     lib.bayesn_train_set_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                               C.c_void_p]
@@ -208,6 +209,10 @@ class Context:
                                                    int(sn_offset) * int(n_chains), out.data_ptr(), self._stream()),
                     'bayesn_init_to_median')
         return out
+
+    def poison_shared_memory(self):
+        """Test aid: leave NaN bit patterns in every SM's shared memory."""
+        self._check(self.lib.bayesn_debug_poison_smem(self.h, self._stream()), 'bayesn_debug_poison_smem')
 
     def ffma_peak_tflops(self):
         v = C.c_double()

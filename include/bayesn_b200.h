@@ -285,6 +285,10 @@ int bayesn_tiles_fill(bayesn_ctx* ctx, const bayesn_tiles_desc* desc, const int3
  * unconstrained positions q [N][n_chains][D] (device, out) for the bound data set. */
 int bayesn_init_to_median(bayesn_ctx* ctx, int n_chains, uint64_t seed, uint64_t unit_offset, float* q, void* stream);
 
+/* Test aid: fill every SM's shared memory with NaN bit patterns (what an unrelated earlier kernel may leave behind);
+ * the evaluation kernels must be insensitive to it. */
+int bayesn_debug_poison_smem(bayesn_ctx* ctx, void* stream);
+
 /* FP32 FMA peak of this device in TFLOP/s, measured with an FFMA-only kernel: the roofline
  * denominator for the SIMT kernels (no reference counterpart; measurement aid). */
 int bayesn_ffma_peak(bayesn_ctx* ctx, double* tflops_out);

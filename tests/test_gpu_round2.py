@@ -421,3 +421,32 @@ def test_sharded_run_under_torchrun_matches_single_gpu(tmp_path):
                         '127.0.0.1', '--master-port', '29519', os.path.join(root, 'scripts', 'sharded_run_check.py'), str(tmp_path)],
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and 'SHARDED_RUN_CHECK OK' in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+def test_stale_shared_memory_is_harmless():
+    """lanes past their band's support read words beyond it (table padding, neighbouring regions, SN slots
+    staged later) and multiply them by an exact zero - which a NaN pattern left in shared memory by an earlier kernel
+    would poison.  cta_setup clears the CTA's allocation: the results after a kernel that fills every SM's shared memory
+    with NaNs are bit-identical to the undisturbed ones (fixed-RV, sampled-RV and latency-mode kernels, short NUTS)."""
+    for model, rv in (('W22_model', None), ('pop_RV_model', None), ('T21_model', 'uniform')):
+        bands = C3_BANDS if model == 'W22_model' else PS1
+        t = C3_T if model == 'W22_model' else np.arange(-8, 40, 4.0)
+        case = make_case(model, bands, t, N=7, seed=3)
+        m, bi = product_model(case)
+        from bayesn_b200 import native
+        rv_mode = native.RV_UNIFORM if rv == 'uniform' else None
+        ctx = m.prepare(case['obs'], None, bi, rv_mode)
+        q = ctx.init_to_median(3, seed=1)
+        ref = {K: ctx.logp_grad(q, warps_per_chain=K) for K in (1, 4)}
+        out0 = ctx.nuts(q, 10, 5, 5, seed=2)
+        s0 = out0['samples'].clone()
+        for K in (1, 4):
+            ctx.poison_shared_memory()
+            lp, g = ctx.logp_grad(q, warps_per_chain=K)
+            torch.cuda.synchronize()
+            assert torch.isfinite(lp).all() and torch.isfinite(g).all(), (model, K)
+            assert torch.equal(lp, ref[K][0]) and torch.equal(g, ref[K][1]), (model, K)
+        ctx.poison_shared_memory()
+        out1 = ctx.nuts(q, 10, 5, 5, seed=2)
+        torch.cuda.synchronize()
+        assert torch.equal(out1['samples'], s0), model
