@@ -223,31 +223,6 @@ class SEDmodel(object):
         ctx.bind_dataset(packed)
         return ctx
 
-    def init_to_median(self, muhat, n_chains, rv_mode=native.RV_FIXED, seed=0, num_samples=15, device='cuda'):
-        """numpyro ``init_to_median(num_samples=15)`` (reference :1757, :2110): per chain, the
-        median of 15 prior draws of every site, mapped to the unconstrained space."""
-        import torch
-        N = len(muhat)
-        g = torch.Generator(device=device)
-        g.manual_seed(int(seed) + 7919)
-        ne = self.n_eps
-        D = self.param_dim(rv_mode)
-        sh = (N, n_chains, num_samples)
-        med = lambda x: x.median(dim=2).values
-        q = torch.empty((N, n_chains, D), dtype=torch.float32, device=device)
-        q[..., :ne] = torch.randn(sh + (ne,), generator=g, device=device).median(dim=2).values
-        q[..., ne + 0] = med(torch.randn(sh, generator=g, device=device))
-        u = torch.rand(sh, generator=g, device=device).clamp_(1e-7, 1 - 1e-7)
-        q[..., ne + 1] = torch.log(med(-self.tauA * torch.log(u)))
-        u = med(torch.rand(sh, generator=g, device=device)).clamp_(1e-6, 1 - 1e-6)
-        q[..., ne + 2] = torch.log(u) - torch.log1p(-u)
-        mu = torch.as_tensor(np.asarray(muhat, dtype=np.float32), device=device)[:, None]
-        q[..., ne + 3] = mu + math.sqrt(25.0 + self.sigma0 ** 2) * med(torch.randn(sh, generator=g, device=device))
-        if rv_mode != native.RV_FIXED:
-            u = med(torch.rand(sh, generator=g, device=device)).clamp_(1e-6, 1 - 1e-6)
-            q[..., ne + 4] = torch.log(u) - torch.log1p(-u)
-        return q.contiguous()
-
     def constrain(self, q, rv_mode=native.RV_FIXED):
         """Unconstrained draws (..., D) -> dict of constrained arrays (torch), reference site names."""
         import torch

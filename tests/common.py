@@ -65,7 +65,7 @@ def compare_logp_grad(case, n_chains=2, rv=None, seed=3, jitter=0.3, fix=None):
     ne, D = m.n_eps, ctx.D
     n_sc = D - ne
     rng = np.random.RandomState(seed)
-    q0 = m.init_to_median(case['obs'][7, 0, :], n_chains, rv_mode, seed=seed).cpu().numpy().astype(np.float64)
+    q0 = ctx.init_to_median(n_chains, seed=seed).cpu().numpy().astype(np.float64)          # device kernel (numpyro init_to_median)
     q0 += jitter * rng.randn(*q0.shape)
     q32 = torch.tensor(q0, dtype=torch.float32, device='cuda').contiguous()
     lp, g = ctx.logp_grad(q32)
