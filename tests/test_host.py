@@ -348,3 +348,31 @@ def test_training_prior_initialisation_modes():
     ne = d['n_eps']
     y = qg[2 * 36 + ne:d['G'] - 3]
     assert np.max(np.abs(y)) < 0.6 and np.max(np.abs(qg[:72])) < 1.0          # medians of 15 draws sit near the prior medians
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The boundary is a plain C ABI: the ctypes mirrors in bayesn_b200/native.py must have the size and field offsets
+    a C compiler gives the structs of include/bayesn_b200.h (a reference-side binding would be written against that
+    header)."""
+    import ctypes as C
+    from bayesn_b200 import native
+    pairs = {'bayesn_model_desc': native.ModelDesc, 'bayesn_dataset_desc': native.DatasetDesc,
+             'bayesn_nuts_cfg': native.NutsCfg, 'bayesn_tiles_desc': native.TilesDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "bayesn_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['return 0; }']
+    src = tmp_path / 'abi.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'abi'
+    subprocess.check_call(['gcc', '-std=c11', '-I' + os.path.join(ROOT, 'include'), '-o', str(exe), str(src)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    for line in out.splitlines():
+        cname, what, val = line.split()
+        cls = pairs[cname]
+        if what == 'size':
+            assert C.sizeof(cls) == int(val), (cname, C.sizeof(cls), val)
+        else:
+            assert getattr(cls, what).offset == int(val), (cname, what, getattr(cls, what).offset, val)
