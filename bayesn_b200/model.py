@@ -354,7 +354,15 @@ class SEDmodel(object):
             buf = self._pinned = torch.empty(n, dtype=torch.uint8).pin_memory()
         view = buf[:n].view(t.dtype).view(t.shape)
         view.copy_(t)
-        return torch.empty(t.shape, dtype=t.dtype).copy_(view).numpy()       # torch's host copy is multi-threaded
+        # torch's host copy is multi-threaded; torchrun pins OMP_NUM_THREADS=1, so give the copy this rank's share of
+        # the host cores for its duration
+        nt = torch.get_num_threads()
+        share = max(1, (os.cpu_count() or 8) // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', 1))))
+        try:
+            torch.set_num_threads(max(nt, min(8, share)))
+            return torch.empty(t.shape, dtype=t.dtype).copy_(view).numpy()
+        finally:
+            torch.set_num_threads(nt)
 
     def fit_batch(self, obs, weights, band_inds=None, num_chains=4, num_warmup=250, num_samples=250,
                   max_tree_depth=10, seed=0, RV=None, fix_tmax=False, fix_theta=False, theta_val=0.0, fix_AV=False,
