@@ -376,3 +376,69 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
             assert C.sizeof(cls) == int(val), (cname, C.sizeof(cls), val)
         else:
             assert getattr(cls, what).offset == int(val), (cname, what, getattr(cls, what).offset, val)
+
+
+def test_parse_yaml_input_snana_batch_keys(tmp_path):
+    """jobsplit switches the SNANA batch mode on (reference :1703-1709); save_chains / warps_per_chain defaults."""
+    from bayesn_b200 import driver
+
+    class M:
+        l_knots = np.array([3000., 5000.])
+        tau_knots = np.array([-10., 40.])
+    a = driver.parse_yaml_input(M, dict(mode='fitting', outputdir=str(tmp_path / 'o')))
+    assert a['snana'] is False and a['jobsplit'] == [1, 1] and a['save_chains'] is True and a['warps_per_chain'] == 'auto'
+    assert (tmp_path / 'o').is_dir()
+    b = driver.parse_yaml_input(M, dict(mode='fitting', outputdir=str(tmp_path / 'p'), jobsplit=[3, 8], sim_prescale=2))
+    assert b['snana'] is True and b['jobid'] == 3 and b['njobtot'] == 16
+    assert not (tmp_path / 'p').exists()             # batch fitting writes next to outfile_prefix, not into outputdir
+    with pytest.raises(ValueError):
+        driver.parse_yaml_input(M, dict(outputdir=str(tmp_path)))
+    with pytest.raises(NotImplementedError):
+        driver.parse_yaml_input(M, dict(mode='fitting', fit_method='vi', outputdir=str(tmp_path)))
+
+
+def test_survey_id_from_sndata_root(tmp_path, monkeypatch):
+    from bayesn_b200 import driver
+    monkeypatch.delenv('SNDATA_ROOT', raising=False)
+    assert driver.survey_id('LSST') == 0
+    (tmp_path / 'SURVEY.DEF').write_text('# comment\nSURVEY: SDSS 1\nSURVEY: LSST 12\n')
+    monkeypatch.setenv('SNDATA_ROOT', str(tmp_path))
+    assert driver.survey_id('LSST') == 12 and driver.survey_id('SDSS') == 1 and driver.survey_id('NOPE') == 0
+
+
+def test_output_writers_reference_layout(tmp_path):
+    """host_samples turns device draws (N, C, S[, dim]) into the reference's (chains, draws[, dim], N); write_chains
+    writes chains.pkl + fit_summary.csv; write_fitres drops NaN distances; write_lcplot keeps the reference's columns."""
+    import pickle
+    import pandas as pd
+    from bayesn_b200 import driver, outputs
+    g = torch.Generator().manual_seed(1)
+    N, C, S, ne = 3, 2, 6, 4
+    cons = {'theta': torch.randn((N, C, S), generator=g), 'eps': torch.randn((N, C, S, ne), generator=g)}
+    hs = outputs.host_samples(cons)
+    assert hs['theta'].shape == (C, S, N) and hs['eps'].shape == (C, S, ne, N)
+    assert hs['eps'][1, 2, 3, 0] == pytest.approx(float(cons['eps'][0, 1, 2, 3]))
+    outputs.write_chains(hs, str(tmp_path))
+    back = pickle.load(open(tmp_path / 'chains.pkl', 'rb'))
+    assert np.array_equal(back['eps'], hs['eps'])
+    summ = pd.read_csv(tmp_path / 'fit_summary.csv', index_col=0)
+    assert 'theta[0]' in summ.index and 'eps[3,2]' in summ.index and {'mean', 'sd', 'r_hat'} <= set(summ.columns)
+    cols = {'zHEL': np.array([0.1, 0.2, 0.3]), 'MU_LCFIT': np.array([35.0, np.nan, 36.0])}
+    assert outputs.write_fitres(str(tmp_path / 'x.FITRES.TEXT'), ['a', 'b', 'c'], cols) == 1
+    rows = [l for l in open(tmp_path / 'x.FITRES.TEXT') if l.startswith('SN:')]
+    assert len(rows) == 2 and rows[0].split()[:2] == ['SN:', 'a']
+
+    class M:
+        tau_knots = np.array([-10., 0., 10.])
+    t = np.arange(-10., 10., 2)
+    ds = dict(obs=np.zeros((10, 2, 2)), peak_mjds=np.array([58000., 58100.]),
+              lcplot=[dict(CID='s1', MJD=np.array([57999., 58001.]), FLUXCAL=np.array([1., 2.]), FLUXCALERR=np.array([.1, .1]),
+                           FLT=np.array(['g_PS1', 'r_PS1'])),
+                      dict(CID='s2', MJD=np.array([58099.]), FLUXCAL=np.array([3.]), FLUXCALERR=np.array([.2]), FLT=np.array(['g_PS1']))])
+    ds['obs'][5, 0, :] = [0.01, 0.02]
+    fm = np.arange(2 * 2 * len(t), dtype=float).reshape(2, 2, len(t))
+    out = driver.write_lcplot(M, str(tmp_path / 'x.LCPLOT'), ds, t, fm, np.zeros_like(fm))
+    assert list(out.columns) == ['CID', 'MJD', 'FLUXCAL', 'FLUXCALERR', 'FLT', 'DATA_FLAG']
+    assert (out.DATA_FLAG == 1).sum() == 3 and (out.DATA_FLAG == 0).sum() == 2 * len(t) + 1 * len(t)
+    s2 = out[(out.CID == 's2') & (out.DATA_FLAG == 0)]
+    assert np.allclose(np.sort(s2.MJD.values), 58100. + t * 1.02) and set(s2.FLT) == {'g_PS1'}
