@@ -410,7 +410,12 @@ class SEDmodel(object):
                 finally:
                     if len(devices) > 1:
                         self._device = None
-                qi = q_init if q_init is not None else ctx.init_to_median(num_chains, seed=seed, sn_offset=sn_offset + l0)
+                if q_init is None:
+                    qi = ctx.init_to_median(num_chains, seed=seed, sn_offset=sn_offset + l0)
+                else:
+                    # initial positions for the whole data set are sliced like the data; a shard-sized array is used as is
+                    qi = torch.as_tensor(q_init, dtype=torch.float32, device=f'cuda:{ctx.device}')
+                    qi = (qi[l0:l1] if qi.shape[0] == N and N != l1 - l0 else qi).contiguous()
                 out = ctx.nuts(qi, sn_offset=sn_offset + l0, **kw)           # asynchronous: the devices run concurrently
             runs.append((ctx, out))
         for ctx, out in runs:
