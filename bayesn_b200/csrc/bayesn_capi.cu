@@ -138,18 +138,31 @@ ModelDev team_model(const ModelDev& M0, int kw, const SmemPlan& P) {
 template <int LP, int TP, int VPL, bool RVFREE, bool STAGE>
 int launch_logp(bayesn_ctx* ctx, int C, int kw, const float* q, float* logp, float* grad, cudaStream_t st) {
     const int upc = WPB / kw;
-    const int ntile = ntile_for(C, upc);
+    const long long units = (long long)ctx->D.N * C;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    // Big batches (more than four waves of CTAs) run the persistent form: tables staged once per CTA, every warp strides
+    // over the units with its own slot of SN data; BAYESN_LOGP_PERSIST=0|1 overrides (measurements, tests).  Small
+    // batches and latency-mode launches keep one CTA per eight units.
+    bool persist = kw == 1 && units > 4LL * 2 * sms * WPB;
+    if (const char* e = getenv("BAYESN_LOGP_PERSIST")) persist = kw == 1 && atoi(e) != 0;
+    const int ntile = persist ? WPB : ntile_for(C, upc);
     // one evaluation per warp: staging L_Sigma in shared memory (12 KB per CTA) costs more than the L1 walks it saves;
-    // latency-mode launches take the sampler's shared-memory path
-    const bool lsmem = kw > 1;
+    // the persistent form and latency-mode launches take the sampler's shared-memory path
+    const bool lsmem = kw > 1 || persist;
     const SmemPlan P = make_plan(LP, TP, ctx->M.n_eps, ctx->D.n_b, ctx->D.N_obs, ctx->D.wt_stride, ntile, RVFREE, STAGE, false, kw, lsmem);
     const size_t bytes = (size_t)P.totalFloats * 4;
     auto kern = lsmem ? logp_grad_kernel<LP, TP, VPL, RVFREE, STAGE, true> : logp_grad_kernel<LP, TP, VPL, RVFREE, STAGE, false>;
     if (bytes > 227 * 1024) return fail(ctx, -3, "dataset needs more shared memory per CTA than sm_100a has");
     CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    const long long units = (long long)ctx->D.N * C;
-    const unsigned grid = (unsigned)((units + upc - 1) / upc);
-    kern<<<grid, WPB * 32, bytes, st>>>(team_model(ctx->M, kw, P), ctx->D, C, ntile, q, logp, grad);
+    unsigned grid = (unsigned)((units + upc - 1) / upc);
+    if (persist) {
+        int occ = 0;
+        CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WPB * 32, bytes));
+        if (occ < 1) return fail(ctx, -3, "persistent log p kernel does not fit");
+        grid = (unsigned)std::min<long long>(grid, (long long)occ * sms);
+    }
+    kern<<<grid, WPB * 32, bytes, st>>>(team_model(ctx->M, kw, P), ctx->D, C, ntile, q, logp, grad, persist ? 1 : 0);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;

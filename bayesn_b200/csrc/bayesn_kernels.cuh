@@ -13,13 +13,41 @@ template <int LP, int TP, int VPL, bool RVFREE, bool STAGE, bool LSMEM = false>
 __global__ void __launch_bounds__(WPB * 32) logp_grad_kernel(ModelDev M, DataDev Dd, int n_chains, int ntile,
                                                              const float* __restrict__ q_in,
                                                              float* __restrict__ logp_out,
-                                                             float* __restrict__ grad_out) {
+                                                             float* __restrict__ grad_out, int persist) {
     extern __shared__ __align__(16) float smem[];
     WarpCtx c;
     int sn, chain;
+    const int lane = threadIdx.x & 31;
+    if constexpr (LSMEM) if (persist) {
+        // Persistent form for big batches (one resident wave of CTAs, every warp strides over the (SN, chain) units):
+        // the model tables - J_l, dust basis, L_Sigma - are staged ONCE per CTA instead of once per eight evaluations,
+        // and each warp stages its unit's observations / supports (/ tile) into its own slot like the sampler's work queue.
+        cta_setup<LP, TP, RVFREE, STAGE, false, LSMEM>(M, Dd, n_chains, ntile, smem, c, sn, chain, true);
+        const SmemPlan P = make_plan(LP, TP, M.n_eps, Dd.n_b, Dd.N_obs, Dd.wt_stride, ntile, RVFREE, STAGE, false, M.kw, LSMEM);
+        const long long total = (long long)Dd.N * n_chains;
+        for (long long u = (long long)blockIdx.x * WPB + (threadIdx.x >> 5); u < total; u += (long long)gridDim.x * WPB) {
+            sn = (int)(u / n_chains);
+            warp_bind<STAGE>(M, Dd, P, smem, c, sn, lane);
+            float q[VPL], g[VPL];
+#pragma unroll
+            for (int s = 0; s < VPL; ++s) {
+                int i = lane + 32 * s;
+                q[s] = (i < M.D) ? q_in[(size_t)u * M.D + i] : 0.f;
+                if (i == M.n_eps + 3) q[s] -= c.muhat;
+            }
+            double lp;
+            eval_logp_grad<LP, TP, VPL, RVFREE, STAGE, false, LSMEM>(M, c, M.hs, q, lp, g, lane);
+            if (lane == 0) logp_out[u] = (float)lp;
+#pragma unroll
+            for (int s = 0; s < VPL; ++s) {
+                int i = lane + 32 * s;
+                if (i < M.D) grad_out[(size_t)u * M.D + i] = g[s];
+            }
+        }
+        return;
+    }
     const bool active = cta_setup<LP, TP, RVFREE, STAGE, false, LSMEM>(M, Dd, n_chains, ntile, smem, c, sn, chain);
     if (!active) return;
-    const int lane = threadIdx.x & 31;
     const size_t unit = (size_t)sn * n_chains + chain;
     float q[VPL], g[VPL];
 #pragma unroll

@@ -450,3 +450,29 @@ def test_stale_shared_memory_is_harmless():
         out1 = ctx.nuts(q, 10, 5, 5, seed=2)
         torch.cuda.synchronize()
         assert torch.equal(out1['samples'], s0), model
+
+
+@pytest.mark.parametrize('C', [1, 4])
+def test_persistent_logp_kernel_matches_one_shot(C, monkeypatch):
+    """Big batches run the log p + gradient kernel in its persistent form (tables staged once per CTA, warps stride
+    over the units, L_Sigma in shared memory): same results as one CTA per eight units up to the summation order of
+    the L_Sigma products, and inside the oracle tolerance.  Ragged unit count, masked observations, an empty SN."""
+    case = make_case('W22_model', C3_BANDS, C3_T, N=333, seed=12)
+    case['obs'][9, :, 5] = 0
+    m, bi = product_model(case)
+    ctx = m.prepare(case['obs'], None, bi)
+    q = ctx.init_to_median(C, seed=2)
+    q = (q + 0.2 * torch.randn(q.shape, generator=torch.Generator(device='cuda').manual_seed(3), device='cuda', dtype=torch.float32)).contiguous()
+    monkeypatch.setenv('BAYESN_LOGP_PERSIST', '0')
+    lp0, g0 = ctx.logp_grad(q)
+    monkeypatch.setenv('BAYESN_LOGP_PERSIST', '1')
+    lp1, g1 = ctx.logp_grad(q)
+    torch.cuda.synchronize()
+    assert torch.isfinite(lp1).all() and torch.isfinite(g1).all()
+    assert torch.allclose(lp1, lp0, rtol=3e-6)
+    gs = g0.abs().amax(dim=-1, keepdim=True)
+    assert float(((g1 - g0).abs() / gs).max()) < 2e-5
+    qk = q.cpu().numpy().astype(np.float64)
+    lpo, go = case['ref'].fit_logp_grad(to_oracle_layout(qk[:, 0], m.n_eps), case['obs'], case['weights'])
+    e = _errors(lp1[:, 0].cpu().numpy().astype(np.float64), g1[:, 0].cpu().numpy().astype(np.float64), lpo, to_kernel_layout(go, 4))
+    assert e[0] < LOGP_TOL and e[1] < GRAD_TOL, e
