@@ -60,63 +60,153 @@ def parse_yaml_input(model, args, cmd_args=None):
     return args
 
 
+def _snrmax(flux, ferr, bands):
+    """SNRMAX1/2/3 of the FITRES table: the highest S/N, the highest in any other band, and in a third band
+    (reference :2676-2690, :2849-2863); -99 when there is no such band."""
+    out = []
+    snr = flux / ferr
+    keep = np.ones(len(snr), dtype=bool)
+    for _ in range(3):
+        if not keep.any():
+            out.append(-99.0)
+            continue
+        i = int(np.argmax(np.where(keep, snr, -np.inf)))
+        out.append(float(snr[i]))
+        keep &= bands != bands[i]
+    return out
+
+
+def _one_light_curve(model, args, meta, lc, peak, zhel, fmap, used):
+    """Per-file steps shared by the two input branches (reference :2600-2645, :2776-2830): rest-frame phases, filter
+    mapping, bands outside the model's wavelength coverage or in ``drop_bands`` removed, error floor, non-finite
+    photometry dropped, phase cut to the tau-knot range; new bands are appended to ``used`` in order of first use."""
+    band_col = lc['BAND'] if 'BAND' in lc else lc['FLT']
+    flt = np.array([fmap.get(str(b), str(b)) for b in band_col])
+    if 'FLUXCAL' in lc:
+        flux, ferr = lc['FLUXCAL'].astype(float), lc['FLUXCALERR'].astype(float)
+    else:
+        flux = 10 ** ((27.5 - lc['MAG']) / 2.5)
+        ferr = (np.log(10) / 2.5) * flux * lc['MAGERR']
+    ferr = np.maximum(ferr, args.get('error_floor', 0.0) * (np.log(10) / 2.5) * flux)
+    t = (lc['MJD'] - peak) / (1 + zhel)
+    keep = np.isfinite(flux) & np.isfinite(ferr) & (t > model.tau_knots.min()) & (t < model.tau_knots.max())
+    for f in np.unique(flt):
+        if f in args.get('drop_bands', []):
+            keep &= flt != f
+            continue
+        if f not in model.band_dict:
+            raise KeyError(f'Filter {f} not present in BayeSN, check your filter mapping')
+        lo, hi = model.band_lim_dict[f]
+        if zhel > lo / model.l_knots[0] - 1 or zhel < hi / model.l_knots[-1] - 1:
+            keep &= flt != f
+    gl = np.array([model.band_dict.get(f, 0) for f in flt])
+    glk = gl[keep]
+    _, first = np.unique(glk, return_index=True)
+    for g in glk[np.sort(first)]:                          # order of first appearance, like pandas .unique()
+        if g not in used:
+            used.append(int(g))
+    return dict(t=t[keep], flux=flux[keep], ferr=ferr[keep], gl=gl[keep], mjd=lc['MJD'][keep], flt=flt[keep])
+
+
+FITRES_COLUMNS = ('IDSURVEY', 'TYPE', 'FIELD', 'zHEL', 'zHELERR', 'zHD', 'zHDERR', 'VPEC', 'VPECERR', 'MWEBV', 'HOST_LOGMASS',
+                  'HOST_LOGMASS_ERR', 'SNRMAX1', 'SNRMAX2', 'SNRMAX3')
+SIM_COLUMNS = (('SIM_GENTYPE', 'SIM_GENTYPE'), ('SIM_TEMPLATE_INDEX', 'SIM_TEMPLATE_INDEX'), ('SIM_LIBID', 'SIM_LIBID'),
+               ('SIM_ZCMB', 'SIM_REDSHIFT_CMB'), ('SIM_VPEC', 'SIM_VPEC'), ('SIM_DLMAG', 'SIM_DLMU'), ('SIM_PEAKMJD', 'SIM_PEAKMJD'),
+               ('SIM_THETA', 'SIM_THETA'), ('SIM_AV', 'SIM_AV'), ('SIM_RV', 'SIM_RV'))
+
+
 def process_dataset(model, args):
-    """SNANA text directory -> reference-layout arrays.  Returns dict(obs (10, N_obs, N) with
-    FLUXCAL (fitting) or MAG (training) in rows 1-2, band_inds, sn_names, peak_mjds, fitres columns).
-    Same per-object steps as reference :2577-2689: rest-frame phases from PEAKMJD, filter mapping,
-    bands outside the model's wavelength coverage dropped, phase cut to the tau-knot range, error floor,
-    zero padding with mask 0, non-positive fluxes masked for training (:2714-2718)."""
-    if 'version_photometry' not in args:
-        raise ValueError('Please pass version_photometry (a directory containing <name>.LIST and SNANA text files)')
-    data_dir = args['version_photometry']
-    name = os.path.split(os.path.normpath(data_dir))[-1]
-    sn_files = np.atleast_1d(np.loadtxt(os.path.join(data_dir, f'{name}.LIST'), dtype=str))
+    """SNANA text input -> reference-layout arrays.  Two branches of the reference's ``process_dataset``:
+
+    * ``version_photometry``: a directory holding ``<name>.LIST`` and one SNANA text file per object (:2577-2753),
+      incl. the SNANA batch subsetting (``jobsplit``: job j of n takes every n-th object, :2586-2587) and the
+      ``SIM_*`` columns of simulated data;
+    * ``data_table`` + ``data_root``: a whitespace table with columns ``SNID``, ``files`` (comma-separated SNANA text
+      files relative to ``data_root``), ``REDSHIFT_CMB``, ``REDSHIFT_CMB_ERR`` and optionally ``SEARCH_PEAKMJD``
+      (:2754-2925); the light curves of an object's files are concatenated.
+
+    Returns dict(obs (10, N_obs, N) with FLUXCAL (fitting) or MAG (training) in rows 1-2, band_inds, sn_names, peak_mjds,
+    lcplot frames, fitres columns in the reference's order).  Zero padding with mask 0, non-positive fluxes masked for
+    training (:2714-2718, :2892-2897).  SNANA FITS input is out of scope."""
     training = 'training' in args['mode'].lower()
     fmap = dict(args.get('map', {}))
     used = [0]
-    lcs, names, peaks, cols = [], [], [], {k: [] for k in ('zHEL', 'zHELERR', 'zHD', 'zHDERR', 'MWEBV', 'HOST_LOGMASS')}
-    survey = 'NULL'
-    for fn in sn_files:
-        meta, lc = snana.read_snana_ascii(os.path.join(data_dir, str(fn)))
-        survey = str(meta.get('SURVEY', 'NULL'))          # reference :2688
-        peak = meta['PEAKMJD'] if 'PEAKMJD' in meta else meta['SEARCH_PEAKMJD']
-        zhel = float(meta['REDSHIFT_HELIO'])
-        zcmb = float(meta.get('REDSHIFT_FINAL', meta.get('REDSHIFT_CMB', zhel)))
-        zhel_err = float(meta.get('REDSHIFT_HELIO_ERR', 5e-4))
-        vpec = float(meta.get('VPEC', 0.0))
-        zpec = np.sqrt((1 + vpec / C_KMS) / (1 - vpec / C_KMS)) - 1
-        zhd = (1 + zcmb) / (1 + zpec) - 1
-        band_col = lc['BAND'] if 'BAND' in lc else lc['FLT']
-        flt = np.array([fmap.get(str(b), str(b)) for b in band_col])
-        if 'FLUXCAL' in lc:
-            flux, ferr = lc['FLUXCAL'].astype(float), lc['FLUXCALERR'].astype(float)
-        else:
-            flux = 10 ** ((27.5 - lc['MAG']) / 2.5)
-            ferr = (np.log(10) / 2.5) * flux * lc['MAGERR']
-        ferr = np.maximum(ferr, args.get('error_floor', 0.0) * (np.log(10) / 2.5) * flux)
-        t = (lc['MJD'] - peak) / (1 + zhel)
-        keep = np.isfinite(flux) & np.isfinite(ferr) & (t > model.tau_knots.min()) & (t < model.tau_knots.max())
-        for f in np.unique(flt):
-            if f not in model.band_dict:
-                raise KeyError(f'Filter {f} not present in BayeSN, check your filter mapping')
-            lo, hi = model.band_lim_dict[f]
-            if zhel > lo / model.l_knots[0] - 1 or zhel < hi / model.l_knots[-1] - 1 or f in args.get('drop_bands', []):
-                keep &= flt != f
-        gl = np.array([model.band_dict[f] for f in flt])
-        glk = gl[keep]
-        _, first = np.unique(glk, return_index=True)
-        for g in glk[np.sort(first)]:                          # order of first appearance, like pandas .unique()
-            if g not in used:
-                used.append(int(g))
-        lcs.append(dict(t=t[keep], flux=flux[keep], ferr=ferr[keep], gl=gl[keep], z=zhel, zerr=zhel_err,
-                        mjd=lc['MJD'][keep], flt=flt[keep],
-                        mu=float(model.cosmo.distmod(np.array([zhd]))[0]), ebv=float(meta.get('MWEBV', 0.0)),
-                        mass=float(meta.get('HOSTGAL_LOGMASS', -9.0))))
-        names.append(str(meta.get('SNID', fn)))
-        peaks.append(float(peak))
-        for k, v in (('zHEL', zhel), ('zHELERR', zhel_err), ('zHD', zcmb), ('zHDERR', float(meta.get('REDSHIFT_FINAL_ERR', 5e-4))),
-                     ('MWEBV', float(meta.get('MWEBV', 0.0))), ('HOST_LOGMASS', float(meta.get('HOSTGAL_LOGMASS', -9.0)))):
-            cols[k].append(v)
+    lcs, names, peaks = [], [], []
+    cols = {k: [] for k in FITRES_COLUMNS}
+    sim_cols = {k: [] for k, _ in SIM_COLUMNS}
+    survey, sim = 'NULL', False
+    sigma_pec = getattr(model, 'sigma_pec', 150 / 3e5)
+
+    def add_fitres(meta, obj, zhel, zhel_err, zhd, zhd_err, idsurvey):
+        snr = _snrmax(obj['flux'], obj['ferr'], obj['gl']) if len(obj['flux']) else [-99.0, -99.0, -99.0]
+        vals = dict(IDSURVEY=idsurvey, TYPE=meta.get('TYPE', 0), FIELD=str(meta.get('FIELD', 'VOID')), zHEL=zhel,
+                    zHELERR=float(meta.get('REDSHIFT_HELIO_ERR', zhel_err)), zHD=zhd, zHDERR=zhd_err,
+                    VPEC=float(meta.get('VPEC', 0.0)), VPECERR=float(meta.get('VPEC_ERR', sigma_pec * 3e5)),
+                    MWEBV=float(meta.get('MWEBV', 0.0)), HOST_LOGMASS=float(meta.get('HOSTGAL_LOGMASS', -9.0)),
+                    HOST_LOGMASS_ERR=float(meta.get('HOSTGAL_LOGMASS_ERR', -9.0)), SNRMAX1=round(snr[0], 2),
+                    SNRMAX2=round(snr[1], 2), SNRMAX3=round(snr[2], 2))
+        for k in FITRES_COLUMNS:
+            cols[k].append(vals[k])
+
+    if 'version_photometry' in args:
+        data_dir = args['version_photometry']
+        name = os.path.split(os.path.normpath(data_dir))[-1]
+        sn_files = np.atleast_1d(np.loadtxt(os.path.join(data_dir, f'{name}.LIST'), dtype=str))
+        meta0, _ = snana.read_snana_ascii(os.path.join(data_dir, str(sn_files[0])))
+        sim = 'SIM_REDSHIFT_HELIO' in meta0                                       # :2581
+        jobid, njob = int(args.get('jobid', 1)), int(args.get('njobtot', 1))
+        if not sim:
+            njob = int(args.get('jobsplit', [1, 1])[1])                           # real data ignore sim_prescale
+        for ind, fn in enumerate(sn_files):
+            if (ind + 1 - jobid) % njob != 0:
+                continue
+            meta, lc = snana.read_snana_ascii(os.path.join(data_dir, str(fn)))
+            survey = str(meta.get('SURVEY', 'NULL'))          # reference :2688
+            peak = meta['PEAKMJD'] if 'PEAKMJD' in meta else meta['SEARCH_PEAKMJD']
+            zhel = float(meta['REDSHIFT_HELIO'])
+            zcmb = float(meta.get('REDSHIFT_FINAL', meta.get('REDSHIFT_CMB', zhel)))
+            zhel_err = float(meta.get('REDSHIFT_HELIO_ERR', 5e-4))
+            zcmb_err = float(meta.get('REDSHIFT_FINAL_ERR', 5e-4))
+            vpec = float(meta.get('VPEC', 0.0))
+            zpec = np.sqrt((1 + vpec / C_KMS) / (1 - vpec / C_KMS)) - 1
+            zhd = (1 + zcmb) / (1 + zpec) - 1
+            obj = _one_light_curve(model, args, meta, lc, peak, zhel, fmap, used)
+            obj.update(z=zhel, zerr=zhel_err, mu=float(model.cosmo.distmod(np.array([zhd]))[0]),
+                       ebv=float(meta.get('MWEBV', 0.0)), mass=float(meta.get('HOSTGAL_LOGMASS', -9.0)))
+            lcs.append(obj)
+            names.append(str(meta.get('SNID', fn)))
+            peaks.append(float(peak))
+            add_fitres(meta, obj, zhel, zhel_err, zcmb, zcmb_err, survey_id(survey))
+            if sim:
+                for k, mk in SIM_COLUMNS:
+                    sim_cols[k].append(meta.get(mk, -9))
+    elif 'data_table' in args:
+        if 'data_root' not in args:
+            raise ValueError('If using data_table, please also pass data_root (which defines the location that the '
+                             'paths in data_table are defined with respect to)')
+        import pandas as pd
+        table = pd.read_csv(os.path.join(args['data_root'], args['data_table']), comment='#', sep=r'\s+')
+        for _, row in table.iterrows():
+            parts, meta = [], {}
+            for fn in str(row['files']).split(','):
+                meta, lc = snana.read_snana_ascii(os.path.join(args['data_root'], fn))
+                peak = row['SEARCH_PEAKMJD'] if 'SEARCH_PEAKMJD' in table.columns else meta['SEARCH_PEAKMJD']
+                zhel = float(meta['REDSHIFT_HELIO'])
+                parts.append(_one_light_curve(model, args, meta, lc, peak, zhel, fmap, used))
+            obj = {k: np.concatenate([p_[k] for p_ in parts]) for k in parts[0]}
+            zcmb, zcmb_err = float(row['REDSHIFT_CMB']), float(row['REDSHIFT_CMB_ERR'])
+            obj.update(z=zhel, zerr=zcmb_err, mu=float(model.cosmo.distmod(np.array([zcmb]))[0]),
+                       ebv=float(meta.get('MWEBV', 0.0)), mass=float(meta.get('HOSTGAL_LOGMASS', -9.0)))
+            lcs.append(obj)
+            names.append(str(row['SNID']))
+            peaks.append(float(peak))
+            add_fitres(meta, obj, zhel, zcmb_err, zcmb, zcmb_err, meta.get('IDSURVEY', 'NULL'))
+            survey = str(meta.get('SURVEY', survey))
+    else:
+        raise ValueError('Please pass either version_photometry (a directory containing <name>.LIST and SNANA text files) '
+                         'or data_table (a table of SNe and their files) with data_root')
+    if not lcs:
+        raise ValueError('no objects selected from the data set (check jobsplit / the LIST file)')
     band_inds = np.array(used)                                  # NULL band + bands in order of first use
     local = {g: i for i, g in enumerate(used)}
     N, n_obs = len(lcs), max(max(len(l['t']) for l in lcs), 1)
@@ -139,8 +229,11 @@ def process_dataset(model, args):
         obs[4, :n, i] = np.where(obs[9, :n, i] != 0, [local[g] for g in l['gl']], 0)
         obs[3, :, i], obs[5, :, i], obs[6, :, i], obs[7, :, i], obs[8, :, i] = l['mass'], l['z'], l['zerr'], l['mu'], l['ebv']
     lcplot = [dict(CID=names[i], MJD=l['mjd'], FLUXCAL=l['flux'], FLUXCALERR=l['ferr'], FLT=l['flt']) for i, l in enumerate(lcs)]
+    fitres = {k: np.array(v) for k, v in cols.items()}
+    if sim:
+        fitres.update({k: np.array(v) for k, v in sim_cols.items()})
     return dict(obs=obs, band_inds=band_inds, sn_names=names, peak_mjds=np.array(peaks), lcplot=lcplot, survey=survey,
-                fitres={k: np.array(v) for k, v in cols.items()})
+                sim=sim, fitres=fitres)
 
 
 def lcplot_curves(model, ds, cons, lo, hi, save_fit_errors=False, chunk=512):
@@ -261,9 +354,14 @@ def fit_dataset(model, ds, args, group=None):
         samples = outputs.host_samples(cons) if args.get('return_samples', True) else {}      # this rank's block only
     drop_count = 0
     if rank == 0:
-        cols = {'zHEL': meta[:, 0], 'MWEBV': meta[:, 1], 'MUHAT': meta[:, 2]}
-        cols.update({k: v for k, v in (ds.get('fitres') or {}).items() if k not in ('zHEL', 'MWEBV')})
+        meta_cols = ds.get('fitres') or {}
+        if meta_cols:
+            # reference order (:2735-2753, :2918-2923): object metadata, then the fit columns, SIM_* columns last (:2336-2338)
+            cols = {k: v for k, v in meta_cols.items() if 'SIM' not in k}
+        else:
+            cols = {'zHEL': meta[:, 0], 'MWEBV': meta[:, 1], 'MUHAT': meta[:, 2]}
         cols.update({k: rows[:, i] for i, k in enumerate(keys)})
+        cols.update({k: v for k, v in meta_cols.items() if 'SIM' in k})
         pre = args['outfile_prefix']
         base = pre if os.path.isabs(pre) else os.path.join(args['outputdir'], pre)
         os.makedirs(os.path.dirname(base) or '.', exist_ok=True)

@@ -97,6 +97,14 @@ def host_samples(cons):
     return out
 
 
+def _fitres_cell(v):
+    if isinstance(v, str):
+        return v
+    if isinstance(v, (int, np.integer)):
+        return str(int(v))
+    return f'{float(v):.4f}'
+
+
 def write_fitres(path, sn_names, columns, version_photometry='NULL', snana_version='NULL'):
     """SNANA FITRES text table (reference :2296-2340 writes it with ``sncosmo.write_lc(fmt='snana',
     metachar='')``): header comment block, ``VARNAMES:`` line, one ``SN:`` row per object.  Rows
@@ -109,8 +117,7 @@ def write_fitres(path, sn_names, columns, version_photometry='NULL', snana_versi
         for i, sn in enumerate(sn_names):
             if not keep[i]:
                 continue
-            vals = ' '.join(f'{float(columns[k][i]):.4f}' if not isinstance(columns[k][i], str) else columns[k][i]
-                            for k in names)
+            vals = ' '.join(_fitres_cell(columns[k][i]) for k in names)
             fh.write(f'SN: {sn} {vals}\n')
     return int((~keep).sum())
 

@@ -442,3 +442,69 @@ def test_output_writers_reference_layout(tmp_path):
     assert (out.DATA_FLAG == 1).sum() == 3 and (out.DATA_FLAG == 0).sum() == 2 * len(t) + 1 * len(t)
     s2 = out[(out.CID == 's2') & (out.DATA_FLAG == 0)]
     assert np.allclose(np.sort(s2.MJD.values), 58100. + t * 1.02) and set(s2.FLT) == {'g_PS1'}
+
+
+def _write_objects(d, model, n=5, seed=4):
+    """A few SNANA text files with hand-made griz photometry (no forward model needed on the CPU)."""
+    from bayesn_b200 import snana
+    rng = np.random.RandomState(seed)
+    tgrid = np.arange(-12, 44, 4.0)                  # two epochs fall outside the tau-knot range (-10, 40)
+    bands = np.repeat(['g', 'r', 'i', 'z'], len(tgrid))
+    tt = np.tile(tgrid, 4)
+    files, zs = [], rng.uniform(0.02, 0.06, n)
+    for i in range(n):
+        flux = rng.uniform(500, 5000, len(tt))
+        flux[3] = -5.0                                # a negative flux: masked for training, kept for fitting
+        err = 0.03 * np.abs(flux) + 1.0
+        snana.write_snana_fluxfile(str(d), f'{100 + i}', 58000.0 + tt * (1 + zs[i]), bands, flux, err, 58000.0, zs[i], zs[i] + 1e-4,
+                                   ebv_mw=0.01 * i, extra={'SURVEY': 'TESTSURVEY', 'TYPE': 1, 'FIELD': 'DEEP', 'VPEC': 100.0,
+                                                           'HOSTGAL_LOGMASS': 10.5})
+        files.append(f'{100 + i}.DAT')
+    name = os.path.split(str(d))[-1]
+    (d / f'{name}.LIST').write_text('\n'.join(files) + '\n')
+    return files, zs, tt
+
+
+def test_process_dataset_text_directory_jobsplit_and_data_table(tmp_path):
+    """process_dataset (reference :2577-2925) on the CPU: padding, phase cut, band order, FITRES metadata in the
+    reference's column order, SNANA batch subsetting, and the data_table branch reading the same files."""
+    from bayesn_b200 import SEDmodel, driver
+    m = SEDmodel(load_model='T21_model')
+    d = tmp_path / 'PHOT'
+    d.mkdir()
+    files, zs, tt = _write_objects(d, m)
+    fmap = {'g': 'g_PS1', 'r': 'r_PS1', 'i': 'i_PS1', 'z': 'z_PS1'}
+    args = driver.parse_yaml_input(m, dict(mode='fitting', version_photometry=str(d), outputdir=str(tmp_path / 'o'), map=fmap))
+    ds = driver.process_dataset(m, args)
+    N, n_in = 5, int(((tt > -10 * 1.0) & (tt < 40)).sum())
+    assert ds['obs'].shape[0] == 10 and ds['obs'].shape[2] == N and ds['sn_names'] == [str(100 + i) for i in range(N)]
+    # (rest-frame phases recomputed from 5-decimal MJDs land on either side of the tau-knot edges: ragged light curves)
+    cnt = ds['obs'][9].sum(axis=0)
+    assert np.all(cnt <= n_in + 4) and np.all(cnt >= n_in - 8) and ds['obs'].shape[1] == int(cnt.max())
+    assert np.all(ds['obs'][0][ds['obs'][9] != 0] > -10) and np.all(ds['obs'][0][ds['obs'][9] != 0] < 40)
+    assert list(ds['band_inds']) == [0] + [m.band_dict[fmap[b]] for b in 'griz']         # NULL + order of first use
+    assert list(ds['fitres'].keys()) == list(driver.FITRES_COLUMNS)
+    assert np.allclose(ds['fitres']['zHEL'], zs) and np.all(ds['fitres']['FIELD'] == 'DEEP') and np.all(ds['fitres']['TYPE'] == 1)
+    assert np.all(ds['fitres']['SNRMAX1'] >= ds['fitres']['SNRMAX2']) and np.all(ds['fitres']['SNRMAX2'] >= ds['fitres']['SNRMAX3'])
+    assert ds['survey'] == 'TESTSURVEY' and ds['sim'] is False
+    # peculiar velocity enters the Hubble-diagram redshift of the distance prior (:2598-2600)
+    zpec = np.sqrt((1 + 100.0 / driver.C_KMS) / (1 - 100.0 / driver.C_KMS)) - 1
+    assert np.allclose(ds['obs'][7, 0, :], m.cosmo.distmod((1 + zs + 1e-4) / (1 + zpec) - 1))
+    # training: magnitudes, non-positive fluxes masked
+    dt = driver.process_dataset(m, dict(args, mode='training_globalRV'))
+    assert dt['obs'][9].sum() == ds['obs'][9].sum() - N and np.all(dt['obs'][1][dt['obs'][9] != 0] > 15)
+    # SNANA batch job 2 of 3 takes objects 2 and 5 (1-based)
+    a2 = driver.parse_yaml_input(m, dict(mode='fitting', version_photometry=str(d), outputdir=str(tmp_path / 'o'), map=fmap,
+                                         jobsplit=[2, 3]))
+    assert driver.process_dataset(m, a2)['sn_names'] == ['101', '104']
+    # the data_table branch on the same files
+    tab = tmp_path / 'table.txt'
+    tab.write_text('# comment\nSNID SEARCH_PEAKMJD REDSHIFT_CMB REDSHIFT_CMB_ERR files\n' +
+                   '\n'.join(f'{100 + i} 58000.0 {zs[i] + 1e-4} 0.0005 PHOT/{files[i]}' for i in range(N)) + '\n')
+    at = driver.parse_yaml_input(m, dict(mode='fitting', data_table='table.txt', data_root=str(tmp_path), outputdir=str(tmp_path / 'o'),
+                                         map=fmap))
+    d2 = driver.process_dataset(m, at)
+    assert d2['sn_names'] == ds['sn_names'] and np.array_equal(d2['obs'][:5], ds['obs'][:5]) and np.array_equal(d2['obs'][9], ds['obs'][9])
+    assert np.allclose(d2['obs'][7, 0, :], m.cosmo.distmod(zs + 1e-4)) and np.all(d2['obs'][6] == 0.0005)
+    with pytest.raises(ValueError):
+        driver.process_dataset(m, dict(at, data_root=None) if False else {k: v for k, v in at.items() if k != 'data_root'})
