@@ -3,6 +3,8 @@ bayesn/bayesn_model.py:1115-1182): log joint density and gradient of the CUDA ke
 through the C ABI, against the float64 oracle on the same seeded inputs.
 
 Tolerances (BASELINE.json north_star): log p relative 1e-5, gradient 1e-4 norm-wise."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -225,3 +227,37 @@ def test_train_sn_kernel_latency_mode_matches_one_warp_per_unit(K, monkeypatch):
     assert np.array_equal(s1[:, :3, 1], sk[:, :3, 1]), (s1[:, :, 1], sk[:, :, 1])       # leapfrogs per transition
     assert np.allclose(s1[:, :3, 3], sk[:, :3, 3], rtol=1e-5)                            # potential energy
     assert float((o1['samples_g'][:, :3] - ok['samples_g'][:, :3]).abs().max()) < 5e-3
+
+
+@pytest.mark.parametrize('init', ['T21_model', 'median'])
+def test_run_training_from_snana_text_directory(tmp_path, init):
+    """End to end like ``run_bayesn input.yaml`` with ``mode: training_globalRV`` (reference :1766-1770, :1913-1924,
+    postprocess :2186-2242): SNANA text files with magnitudes (written by simulate_light_curve(write_to_files=True))
+    -> process_dataset -> device-resident training sampler -> bayesn.yaml / chains.pkl / initial_chains.pkl /
+    input.yaml; every chain starts from ``initial_guess`` of a model or from its own prior median."""
+    import pickle
+    import yaml
+    from bayesn_b200 import SEDmodel
+    m = SEDmodel(load_model='T21_model')
+    np.random.seed(5)
+    N = 12
+    z = np.random.uniform(0.02, 0.06, N)
+    d = tmp_path / 'SIMTRAIN'
+    m.simulate_light_curve(np.arange(-8, 36, 4.0), N, PS1, yerr=0.02, err_type='mag', z=z, mu='z', ebv_mw=0.01, mag=True,
+                           write_to_files=True, output_dir=str(d))
+    files = sorted(os.listdir(d))
+    assert len(files) == N
+    (d / 'SIMTRAIN.LIST').write_text('\n'.join(files) + '\n')
+    out = tmp_path / 'out'
+    W, S = 40, 20
+    samples = m.run(dict(mode='training_globalRV', version_photometry=str(d), outputdir=str(out), num_warmup=W, num_samples=S,
+                         num_chains=2, initialisation=init))
+    L, T = len(m.l_knots), len(m.tau_knots)
+    assert samples['W0'].shape == (2, S, L * T) and samples['theta'].shape == (2, S, N) and samples['AV'].shape == (2, S, N)
+    assert np.all(np.isfinite(samples['W0'])) and np.all(samples['tauA'] > 0) and np.all(samples['sigma0'] > 0)
+    y = yaml.safe_load(open(out / 'bayesn.yaml'))
+    assert np.array(y['W0']).shape == (L, T) and np.array(y['L_SIGMA_EPSILON']).shape == ((L - 2) * T, (L - 2) * T)
+    assert 'RV' not in y                                   # reference quirk (:2235): globalRV runs do not write RV
+    ch = pickle.load(open(out / 'chains.pkl', 'rb'))
+    assert ch['W1'].shape == (2, S, L * T)
+    assert (out / 'initial_chains.pkl').exists() and (out / 'input.yaml').exists()
