@@ -357,7 +357,8 @@ class SEDmodel(object):
         # torch's host copy is multi-threaded; torchrun pins OMP_NUM_THREADS=1, so give the copy this rank's share of
         # the host cores for its duration
         nt = torch.get_num_threads()
-        share = max(1, (os.cpu_count() or 8) // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', 1))))
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 8)
+        share = max(1, cores // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', 1))))
         try:
             torch.set_num_threads(max(nt, min(8, share)))
             return torch.empty(t.shape, dtype=t.dtype).copy_(view).numpy()
