@@ -424,7 +424,6 @@ class SEDmodel(object):
         if return_device:
             ctx, out = runs[0]
             return self.constrain(out['samples'], rv_mode), out
-        keys = None
         parts = []
         for ctx, out in runs:
             cons = self.constrain(out['samples'], rv_mode)                   # (n, C, S[, dim]) on the device
