@@ -660,6 +660,79 @@ class SEDmodel(object):
                               band_weights=band_weights)
         return data, yerr, param_dict
 
+    def simulate_spectrum(self, t, N, dl=10, z=0, mu=0, ebv_mw=0, RV=None, logM=None, del_M=None, AV=None, theta=None,
+                          eps=None):
+        """Reference :2923-3101: rest-frame, host-dust-extinguished spectra of N simulated objects on a linear
+        wavelength grid of spacing ``dl`` between the first and last wavelength knot, at phases ``t``.  Returns
+        (``l_o`` (N, n_wave) observer-frame wavelengths, ``spectra`` (N, n_wave, len(t)), ``param_dict``); priors are
+        sampled in the reference's order (del_M, AV, theta, eps) from the global numpy RNG.
+
+        The reference rebuilds ``model_wave`` / ``J_l_T`` / the Hsiao table of the INSTANCE for that grid (a side effect,
+        SURVEY Appendix E) and computes host / Milky Way extinction arrays it never applies; here the instance is left
+        untouched: the grid is evaluated in chunks of 300 bins by the ``get_spectra`` kernel on temporary tables."""
+        import torch
+        from .static import spline_matrix, inv_kd, F99_XK
+
+        def per_object(val, name, msg=None):
+            val = np.array(val)
+            if len(val.shape) == 0:
+                return val.repeat(N)
+            if val.shape[0] != N:
+                raise ValueError(msg or f'If not providing a scalar {name} value, array must be of same length as the '
+                                        f'number of objects to simulate, N')
+            return val
+        each = lambda name: (f'For {name}, either pass a single scalar value or an array of values for each of the N '
+                             f'simulated objects')
+        del_M = self.sample_del_M(N) if del_M is None else per_object(del_M, 'del_M')
+        AV = self.sample_AV(N) if AV is None else per_object(AV, 'AV')
+        theta = self.sample_theta(N) if theta is None else per_object(theta, 'theta')
+        L, T = self.l_knots.shape[0], self.tau_knots.shape[0]
+        if eps is None:
+            eps = self.sample_epsilon(N)
+        else:
+            eps = np.array(eps)
+            if len(eps.shape) == 0:
+                if eps == 0:
+                    eps = np.zeros((N, L, T))
+                else:
+                    raise ValueError('For epsilon, please pass an array-like object of shape (N, l_knots, tau_knots). The '
+                                     'only scalar value accepted is 0, which will effectively remove the effect of epsilon')
+            elif eps.shape == (L, T):
+                eps = eps[None, ...].repeat(N, axis=0)
+            elif eps.shape != (N, L, T):
+                raise ValueError('For epsilon, please pass an array-like object of shape (N, l_knots, tau_knots)')
+        ebv_mw = per_object(ebv_mw, 'ebv_mw', each('ebv_mw')).astype(float)
+        RV = per_object(self.RV if RV is None else RV, 'RV', each('RV')).astype(float)
+        z = per_object(z, 'z', each('z')).astype(float)
+        mu = per_object(mu, 'mu', each('mu')).astype(float)
+        param_dict = {'del_M': del_M, 'AV': AV, 'theta': theta, 'eps': eps, 'z': z, 'mu': mu, 'ebv_mw': ebv_mw, 'RV': RV}
+        l_r = np.arange(min(self.l_knots), max(self.l_knots) + dl, dl, dtype=float)
+        l_r = l_r[l_r <= max(self.l_knots)]
+        l_o = l_r[None, ...].repeat(N, axis=0) * (1 + z[:, None])
+        t = np.asarray(t, dtype=float)
+        tt = np.repeat(t[..., None], N, axis=1)
+        hsiao_interp = np.array([HSIAO_PHASE0_INDEX + np.floor(tt), HSIAO_PHASE0_INDEX + np.ceil(tt), np.remainder(tt, 1)])
+        J_t = self.J_t_map(tt).transpose(1, 2, 0)                       # (N, T, n_t)
+        dev = f'cuda:{self._device_index()}'
+        to = lambda a: torch.as_tensor(np.array(a, dtype=np.float32), device=dev)
+        args = (to(theta), to(AV), to(self.W0), to(self.W1), to(eps), to(RV), to(J_t), to(hsiao_interp))
+        KD_l = inv_kd(self.l_knots)
+        ph, hw, hf = datafiles.load_hsiao()
+        KD_h, KD_x = inv_kd(hw), inv_kd(F99_XK)
+        nb = native.NBINS
+        pad = lambda a: np.concatenate([a, np.zeros((nb - a.shape[0],) + a.shape[1:])], axis=0)
+        ctx = self._context(native.RV_FIXED)
+        spectra = np.zeros((N, l_r.shape[0], t.shape[0]))
+        for c0 in range(0, l_r.shape[0], nb):
+            lam = l_r[c0:c0 + nb]
+            ctx.set_model(tau_knots=self.tau_knots, KD_t=self.KD_t, J_l=pad(spline_matrix(lam, self.l_knots, KD_l)),
+                          hsiao=pad(spline_matrix(lam, hw, KD_h) @ hf.T), M_fitz=pad(spline_matrix(1e4 / lam, F99_XK, KD_x)),
+                          a_dust=np.ones(nb), W0=self.W0, W1=self.W1, L_Sigma=self.L_Sigma, tauA=self.tauA,
+                          Ds_prior_sd=math.sqrt(25.0 + self.sigma0 ** 2))
+            out = ctx.spectra_batch(*args)                               # (N, 300, n_t)
+            spectra[:, c0:c0 + lam.shape[0]] = out[:, :lam.shape[0]].cpu().numpy()
+        return l_o, spectra, param_dict
+
     def simulated_obs_array(self, data, yerr, param_dict):
         """Pack the output of the last ``simulate_light_curve(mag=False)`` call into the
         reference's (10, N_obs, N) ``obs`` layout."""

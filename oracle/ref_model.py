@@ -26,6 +26,7 @@ here                                  reference
 ``RefSED.train_logp``                 ``train_model_globalRV :1115-1182``
 ``RefSED.prepare_fit_data``           ``fit :2061-2106``
 ``RefSED.simulate_light_curve``       ``simulate_light_curve :3103-3345``
+``RefSED.spectrum_on_linear_grid``    ``simulate_spectrum :3067-3087`` (grid rebuild + get_spectra)
 ====================================  =======================================================
 
 Third-party pieces that are absent from the tree are restated from their published algorithms:
@@ -377,6 +378,25 @@ class RefSED:
         f_A = 10 ** (-0.4 * A)
         model_spectra = model_spectra * f_A[..., None]
         return model_spectra
+
+    # ------------------------------------------------------------ bayesn_model.py:3067-3087
+    def spectrum_on_linear_grid(self, t, dl, theta, AV, eps, RV):
+        """The deterministic part of ``simulate_spectrum``: as the reference does, REPLACES this instance's wavelength
+        grid and the tables built on it (J_l_T, M_fitz_block, Hsiao) by ones on a linear grid of spacing ``dl`` between
+        the first and last wavelength knot, then evaluates ``get_spectra`` at phases ``t`` for every object.  Returns
+        (l_r, spectra (N, n_wave, len(t)))."""
+        N = len(theta)
+        l_r = np.arange(min(self.l_knots), max(self.l_knots) + dl, dl, dtype=float)
+        l_r = l_r[l_r <= max(self.l_knots)]
+        self.model_wave = l_r
+        self.J_l_T = spline_coeffs_irr(self.model_wave, self.l_knots, invKD_irr(self.l_knots))
+        self.M_fitz_block = spline_coeffs_irr(1e4 / self.model_wave, self.xk, invKD_irr(self.xk))
+        self._load_hsiao_template()
+        tt = torch.as_tensor(np.repeat(np.asarray(t, dtype=float)[..., None], N, axis=1))
+        J_t, hsiao_interp = self.J_t_and_hsiao(tt)
+        tn = lambda a: torch.as_tensor(np.asarray(a, dtype=float))
+        spectra = self.get_spectra(tn(theta), tn(AV), tn(self.W0), tn(self.W1), tn(eps), tn(RV), J_t, hsiao_interp)
+        return l_r, spectra.numpy()
 
     # ------------------------------------------------------------ bayesn_model.py:645-709
     def get_flux_batch(self, M0, theta, AV, W0, W1, eps, Ds, RV, band_indices, mask, J_t, hsiao_interp, weights,

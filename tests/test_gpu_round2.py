@@ -476,3 +476,37 @@ def test_persistent_logp_kernel_matches_one_shot(C, monkeypatch):
     lpo, go = case['ref'].fit_logp_grad(to_oracle_layout(qk[:, 0], m.n_eps), case['obs'], case['weights'])
     e = _errors(lp1[:, 0].cpu().numpy().astype(np.float64), g1[:, 0].cpu().numpy().astype(np.float64), lpo, to_kernel_layout(go, 4))
     assert e[0] < LOGP_TOL and e[1] < GRAD_TOL, e
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('model,dl', [('M20_model', 10.0), ('W22_model', 37.0)])
+def test_simulate_spectrum_matches_oracle_grid_rebuild(model, dl):
+    """simulate_spectrum (reference :2923-3101): spectra on a linear wavelength grid that is NOT the model's 300-bin
+    grid (1 501 bins for M20 at dl = 10: six chunks through the get_spectra kernel), against the oracle, which rebuilds
+    its tables on that grid the way the reference does.  Also the argument handling and that the instance's own tables
+    survive (the reference overwrites them)."""
+    from oracle.ref_model import RefSED
+    from bayesn_b200 import SEDmodel
+    m = SEDmodel(load_model=model)
+    J_before = m.J_l_T.copy()
+    N, t = 6, np.array([-7.5, 0.0, 3.25, 18.0, 39.5])
+    np.random.seed(5)
+    z = np.linspace(0.01, 0.3, N)
+    RV = np.linspace(2.2, 3.8, N)
+    l_o, spec, pd = m.simulate_spectrum(t, N, dl=dl, z=z, RV=RV)
+    ref = RefSED(model, bands=['g_PS1'])          # private instance: the call below replaces its grid
+    l_r, s_ref = ref.spectrum_on_linear_grid(t, dl, pd['theta'], pd['AV'], pd['eps'], pd['RV'])
+    assert spec.shape == s_ref.shape == (N, l_r.shape[0], t.shape[0]) and l_r.shape[0] > 300 * (dl == 10.0)
+    assert np.array_equal(l_o, l_r[None] * (1 + z[:, None]))
+    err = np.max(np.abs(spec - s_ref) / np.abs(s_ref))
+    _report('simulate_spectrum', dict(model=model, dl=dl, n_wave=int(l_r.shape[0]), rel=float(err)))
+    assert err < 1e-5
+    assert np.array_equal(m.J_l_T, J_before) and m.grid.model_wave.shape == (300,)
+    assert set(pd) == {'del_M', 'AV', 'theta', 'eps', 'z', 'mu', 'ebv_mw', 'RV'} and pd['eps'].shape[0] == N
+    # scalar broadcasting, eps = 0, per-object arrays of the wrong length
+    _, s0, p0 = m.simulate_spectrum(t[:2], 3, dl=50, theta=0.5, AV=0.1, del_M=0.0, eps=0)
+    assert s0.shape[0] == 3 and np.array_equal(s0[0], s0[2]) and not p0['eps'].any()
+    with pytest.raises(ValueError, match='RV'):
+        m.simulate_spectrum(t, 3, RV=np.ones(2))
+    with pytest.raises(ValueError, match='epsilon'):
+        m.simulate_spectrum(t, 3, eps=1.0)

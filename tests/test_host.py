@@ -508,3 +508,16 @@ def test_process_dataset_text_directory_jobsplit_and_data_table(tmp_path):
     assert np.allclose(d2['obs'][7, 0, :], m.cosmo.distmod(zs + 1e-4)) and np.all(d2['obs'][6] == 0.0005)
     with pytest.raises(ValueError):
         driver.process_dataset(m, dict(at, data_root=None) if False else {k: v for k, v in at.items() if k != 'data_root'})
+
+
+def test_simulate_spectrum_argument_errors_match_reference():
+    """simulate_spectrum (reference :2962-3056) validates its per-object arguments before any device work."""
+    from bayesn_b200 import SEDmodel
+    m = SEDmodel(load_model='T21_model')
+    t = np.array([0.0, 10.0])
+    for kw, msg in [(dict(del_M=np.zeros(2)), 'del_M'), (dict(AV=np.zeros(4)), 'AV'), (dict(theta=np.zeros(2)), 'theta'),
+                    (dict(eps=0.5), 'only scalar value accepted is 0'), (dict(eps=np.zeros((2, 2))), 'shape'),
+                    (dict(z=np.zeros(2)), 'For z'), (dict(mu=np.zeros(2)), 'For mu'), (dict(RV=np.ones(2)), 'For RV'),
+                    (dict(ebv_mw=np.zeros(2)), 'For ebv_mw')]:
+        with pytest.raises(ValueError, match=msg):
+            m.simulate_spectrum(t, 3, **kw)
