@@ -19,6 +19,12 @@ qu = ctx_u.init_to_median(2, seed=1)
 ctx_u.logp_grad(qu)
 out = ctx.nuts(q, 12, 6, 5, seed=1)
 assert torch.isfinite(out['samples']).all()
+# round 2: latency mode (K warps per (SN, chain)) in the one-shot kernel and the sampler, both schedules
+for K in (2, 4, 8):
+    lpk, gk = ctx.logp_grad(q, warps_per_chain=K)
+    assert torch.allclose(lpk, lp, rtol=2e-6) and torch.isfinite(gk).all()
+    ok = ctx.nuts(q, 12, 6, 5, seed=1, warps_per_chain=K)
+    assert torch.isfinite(ok['samples']).all()
 obs_t, w_t, bi_t = btrain.simulate_training_set(m, 6, seed=2, bands=('g_PS1', 'r_PS1', 'i_PS1', 'z_PS1'), t=np.arange(-8, 36, 6.0))
 ct = m.prepare_training(obs_t, None, bi_t)
 qg0, ql0 = btrain.initial_position(m, obs_t, 2, 'T21_model', seed=1)
