@@ -15,8 +15,9 @@ import numpy as np
 
 
 def split_rhat_device(x):
-    """Split-R-hat (Gelman et al. 2013, as arviz / numpyro compute it) of ``x`` (..., C, S) torch
-    tensor, reduced over the last two axes on the device."""
+    """Classic split-R-hat (Gelman et al. 2013; numpyro.diagnostics.split_gelman_rubin, the ``r_hat`` column of
+    ``print_summary``) of ``x`` (..., C, S) torch tensor, reduced over the last two axes on the device.  The FITRES
+    columns use the rank-normalised statistic of ``arviz.summary`` instead (``summary.rank_rhat_t``)."""
     import torch
     C, S = x.shape[-2], x.shape[-1]
     h = S // 2
@@ -66,16 +67,20 @@ def device_fit_summary(model, cons, muhat, seed=0, sn_offset=0):
     if 'mu' not in cons:
         draw_mu_device(model, cons, muhat, seed=seed, sn_offset=sn_offset)
     mu, Ds = cons['mu'], cons['Ds']
-    sites = {'mu': mu, 'delM': cons['delM'], 'theta': cons['theta'], 'AV': cons['AV'], 'Ds': Ds}
+    # MEANRHAT / MAXRHAT: over the r_hat column of arviz.summary (:2315-2318) - rank-normalised split R-hat of every
+    # site left after the *_tform ones are dropped: mu, delM, theta, AV, Ds, tmax, peak_MJD, eps (n_eps rows), RV when
+    # it is sampled - evaluated for every (site, SN) on the device.  peak_MJD is an increasing affine map of tmax
+    # (:2255-2257), so its rank statistic IS tmax's: that row is entered twice instead of building the draws.
+    from .summary import rank_rhat_t
+    sites = [mu, cons['delM'], cons['theta'], cons['AV'], Ds] + ([cons['RV']] if 'RV' in cons else [])
+    rh = [rank_rhat_t(v) for v in sites]
     if 'tmax' in cons:
-        sites['tmax'] = cons['tmax']
-    # arviz.summary drops the *_tform sites for the FITRES r-hat columns (:2314-2316) but keeps eps
-    rh = [split_rhat_device(v) for v in sites.values()]
+        rh += [rank_rhat_t(cons['tmax'])] * 2
+    rhat = torch.stack(rh)
     if 'eps' in cons:
-        rh.append(split_rhat_device(cons['eps'].permute(0, 3, 1, 2)).transpose(0, 1))      # (n_eps, N) rows
-        rhat = torch.cat([torch.stack(rh[:-1]), rh[-1]], dim=0)
-    else:
-        rhat = torch.stack(rh)
+        e = cons['eps']                                                                     # (N, C, S, n_eps)
+        r_eps = rank_rhat_t(e.permute(0, 3, 1, 2).reshape(-1, e.shape[1], e.shape[2])).reshape(e.shape[0], e.shape[3])
+        rhat = torch.cat([rhat, r_eps.transpose(0, 1)], dim=0)                              # (rows, N)
     flat = lambda t: t.reshape(t.shape[0], -1).double()
     out = {'MU_LCFIT': flat(mu).mean(dim=1), 'MUERR_LCFIT': flat(mu).std(dim=1, unbiased=False),
            'THETA': flat(cons['theta']).mean(dim=1), 'THETAERR': flat(cons['theta']).std(dim=1, unbiased=False),

@@ -388,6 +388,13 @@ def test_batch_fit_postprocess_fitres_matches_host_summaries(tmp_path):
     # split R-hat of one site against the host implementation
     rh = outputs.split_rhat_device(cons['theta']).cpu().numpy()
     assert np.allclose(rh, [summary.split_rhat(theta[s]) for s in range(6)], rtol=1e-6)
+    # MEANRHAT / MAXRHAT: arviz.summary's rank-normalised r_hat over mu, delM, theta, AV, Ds, tmax, peak_MJD and eps (:2315-2318)
+    hs = outputs.host_samples(cons)
+    sites = [hs[k][..., None, :] if hs[k].ndim == 3 else hs[k] for k in ('mu', 'delM', 'theta', 'AV', 'Ds', 'tmax', 'tmax', 'eps')]    # peak_MJD == tmax
+    per_sn = np.concatenate(sites, axis=2)                                               # (C, S, rows, N)
+    want = np.array([[summary.rank_rhat(per_sn[:, :, r, s]) for r in range(per_sn.shape[2])] for s in range(6)])
+    assert np.allclose(cols['MEANRHAT'], want.mean(axis=1), rtol=1e-9)
+    assert np.allclose(cols['MAXRHAT'], want.max(axis=1), rtol=1e-9)
     assert np.all(cols['MAXRHAT'] >= cols['MEANRHAT']) and np.all(cols['MAXRHAT'] < 1.5)
     # mu is drawn post hoc: std^2 ~ var(Ds) + sigma0^2-ish
     ds_sd = cons['Ds'].cpu().numpy().reshape(6, -1).std(axis=1)

@@ -200,8 +200,43 @@ def test_summary_statistics():
         ar[:, i] = 0.9 * ar[:, i - 1] + rng.randn(4)
     ess = summary.effective_sample_size(ar)
     assert 250 < ess < 700          # theory: 8000 (1-0.9)/(1+0.9) = 421
-    tab = summary.summary_table({'a': x, 'b': np.stack([x, ar], axis=-1)})
-    assert list(tab.index) == ['a', 'b[0]', 'b[1]'] and 'r_hat' in tab.columns
+    tab = summary.summary_table({'a': x, 'b': np.stack([x, ar], axis=-1)}, device='cpu')
+    assert list(tab.index) == ['a', 'b[0]', 'b[1]']
+    assert list(tab.columns) == ['mean', 'sd', 'hdi_3%', 'hdi_97%', 'mcse_mean', 'mcse_sd', 'ess_bulk', 'ess_tail', 'r_hat']
+
+
+def test_arviz_style_diagnostics_batched_against_per_site():
+    """fit_summary.csv / FITRES r-hat: the rank-normalised diagnostics of arviz.summary (Vehtari et al. 2021).  The
+    batched torch path against the per-site numpy statement on sites with autocorrelation, ties (stuck transitions),
+    a shifted chain, a chain of a different scale; and the properties the statistics are built for."""
+    import torch
+    from scipy.stats import rankdata
+    from bayesn_b200 import summary
+    rng = np.random.RandomState(3)
+    C, S, B = 4, 250, 120
+    x = rng.randn(C, S, B)
+    for i in range(1, S):
+        x[:, i, :40] = 0.8 * x[:, i - 1, :40] + x[:, i, :40]
+    x[:, :, 40:60] = np.round(x[:, :, 40:60], 1)
+    x[:, :, 60:70] = np.repeat(x[:, ::5, 60:70], 5, axis=1)
+    x[0, :, 70:80] += 1.5
+    x[1, :, 80:90] *= 3.0
+    a = summary.summary_table({'s': x}, device='cpu')
+    b = summary.summary_table_per_site({'s': x})
+    assert list(a.index) == list(b.index) and list(a.columns) == list(b.columns)
+    for c in a.columns:
+        assert np.allclose(a[c].values, b[c].values, rtol=1e-9, atol=1e-12), c
+    t = np.round(rng.randn(500), 1)
+    assert np.array_equal(summary._rank_average(t), rankdata(t))
+    xt = torch.from_numpy(np.ascontiguousarray(np.moveaxis(x, 2, 0)))
+    assert np.allclose(summary.rank_rhat_t(xt).numpy(), a['r_hat'].values, rtol=1e-12)
+    iid = a['r_hat'].values[90:]
+    assert np.all(np.abs(iid - 1) < 0.02)
+    assert np.all(a['r_hat'].values[70:80] > 1.1)                       # shifted chain: bulk statistic
+    classic = np.array([summary.split_rhat(x[:, :, i]) for i in range(80, 90)])
+    assert np.all(a['r_hat'].values[80:90] > 1.05) and np.all(classic < 1.02)       # scale: only the folded statistic sees it
+    assert np.all(a['ess_bulk'].values[:40] < 400) and np.all(a['ess_bulk'].values[90:] > 600)
+    assert np.allclose(a['mcse_mean'].values[90:], a['sd'].values[90:] / np.sqrt(1000), rtol=0.25)
 
 
 def test_training_oracle_gradient_finite_difference_and_golden():
