@@ -213,7 +213,8 @@ def constrain(model, samples_g, samples_l, muhat=None):
 
 def postprocess_training(model, samples, outputdir=None, mode='training_globalRV'):
     """Reference ``postprocess`` :2186-2242: W1 / theta sign convention and rescaling, posterior-mean
-    model written as ``bayesn.yaml`` (+ ``initial_chains.pkl`` / ``chains.pkl``).  Returns the YAML dict."""
+    model written as ``bayesn.yaml`` (+ ``initial_chains.pkl`` / ``fit_summary.csv`` / ``chains.pkl``, :2358-2364).
+    Returns the YAML dict and the post-processed samples."""
     import yaml
     samples = dict(samples)
     if outputdir is not None:
@@ -245,6 +246,9 @@ def postprocess_training(model, samples, outputdir=None, mode='training_globalRV
     if outputdir is not None:
         with open(os.path.join(outputdir, 'bayesn.yaml'), 'w') as fh:
             yaml.safe_dump(yaml_data, fh)
+        # convergence table of every parameter, then the post-processed chains (reference :2358-2364)
+        from . import summary
+        summary.summary_table(samples).to_csv(os.path.join(outputdir, 'fit_summary.csv'))
         with open(os.path.join(outputdir, 'chains.pkl'), 'wb') as fh:
             pickle.dump(samples, fh)
     return yaml_data, samples

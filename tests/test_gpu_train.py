@@ -260,4 +260,4 @@ def test_run_training_from_snana_text_directory(tmp_path, init):
     assert 'RV' not in y                                   # reference quirk (:2235): globalRV runs do not write RV
     ch = pickle.load(open(out / 'chains.pkl', 'rb'))
     assert ch['W1'].shape == (2, S, L * T)
-    assert (out / 'initial_chains.pkl').exists() and (out / 'input.yaml').exists()
+    assert (out / 'initial_chains.pkl').exists() and (out / 'input.yaml').exists() and (out / 'fit_summary.csv').exists()

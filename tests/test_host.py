@@ -248,6 +248,11 @@ def test_training_postprocess_sign_and_scale(tmp_path):
     back = yaml.safe_load(open(tmp_path / 'bayesn.yaml'))
     assert np.allclose(back['W0'], m.W0) and np.allclose(back['L_SIGMA_EPSILON'], 0.1 * np.eye(ne))
     assert (tmp_path / 'chains.pkl').exists() and (tmp_path / 'initial_chains.pkl').exists()
+    import pandas as pd
+    summ = pd.read_csv(tmp_path / 'fit_summary.csv', index_col=0)          # arviz.summary layout, one row per scalar
+    assert list(summ.columns) == ['mean', 'sd', 'hdi_3%', 'hdi_97%', 'mcse_mean', 'mcse_sd', 'ess_bulk', 'ess_tail', 'r_hat']
+    assert 'theta[4]' in summ.index and f'L_Omega[{ne - 1},{ne - 1}]' in summ.index and 'tauA' in summ.index
+    assert np.isfinite(summ.loc['theta[0]', 'r_hat']) and np.isnan(summ.loc['tauA', 'r_hat'])      # constants: NaN, as arviz
 
 
 def test_process_dataset_reads_snana_text_directory(tmp_path):
