@@ -103,17 +103,21 @@ def host_samples(cons):
 
 
 def _fitres_cell(v):
+    """Text of one FITRES cell as the reference produces it: the table is rounded to four decimals
+    (``fitres_table.round(4)``, :2330) and every value written with ``str()`` - so 35.1, not 35.1000."""
     if isinstance(v, str):
         return v
     if isinstance(v, (int, np.integer)):
         return str(int(v))
-    return f'{float(v):.4f}'
+    return str(np.round(np.float64(v), 4))
 
 
 def write_fitres(path, sn_names, columns, version_photometry='NULL', snana_version='NULL'):
-    """SNANA FITRES text table (reference :2296-2340 writes it with ``sncosmo.write_lc(fmt='snana',
-    metachar='')``): header comment block, ``VARNAMES:`` line, one ``SN:`` row per object.  Rows
-    with a NaN distance are dropped (:2332-2333).  Returns the number of rows dropped."""
+    """SNANA FITRES text table (reference :2296-2340).  The reference hands an astropy table whose first column is
+    named ``VARNAMES:`` and holds ``SN:`` (:2734-2742), with the header comment lines smuggled in as meta keys, to
+    ``sncosmo.write_lc(..., metachar='')`` - i.e. blank-separated ``key value`` meta lines, one line of column names,
+    one line per row: the header comment block, the ``VARNAMES:`` line and one ``SN:`` row per object written here.
+    Rows with a NaN distance are dropped (:2332-2333).  Returns the number of rows dropped."""
     names = list(columns.keys())
     keep = ~np.isnan(np.asarray(columns['MU_LCFIT'], dtype=float))
     with open(path, 'w') as fh:

@@ -54,38 +54,47 @@ def read_snana_ascii(path):
 
 def write_snana_lcfile(output_dir, snname, mjd, flt, mag, magerr, tmax, z_helio, z_cmb, z_cmb_err, ebv_mw, ra=None,
                        dec=None, author='anonymous', survey=None, paper=None, filename=None):
-    """Same header keys and OBS columns as the reference writer (``bayesn/bayesn_io.py:13-132``):
-    MJD FLT MAG MAGERR."""
-    mjd, mag, magerr = np.asarray(mjd, float), np.asarray(mag, float), np.asarray(magerr, float)
+    """Write user data to an SNANA-like light-curve file: the reference writer (``bayesn/bayesn_io.py:13-132``), same
+    arguments, header keys in the same order (preamble comment, SNID, SOURCE = ``survey``, RA, DEC, MWEBV,
+    REDSHIFT_HELIO, REDSHIFT_CMB, REDSHIFT_CMB_ERR, PEAKMJD, FILTERS, NOBS, NVAR), the same six columns
+    ``MJD FLT FLUXCAL FLUXCALERR MAG MAGERR`` (zero point 27.5, fluxes rounded to four decimals, values written with
+    ``str``), default file name ``snname[_survey][_paper].snana.dat``, the terminating ``END:``.  Like the reference it
+    returns the FILE NAME, not the path, and refuses a missing directory.  (The reference builds an astropy table whose
+    first column ``VARLIST:`` holds ``OBS:`` and lets sncosmo's plain ASCII writer print ``key value`` meta lines, the
+    column names and the rows - the text below.)"""
+    import time
     if not (len(mjd) == len(flt) == len(mag) == len(magerr)):
         raise ValueError('Provided columns are not the same length!')
+    if not os.path.exists(output_dir):
+        raise ValueError('Requested output directory does not exist!')
+    mjd, mag, magerr = np.asarray(mjd), np.asarray(mag, dtype=float), np.asarray(magerr, dtype=float)
+    fluxcal = 10 ** ((27.5 - mag) / 2.5)
+    fluxcalerr = np.round(fluxcal * magerr * np.log(10) / 2.5, 4)
+    fluxcal = np.round(fluxcal, 4)
+    divider = '-' * 59
+    datestamp = time.strftime('%Y.%m.%d', time.localtime())
+    timestamp = time.strftime('%H.%M hrs (%Z)', time.localtime())
+    lines = [f'# {snname} ', '# SNANA-like file generated from user-provided data',
+             '# Zeropoint of the converted SNANA file: 27.5 mag', f'# {divider}', f'# Data table created by: {author}',
+             f'# On date: {datestamp} (yyyy.mm.dd); {timestamp}.', '# Script used: BayeSNmodel.io.write_snana_lcfile.py',
+             f'# {divider}', f'SNID: {snname}']
+    if survey is not None:
+        lines.append(f'SOURCE: {survey}')
+    if ra is not None:
+        lines.append(f'RA: {ra}')
+    if dec is not None:
+        lines.append(f'DEC: {dec}')
+    filters = ','.join(np.unique(np.asarray(flt, dtype=str)))
+    lines += [f'MWEBV: {ebv_mw}', f'REDSHIFT_HELIO: {z_helio}', f'REDSHIFT_CMB: {z_cmb}', f'REDSHIFT_CMB_ERR: {z_cmb_err}',
+              f'PEAKMJD: {tmax}', f'FILTERS: {filters}', f'# {divider}', f'NOBS: {len(mjd)}', 'NVAR: 6',
+              'VARLIST: MJD FLT FLUXCAL FLUXCALERR MAG MAGERR']
+    for row in zip(mjd, flt, fluxcal, fluxcalerr, mag, magerr):
+        lines.append('OBS: ' + ' '.join(str(v) for v in row))
     if filename is None:
-        filename = f'{snname}.snana.dat'
-    path = os.path.join(output_dir, filename)
-    with open(path, 'w') as fh:
-        fh.write(f'SNID: {snname}\n')
-        fh.write(f'SOURCE: {author}\n' if author else '')
-        if survey is not None:
-            fh.write(f'SURVEY: {survey}\n')
-        if paper is not None:
-            fh.write(f'PAPER: {paper}\n')
-        if ra is not None:
-            fh.write(f'RA: {ra}\n')
-        if dec is not None:
-            fh.write(f'DEC: {dec}\n')
-        fh.write(f'FILTERS: {",".join(sorted(set(flt)))}\n')
-        fh.write(f'MWEBV: {ebv_mw}\n')
-        fh.write(f'REDSHIFT_HELIO: {z_helio}\n')
-        fh.write(f'REDSHIFT_CMB: {z_cmb}\n')
-        fh.write(f'REDSHIFT_CMB_ERR: {z_cmb_err}\n')
-        fh.write(f'REDSHIFT_FINAL: {z_cmb} +- {z_cmb_err}\n')
-        fh.write(f'SEARCH_PEAKMJD: {tmax}\n')
-        fh.write(f'NOBS: {len(mjd)}\nNVAR: 4\n')
-        fh.write('VARLIST: MJD FLT MAG MAGERR\n')
-        for a, b, c, d in zip(mjd, flt, mag, magerr):
-            fh.write(f'OBS: {a:.5f} {b} {c:.5f} {d:.5f}\n')
-        fh.write('END:\n')
-    return path
+        filename = snname + (survey is not None) * f'_{survey}' + (paper is not None) * f'_{paper}' + '.snana.dat'
+    with open(os.path.join(output_dir, filename), 'w') as fh:
+        fh.write('\n'.join(lines) + '\nEND:')
+    return filename
 
 
 def write_snana_fluxfile(output_dir, snname, mjd, flt, fluxcal, fluxcalerr, peak_mjd, z_helio, z_final, z_err=5e-4,

@@ -181,12 +181,31 @@ def test_hsiao_and_fits_readers():
 
 
 def test_snana_roundtrip(tmp_path):
+    """write_snana_lcfile keeps the reference's layout (bayesn/bayesn_io.py:13-132): header keys and their order, six
+    columns, default file name, returned value, END: terminator - and the reader takes it back."""
     from bayesn_b200 import snana
-    path = snana.write_snana_lcfile(str(tmp_path), 'sn1', [1.0, 2.5], ['g_PS1', 'r_PS1'], [17.1, 17.3], [0.02, 0.03],
-                                    0.0, 0.03, 0.031, 1e-4, 0.02)
-    meta, lc = snana.read_snana_ascii(path)
-    assert meta['REDSHIFT_HELIO'] == 0.03 and meta['MWEBV'] == 0.02
-    assert list(lc['FLT']) == ['g_PS1', 'r_PS1'] and np.allclose(lc['MAG'], [17.1, 17.3])
+    name = snana.write_snana_lcfile(str(tmp_path), 'sn1', [1.0, 2.5], ['r_PS1', 'g_PS1'], [17.1, 17.3], [0.02, 0.03],
+                                    0.5, 0.03, 0.031, 1e-4, 0.02, ra=10.5, survey='PS1MD', paper='X20')
+    assert name == 'sn1_PS1MD_X20.snana.dat'
+    text = open(tmp_path / name).read()
+    lines = text.split('\n')
+    assert lines[0] == '# sn1 ' and lines[1] == '# SNANA-like file generated from user-provided data'
+    keys = [l.split(':')[0] for l in lines if l and not l.startswith('#') and not l.startswith('OBS')]
+    assert keys == ['SNID', 'SOURCE', 'RA', 'MWEBV', 'REDSHIFT_HELIO', 'REDSHIFT_CMB', 'REDSHIFT_CMB_ERR', 'PEAKMJD',
+                    'FILTERS', 'NOBS', 'NVAR', 'VARLIST', 'END']
+    assert 'SOURCE: PS1MD' in lines and 'FILTERS: g_PS1,r_PS1' in lines and 'NVAR: 6' in lines
+    assert 'VARLIST: MJD FLT FLUXCAL FLUXCALERR MAG MAGERR' in lines
+    assert 'OBS: 1.0 r_PS1 14454.3977 266.2598 17.1 0.02' in lines and text.endswith('\nEND:')
+    meta, lc = snana.read_snana_ascii(str(tmp_path / name))
+    assert meta['REDSHIFT_HELIO'] == 0.03 and meta['MWEBV'] == 0.02 and meta['PEAKMJD'] == 0.5 and meta['SNID'] == 'sn1'
+    assert list(lc['FLT']) == ['r_PS1', 'g_PS1'] and np.allclose(lc['MAG'], [17.1, 17.3])
+    assert np.allclose(lc['FLUXCAL'], 10 ** ((27.5 - np.array([17.1, 17.3])) / 2.5), atol=1e-4)
+    assert snana.write_snana_lcfile(str(tmp_path), 'sn2', [1.0], ['g_PS1'], [17.0], [0.1], 0, 0.03, 0.03, 1e-4, 0.0) \
+        == 'sn2.snana.dat'
+    with pytest.raises(ValueError, match='does not exist'):
+        snana.write_snana_lcfile(str(tmp_path / 'nope'), 'sn1', [1.0], ['g_PS1'], [17.0], [0.1], 0, 0.03, 0.03, 1e-4, 0.0)
+    with pytest.raises(ValueError, match='same length'):
+        snana.write_snana_lcfile(str(tmp_path), 'sn1', [1.0, 2.0], ['g_PS1'], [17.0], [0.1], 0, 0.03, 0.03, 1e-4, 0.0)
 
 
 def test_summary_statistics():
