@@ -35,6 +35,8 @@ def parse_yaml_input(model, args, cmd_args=None):
                  ('outputdir', os.getcwd()), ('outfile_prefix', 'output'), ('sim_prescale', 1),
                  ('save_fit_errors', False), ('error_floor', 0.0)):
         args[k] = args.get(k, d)
+    pdp = args.get('private_data_path', [])
+    args['private_data_path'] = [pdp] if isinstance(pdp, str) else list(pdp)
     args['l_knots'] = args.get('l_knots', model.l_knots.tolist())
     args['tau_knots'] = args.get('tau_knots', model.tau_knots.tolist())
     args['fit_method'] = str(args['fit_method']).lower()
@@ -58,6 +60,40 @@ def parse_yaml_input(model, args, cmd_args=None):
     if not (args['mode'].lower() == 'fitting' and args['snana']):
         os.makedirs(args['outputdir'], exist_ok=True)
     return args
+
+
+def resolve_photometry_dir(args):
+    """Where ``version_photometry`` lives (reference :2401-2426).  Outside SNANA batch mode it is a path.  With
+    ``jobsplit`` (``args['snana']``) it is the NAME of a photometry version, looked up under ``$SNDATA_ROOT/lcmerge``,
+    ``$SNDATA_ROOT/SIM``, the directories listed in ``$SNDATA_ROOT/SIM/PATH_SNDATA_SIM.LIST`` and ``private_data_path``
+    (entries may start with ``$ENVVAR``); it has to exist in exactly one of them.  (The reference glues the path
+    components after the first together without separators, so only one-level sub-directories of an environment
+    variable work there; here the rest of the path is kept as it is, and absolute paths are taken literally.)"""
+    data_dir = args['version_photometry']
+    if not args.get('snana'):
+        return data_dir
+    root = os.environ.get('SNDATA_ROOT')
+    dir_list = ['SNDATA_ROOT/lcmerge', 'SNDATA_ROOT/SIM']
+    sim_list = os.path.join(root, 'SIM', 'PATH_SNDATA_SIM.LIST') if root else None
+    if sim_list and os.path.exists(sim_list):
+        dir_list += [str(d)[1:] if str(d).startswith('$') else str(d) for d in np.atleast_1d(np.loadtxt(sim_list, dtype=str))]
+    dir_list += [p[1:] if p.startswith('$') else p for p in args.get('private_data_path', [])]
+    found = []
+    for d in dir_list:
+        if os.path.isabs(d):
+            cand = os.path.join(d, data_dir)
+        else:
+            head, _, rest = d.partition('/')
+            cand = os.path.join(os.environ.get(head, 'NULL'), rest, data_dir)
+        if os.path.exists(cand) and os.path.realpath(cand) not in [os.path.realpath(f) for f in found]:
+            found.append(cand)
+    if len(found) == 0:
+        raise ValueError(f'Requested photometry {data_dir} was not found in any of the usual public '
+                         f'locations, maybe you need to specify an additional private data location')
+    if len(found) > 1:
+        raise ValueError(f'Requested photometry {data_dir} was found in multiple locations, please remove '
+                         f'duplicates and ensure the one you want to use remains')
+    return found[0]
 
 
 def _snrmax(flux, ferr, bands):
@@ -148,8 +184,11 @@ def process_dataset(model, args):
         for k in FITRES_COLUMNS:
             cols[k].append(vals[k])
 
+    if 'version_photometry' not in args and 'data_table' not in args:
+        raise ValueError('Please pass either data_dir (for a directory containing all SNANA files such as a '
+                         'simulation output) or a combination of data_table and data_root')
     if 'version_photometry' in args:
-        data_dir = args['version_photometry']
+        data_dir = resolve_photometry_dir(args)
         name = os.path.split(os.path.normpath(data_dir))[-1]
         sn_files = np.atleast_1d(np.loadtxt(os.path.join(data_dir, f'{name}.LIST'), dtype=str))
         meta0, _ = snana.read_snana_ascii(os.path.join(data_dir, str(sn_files[0])))

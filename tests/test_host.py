@@ -515,6 +515,42 @@ def test_process_dataset_text_directory_jobsplit_and_data_table(tmp_path):
         driver.process_dataset(m, dict(at, data_root=None) if False else {k: v for k, v in at.items() if k != 'data_root'})
 
 
+def test_snana_batch_mode_finds_photometry_version_by_name(tmp_path, monkeypatch):
+    """With ``jobsplit`` (SNANA batch mode) ``version_photometry`` is the NAME of a photometry version searched under
+    $SNDATA_ROOT/lcmerge, $SNDATA_ROOT/SIM, the directories of PATH_SNDATA_SIM.LIST and ``private_data_path``
+    (reference :2401-2426); IDSURVEY comes from $SNDATA_ROOT/SURVEY.DEF (:2427-2433)."""
+    from bayesn_b200 import SEDmodel, driver
+    m = SEDmodel(load_model='T21_model')
+    root = tmp_path / 'sndata'
+    (root / 'SIM').mkdir(parents=True)
+    (root / 'lcmerge').mkdir()
+    extra = tmp_path / 'moresims'
+    extra.mkdir()
+    (root / 'SIM' / 'PATH_SNDATA_SIM.LIST').write_text('$MORESIMS\n')
+    (root / 'SURVEY.DEF').write_text('SURVEY: OTHER 5\nSURVEY: TESTSURVEY 42\n')
+    monkeypatch.setenv('SNDATA_ROOT', str(root))
+    monkeypatch.setenv('MORESIMS', str(extra))
+    monkeypatch.setenv('MYPRIV', str(tmp_path))
+    fmap = {'g': 'g_PS1', 'r': 'r_PS1', 'i': 'i_PS1', 'z': 'z_PS1'}
+    for where, name in ((root / 'SIM', 'VER_A'), (extra, 'VER_B'), (tmp_path / 'priv' / 'deep', 'VER_C')):
+        d = where / name
+        d.mkdir(parents=True)
+        _write_objects(d, m)
+    base = dict(mode='fitting', outputdir=str(tmp_path / 'o'), map=fmap, jobsplit=[1, 1])
+    for name, extra_args in (('VER_A', {}), ('VER_B', {}), ('VER_C', dict(private_data_path='$MYPRIV/priv/deep'))):
+        args = driver.parse_yaml_input(m, dict(base, version_photometry=name, **extra_args))
+        assert args['snana'] and isinstance(args['private_data_path'], list)
+        ds = driver.process_dataset(m, args)
+        assert len(ds['sn_names']) == 5 and ds['survey'] == 'TESTSURVEY' and np.all(np.asarray(ds['fitres']['IDSURVEY']) == 42)
+    with pytest.raises(ValueError, match='not found in any of the usual public'):
+        driver.process_dataset(m, driver.parse_yaml_input(m, dict(base, version_photometry='VER_C')))
+    (root / 'lcmerge' / 'VER_A').mkdir()
+    with pytest.raises(ValueError, match='found in multiple locations'):
+        driver.process_dataset(m, driver.parse_yaml_input(m, dict(base, version_photometry='VER_A')))
+    with pytest.raises(ValueError, match='Please pass either data_dir'):
+        driver.process_dataset(m, driver.parse_yaml_input(m, dict(mode='fitting', outputdir=str(tmp_path / 'o'))))
+
+
 def test_simulate_spectrum_argument_errors_match_reference():
     """simulate_spectrum (reference :2962-3056) validates its per-object arguments before any device work."""
     from bayesn_b200 import SEDmodel
