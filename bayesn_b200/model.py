@@ -671,7 +671,7 @@ class SEDmodel(object):
         SURVEY Appendix E) and computes host / Milky Way extinction arrays it never applies; here the instance is left
         untouched: the grid is evaluated in chunks of 300 bins by the ``get_spectra`` kernel on temporary tables."""
         import torch
-        from .static import spline_matrix, inv_kd, F99_XK
+        from .static import spline_matrix, inv_kd, fitz_matrix
 
         def per_object(val, name, msg=None):
             val = np.array(val)
@@ -718,7 +718,7 @@ class SEDmodel(object):
         args = (to(theta), to(AV), to(self.W0), to(self.W1), to(eps), to(RV), to(J_t), to(hsiao_interp))
         KD_l = inv_kd(self.l_knots)
         ph, hw, hf = datafiles.load_hsiao()
-        KD_h, KD_x = inv_kd(hw), inv_kd(F99_XK)
+        KD_h = inv_kd(hw)
         nb = native.NBINS
         pad = lambda a: np.concatenate([a, np.zeros((nb - a.shape[0],) + a.shape[1:])], axis=0)
         ctx = self._context(native.RV_FIXED)
@@ -726,7 +726,7 @@ class SEDmodel(object):
         for c0 in range(0, l_r.shape[0], nb):
             lam = l_r[c0:c0 + nb]
             ctx.set_model(tau_knots=self.tau_knots, KD_t=self.KD_t, J_l=pad(spline_matrix(lam, self.l_knots, KD_l)),
-                          hsiao=pad(spline_matrix(lam, hw, KD_h) @ hf.T), M_fitz=pad(spline_matrix(1e4 / lam, F99_XK, KD_x)),
+                          hsiao=pad(spline_matrix(lam, hw, KD_h) @ hf.T), M_fitz=pad(fitz_matrix(lam)),
                           a_dust=np.ones(nb), W0=self.W0, W1=self.W1, L_Sigma=self.L_Sigma, tauA=self.tauA,
                           Ds_prior_sd=math.sqrt(25.0 + self.sigma0 ** 2))
             out = ctx.spectra_batch(*args)                               # (N, 300, n_t)

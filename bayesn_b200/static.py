@@ -186,6 +186,40 @@ def f99_alav(wave, RV):
     return 1.0 + k / RV
 
 
+def fitz_matrix(wave):
+    """(n, 9) matrix M with k(lambda - V)/E(B - V) = M yk(R_V) on the rest-frame wavelengths ``wave`` for EVERY R_V - the
+    reference's ``M_fitz_block`` (:313-316) with its FM90 ultraviolet override (``get_spectra`` :627-638) folded in.
+
+    At lambda >= 2700 A the rows are the natural-cubic-spline weights of the nine F99 anchors.  Below, the reference
+    overwrites the spline value by k = c1 + c2 x + c3 D(x) (+ c4 F(x) at x >= 5.9), with c2 = -0.824 + 4.717 / R_V and
+    c1 = 2.030 - 3.007 c2.  That is P(x) + Q(x) / R_V with
+        P = 2.030 + c3 D + c4 F - 0.824 (x - 3.007),    Q = 4.717 (x - 3.007),
+    and the two ultraviolet anchors yk[7], yk[8] are the same expression at x = 1e4/2700, 1e4/2600: they span {1, 1/R_V}.
+    So the row (0, ..., 0, alpha, beta) with alpha (P7, Q7) + beta (P8, Q8) = (P, Q) reproduces the override exactly and
+    every kernel that forms M yk - fixed, per-object or sampled R_V, forward or gradient - gets the branch for free."""
+    wave = np.asarray(wave, dtype=np.float64)
+    M = spline_matrix(1e4 / wave, F99_XK, inv_kd(F99_XK))
+    uv = wave < UV_LIMIT_AA
+    if np.any(uv):
+        def pq(x):
+            x2 = x * x
+            y = x2 - F99_X0 ** 2
+            P = 2.030 + F99_C3 * x2 / (y * y + x2 * F99_GAMMA ** 2) - 0.824 * (x - 3.007)
+            return P, 4.717 * (x - 3.007)
+        x = 1e4 / wave[uv]
+        P, Q = pq(x)
+        far = x >= F99_C5
+        yy = x[far] - F99_C5
+        P[far] += F99_C4 * (0.5392 * yy ** 2 + 0.05644 * yy ** 3)
+        (P7, P8), (Q7, Q8) = pq(F99_XK[7:9])
+        det = P7 * Q8 - P8 * Q7
+        rows = np.zeros((x.shape[0], 9))
+        rows[:, 7] = (P * Q8 - P8 * Q) / det
+        rows[:, 8] = (P7 * Q - P * Q7) / det
+        M[uv] = rows
+    return M
+
+
 # ----------------------------------------------------------------------------------------
 # model grid, Hsiao template, filters
 # ----------------------------------------------------------------------------------------
@@ -196,13 +230,6 @@ class ModelGrid:
         self.l_knots = np.asarray(l_knots, dtype=np.float64)
         self.tau_knots = np.asarray(tau_knots, dtype=np.float64)
         self.max_redshift = MAX_REDSHIFT
-        if self.l_knots[0] < UV_LIMIT_AA:
-            # the FM90 UV branch of the host-dust law (reference get_spectra :627-638, rest wavelengths below
-            # 2700 A) is not built into the kernels: every shipped model starts at 2800 A or redder.  Refuse
-            # instead of silently applying the optical spline where the reference would not.
-            raise ValueError(f'l_knots[0] = {self.l_knots[0]:.1f} A is below {UV_LIMIT_AA:.0f} A: the Fitzpatrick99 UV '
-                             f'branch (reference bayesn_model.py:627-638) is not implemented in the sm_100a kernels; '
-                             f'models must start at >= {UV_LIMIT_AA:.0f} A rest frame')
         lo, hi = np.log10(self.l_knots[0]), np.log10(self.l_knots[-1])
         self.model_log_wave = np.linspace(lo, hi, SPECTRUM_BINS)
         self.model_spacing = self.model_log_wave[1] - self.model_log_wave[0]
@@ -214,7 +241,7 @@ class ModelGrid:
         self.KD_l = inv_kd(self.l_knots)
         self.J_l = spline_matrix(self.model_wave, self.l_knots, self.KD_l)      # (300, L)
         self.KD_t = inv_kd(self.tau_knots)                                      # (T, T)
-        self.M_fitz = spline_matrix(1e4 / self.model_wave, F99_XK, inv_kd(F99_XK))  # (300, 9)
+        self.M_fitz = fitz_matrix(self.model_wave)                               # (300, 9), FM90 UV rows below 2700 A
         ph, hw, hf = datafiles.load_hsiao()
         self.hsiao_phase = ph
         J_h = spline_matrix(self.model_wave, hw, inv_kd(hw))                    # (300, 2401)

@@ -276,8 +276,15 @@ class RefSED:
                             1e4 / 2700., 1e4 / 2600.])
         KD_x = invKD_irr(self.xk)
         self.M_fitz_block = spline_coeffs_irr(1e4 / self.model_wave, self.xk, KD_x)
+        self._set_uv_indices()
+
+    # ------------------------------------------------------------ bayesn_model.py:475-481
+    def _set_uv_indices(self):
+        """Bins below 2700 A take the FM90 ultraviolet form of the F99 law in ``get_spectra`` (:627-638)."""
         self.uv_ind1 = self.model_wave < 2700
-        assert not self.uv_ind1.any(), 'UV branch (:627-638) not restated: no shipped model reaches < 2700 A'
+        self.uv_ind2 = (self.model_wave < 2700) & ((1e4 / self.model_wave) >= 5.9)
+        self.uv_ind3 = (1e4 / self.model_wave[self.uv_ind1]) >= 5.9
+        self.uv_x = 1e4 / self.model_wave[self.uv_ind1]
 
     # ------------------------------------------------------------ bayesn_model.py:499-554
     def _calculate_band_weights(self, redshifts, ebv):
@@ -375,6 +382,21 @@ class RefSED:
             f99_c1 + f99_c2 * xk[7] + f99_c3 * f99_d1,
             f99_c1 + f99_c2 * xk[8] + f99_c3 * f99_d2], dim=1)            # (num_batch, 9)
         A = AV[..., None] * (1 + (torch.as_tensor(self.M_fitz_block) @ yk.T).T / RV[..., None])
+        if self.uv_ind1.any():                                             # :627-638
+            f99_c4, f99_c5 = 0.41, 5.9
+            uv_x = torch.as_tensor(self.uv_x)
+            c2 = -0.824 + 4.717 / RV[..., None]
+            c1 = 2.030 - 3.007 * c2
+            x2 = uv_x * uv_x
+            y = x2 - f99_x0 * f99_x0
+            d = x2 / (y * y + x2 * f99_gamma * f99_gamma)
+            k = c1 + c2 * uv_x + f99_c3 * d
+            A = A.clone()
+            A[:, torch.as_tensor(self.uv_ind1)] = AV[..., None] * (1. + k / RV[..., None])
+            y = uv_x - f99_c5
+            y2 = y * y
+            k = k + f99_c4 * (0.5392 * y2 + 0.05644 * y2 * y)
+            A[:, torch.as_tensor(self.uv_ind2)] = AV[..., None] * (1. + k[..., torch.as_tensor(self.uv_ind3)] / RV[..., None])
         f_A = 10 ** (-0.4 * A)
         model_spectra = model_spectra * f_A[..., None]
         return model_spectra
@@ -389,6 +411,7 @@ class RefSED:
         l_r = np.arange(min(self.l_knots), max(self.l_knots) + dl, dl, dtype=float)
         l_r = l_r[l_r <= max(self.l_knots)]
         self.model_wave = l_r
+        self._set_uv_indices()
         self.J_l_T = spline_coeffs_irr(self.model_wave, self.l_knots, invKD_irr(self.l_knots))
         self.M_fitz_block = spline_coeffs_irr(1e4 / self.model_wave, self.xk, invKD_irr(self.xk))
         self._load_hsiao_template()

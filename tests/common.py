@@ -85,3 +85,21 @@ def compare_logp_grad(case, n_chains=2, rv=None, seed=3, jitter=0.3, fix=None):
         worst_lp = max(worst_lp, float(np.max(np.abs(lp[:, c] - lpo) / np.abs(lpo))))
         worst_g = max(worst_g, float(np.max(np.max(np.abs(g[:, c] - go), axis=1) / np.max(np.abs(go), axis=1))))
     return dict(logp_rel=worst_lp, grad_rel=worst_g, weights_rel=w_rel, ctx=ctx, model=m, D=D)
+
+
+def write_uv_model(tmp_path, blue_knot=2300.0, base='T21_model', pop_rv=False):
+    """A custom model whose first wavelength knot lies below 2700 A (the FM90 ultraviolet branch of the host-dust law,
+    reference get_spectra :627-638): a shipped model with its blue knot moved.  Returns the path of its BAYESN.YAML."""
+    import os
+    import yaml
+    from bayesn_b200 import datafiles
+    d = dict(datafiles.load_model_yaml(base))
+    d['L_KNOTS'] = [float(blue_knot)] + [float(x) for x in d['L_KNOTS'][1:]]
+    if pop_rv:
+        d.pop('RV', None)
+        d['MUR'], d['SIGMAR'] = 2.8, 0.6
+    out = {k: (np.asarray(v).tolist() if not isinstance(v, (int, float, str)) else v) for k, v in d.items()}
+    path = os.path.join(str(tmp_path), f'uv{"_pop" if pop_rv else ""}_model.yaml')
+    with open(path, 'w') as fh:
+        yaml.safe_dump(out, fh)
+    return path

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.common import make_case, product_model, to_kernel_layout, to_oracle_layout
+from tests.common import compare_logp_grad, make_case, product_model, to_kernel_layout, to_oracle_layout, write_uv_model
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -510,3 +510,35 @@ def test_simulate_spectrum_matches_oracle_grid_rebuild(model, dl):
         m.simulate_spectrum(t, 3, RV=np.ones(2))
     with pytest.raises(ValueError, match='epsilon'):
         m.simulate_spectrum(t, 3, eps=1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('pop_rv,rv', [(False, None), (False, 'uniform'), (True, None)])
+def test_ultraviolet_dust_branch_parity(tmp_path, pop_rv, rv):
+    """A model reaching below 2700 A rest frame (blue knot at 2300 A, SNe at z = 0.5-0.65 so that g_PS1 integrates over
+    the FM90 ultraviolet bins, reference get_spectra :627-638): log p / gradient with fixed, uniform and population R_V,
+    and the spectra, against the oracle's explicit override."""
+    path = write_uv_model(tmp_path, pop_rv=pop_rv)
+    case = make_case(path, ['g_PS1', 'r_PS1', 'i_PS1'], np.arange(-8, 36, 4.0), N=7, seed=12, zrange=(0.5, 0.65))
+    ref = case['ref']
+    assert ref.uv_ind1.sum() > 20
+    res = compare_logp_grad(case, n_chains=2, rv=rv)
+    _report('uv_branch', dict(pop_rv=pop_rv, rv=str(rv), logp_rel=res['logp_rel'], grad_rel=res['grad_rel']))
+    assert res['logp_rel'] < LOGP_TOL and res['grad_rel'] < GRAD_TOL, res
+    m = res['model']
+    obs, p = case['obs'], case['params']
+    N = obs.shape[-1]
+    J_t, hsi = ref.J_t_and_hsiao(torch.as_tensor(obs[0]))
+    RV = np.linspace(1.5, 5.0, N)
+    tt = lambda a: torch.as_tensor(np.asarray(a))
+    s_ref = ref.get_spectra(tt(p['theta']), tt(p['AV']), tt(ref.W0), tt(ref.W1), tt(p['eps']), tt(RV), J_t, hsi).numpy()
+    s_gpu = m.get_spectra(p['theta'], p['AV'], ref.W0, ref.W1, p['eps'], RV, J_t.numpy(), hsi.numpy())
+    assert np.max(np.abs(s_gpu - s_ref) / np.abs(s_ref)) < 1e-5
+    # the ultraviolet bins carry weight in these fits: without the override the oracle's log p moves by more than the tolerance
+    sel = ref.uv_ind1.copy()
+    ref.uv_ind1, ref.uv_ind2, ref.uv_ind3, ref.uv_x = sel & False, sel & False, ref.uv_ind3[:0], ref.uv_x[:0]
+    try:
+        res0 = compare_logp_grad(case, n_chains=2, rv=rv)
+    finally:
+        ref._set_uv_indices()
+    assert res0['logp_rel'] > 3 * LOGP_TOL and res0['logp_rel'] > 5 * res['logp_rel'], (res0['logp_rel'], res['logp_rel'])

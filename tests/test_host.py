@@ -562,3 +562,45 @@ def test_simulate_spectrum_argument_errors_match_reference():
                     (dict(ebv_mw=np.zeros(2)), 'For ebv_mw')]:
         with pytest.raises(ValueError, match=msg):
             m.simulate_spectrum(t, 3, **kw)
+
+
+def test_f99_ultraviolet_branch_lives_in_the_dust_table(tmp_path):
+    """Host-dust law below 2700 A (reference get_spectra :627-638): the FM90 form k = c1 + c2 x + c3 D (+ c4 F) is
+    P(x) + Q(x) / R_V, which the two ultraviolet anchors of the F99 spline span - so the rows of ``M_fitz`` carry it
+    exactly for every R_V, and the oracle's explicit override agrees."""
+    import torch
+    from bayesn_b200 import SEDmodel
+    from bayesn_b200.static import fitz_matrix, f99_yk, f99_alav
+    from oracle.ref_model import RefSED
+    from tests.common import write_uv_model
+    wave = np.concatenate([np.linspace(1150, 2699.99, 300), np.linspace(2700, 18000, 60)])
+    M = fitz_matrix(wave)
+    assert np.all(M[:300, :7] == 0) and np.any(M[300:, :7] != 0)
+    for RV in (1.2, 2.0, 3.1, 4.5, 6.0):
+        yk, dyk = f99_yk(np.float64(RV))
+        assert np.allclose(1 + M @ yk / RV, f99_alav(wave, RV), rtol=0, atol=1e-12)
+        h = 1e-5                                            # and the R_V derivative the sampled-R_V kernels use
+        fd = (f99_alav(wave, RV + h) - f99_alav(wave, RV - h)) / (2 * h)
+        assert np.allclose(M @ dyk / RV - M @ yk / RV ** 2, fd, atol=1e-7)
+    path = write_uv_model(tmp_path)
+    m = SEDmodel(load_model=path)                           # accepted now (it used to be rejected)
+    ref = RefSED(path, bands=['g_PS1'])
+    nuv = int((m.grid.model_wave < 2700).sum())
+    assert nuv > 20 and ref.uv_ind1.sum() == nuv
+    N = 4
+    RV = np.array([1.5, 2.5, 3.1, 5.0])
+    AV = np.array([0.1, 0.5, 1.0, 0.3])
+    t = torch.zeros(1, N, dtype=torch.float64)
+    J_t, hsi = ref.J_t_and_hsiao(t)
+    tn = lambda a: torch.as_tensor(np.asarray(a, dtype=float))
+    z = np.zeros
+    s1 = ref.get_spectra(tn(z(N)), tn(AV), tn(ref.W0), tn(ref.W1), tn(z((N,) + ref.W0.shape)), tn(RV), J_t, hsi).numpy()
+    s0 = ref.get_spectra(tn(z(N)), tn(0 * AV), tn(ref.W0), tn(ref.W1), tn(z((N,) + ref.W0.shape)), tn(RV), J_t, hsi).numpy()
+    A_oracle = -2.5 * np.log10(s1[:, :, 0] / s0[:, :, 0])
+    a_prod, _ = m.grid.dust_basis(RV)
+    assert np.allclose(A_oracle, AV[:, None] * a_prod, rtol=1e-10, atol=1e-12)
+    assert np.allclose(a_prod, np.stack([f99_alav(m.grid.model_wave, r) for r in RV]), atol=1e-12)
+    # the override is not cosmetic: the optical spline extrapolated below 2700 A is off by several per cent
+    from bayesn_b200.static import spline_matrix, inv_kd, F99_XK
+    a_spline = 1 + (spline_matrix(1e4 / m.grid.model_wave, F99_XK, inv_kd(F99_XK)) @ f99_yk(np.float64(3.1))[0]) / 3.1
+    assert np.max(np.abs(a_spline[:nuv] / a_prod[2, :nuv] - 1)) > 0.01
