@@ -53,7 +53,10 @@ typedef struct {
     const float* KD_t;        /* [T][T]   invKD_irr(tau_knots) */
     const float* J_l;         /* [300][L] spline_coeffs_irr(model_wave, l_knots) */
     const float* hsiao;       /* [300][105] Hsiao template on the model grid */
-    const float* M_fitz;      /* [300][9] F99 spline basis */
+    const float* M_fitz;      /* [300][9] F99 basis: k(lambda-V)/E(B-V) = M_fitz yk(R_V).  Spline weights of the nine
+                                 anchors (reference M_fitz_block, bayesn_model.py:313-316); for bins below 2700 A the
+                                 row must be (0,..,0,alpha,beta) reproducing the FM90 ultraviolet override of
+                                 get_spectra (:627-638) - bayesn_b200.static.fitz_matrix builds it */
     const float* a_dust;      /* [300] 1 + (M_fitz yk(RV))/RV for the global RV (RV_FIXED only) */
     const float* W0;          /* [L][T] */
     const float* W1;          /* [L][T] */
