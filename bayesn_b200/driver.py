@@ -62,6 +62,24 @@ def parse_yaml_input(model, args, cmd_args=None):
     return args
 
 
+def apply_training_knots(model, args):
+    """Training runs may define the model they infer on their own knots (``l_knots`` / ``tau_knots`` of the input,
+    reference :1721-1727): the wavelength / time grids, filter curves and spline tables are rebuilt for them.  W0, W1
+    and L_Sigma of the loaded model then no longer have the shape of the model being trained; they are not used by
+    the training density (the sampler carries its own), so they are replaced by placeholders of the new shape."""
+    lk, tk = np.array(args['l_knots'], dtype=float), np.array(args['tau_knots'], dtype=float)
+    if lk.shape == model.l_knots.shape and tk.shape == model.tau_knots.shape \
+            and np.array_equal(lk, model.l_knots) and np.array_equal(tk, model.tau_knots):
+        return False
+    model.l_knots, model.tau_knots = lk, tk
+    model._setup_band_weights()
+    L, T = len(lk), len(tk)
+    if np.shape(model.W0) != (L, T):
+        ne = (L - 2) * T
+        model.W0, model.W1, model.L_Sigma = np.zeros((L, T)), np.zeros((L, T)), 0.1 * np.eye(ne)
+    return True
+
+
 def resolve_photometry_dir(args):
     """Where ``version_photometry`` lives (reference :2401-2426).  Outside SNANA batch mode it is a path.  With
     ``jobsplit`` (``args['snana']``) it is the NAME of a photometry version, looked up under ``$SNDATA_ROOT/lcmerge``,
@@ -436,6 +454,8 @@ def run(model, args, cmd_args=None, group=None):
         group = torch.distributed.group.WORLD
     if group is not None:
         rank, world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
+    if 'training' in mode:
+        apply_training_knots(model, args)
     ds = process_dataset(model, args)
     model.data, model.sn_list, model.peak_mjds = ds['obs'], ds['sn_names'], ds['peak_mjds']
     model.used_band_inds = ds['band_inds']

@@ -151,6 +151,46 @@ class SEDmodel(object):
         from . import driver
         return driver.process_dataset(self, args)
 
+    # thin mirrors of reference methods that live in other modules here
+    def parse_yaml_input(self, args, cmd_args=None):
+        """Reference :1656-1733: defaults + command-line overrides, the knots of a training run, then the data set."""
+        from . import driver
+        args = driver.parse_yaml_input(self, args, cmd_args)
+        if 'training' in args['mode'].lower():
+            driver.apply_training_knots(self, args)
+        ds = driver.process_dataset(self, args)
+        self.data, self.sn_list, self.peak_mjds = ds['obs'], ds['sn_names'], ds['peak_mjds']
+        self.used_band_inds = ds['band_inds']
+        t = self.data[0, ...]
+        self.hsiao_interp = np.array([HSIAO_PHASE0_INDEX + np.floor(t), HSIAO_PHASE0_INDEX + np.ceil(t), np.remainder(t, 1)])
+        self._dataset = ds
+        return args
+
+    def initial_guess(self, args, reference_model='M20_model'):
+        """Reference :1568-1654: the dictionary of starting values of a training run (global numpy RNG, the
+        reference's draw order), for the data set loaded by ``parse_yaml_input`` / ``run``."""
+        from . import train as btrain
+        return btrain.initial_values(self, self.data, reference_model, mode=args.get('mode', 'training_globalRV'))
+
+    def postprocess(self, samples, args):
+        """Reference :2169-2367 for samples in the reference layout: the training branch (sign convention, rescaling,
+        ``bayesn.yaml``, chains) or, for fits, ``chains.pkl`` + ``fit_summary.csv`` (the FITRES / LCPLOT tables are
+        written by ``run`` from the device-side summaries)."""
+        from . import train as btrain, outputs
+        if 'W1' in samples:
+            return btrain.postprocess_training(self, samples, args['outputdir'], args['mode'])
+        return outputs.write_chains(samples, args['outputdir'])
+
+    @staticmethod
+    def spline_coeffs_irr_step(x_now, x, invkd):
+        """Reference :761-816: the row of the cubic-spline matrix at one point (vectorised here over any shape)."""
+        return spline_row(x_now, np.asarray(x, dtype=np.float64), np.asarray(invkd, dtype=np.float64))
+
+    def _load_hsiao_template(self):
+        """Reference :260-285: the Hsiao template resampled onto the model's wavelength grid."""
+        self.hsiao_flux = self.grid.hsiao_flux
+        self.hsiao_t = self.grid.hsiao_phase
+
     def prepare_training(self, obs, weights, band_inds=None):
         """Upload a training set (``obs[1]``/``obs[2]`` in magnitudes, reference :2711-2730) and
         return the native context for ``train_logp_grad`` (``train_model_globalRV``, :1115-1182)."""

@@ -41,7 +41,7 @@ def simulate_training_set(model, N, seed=0, bands=('B_CSP', 'V_CSP', 'r_CSP', 'i
     return obs, weights, band_inds
 
 
-def initial_values(model, obs, reference_model='M20_model', rng=None):
+def initial_values(model, obs, reference_model='M20_model', rng=None, mode='training_globalRV'):
     """``SEDmodel.initial_guess`` (reference :1568-1654): W0 / W1 of a trained model interpolated
     onto this model's knots (cubic in wavelength, linear in time, zero outside), jittered; fixed
     starting values for the other globals; prior draws for the latents."""
@@ -49,8 +49,12 @@ def initial_values(model, obs, reference_model='M20_model', rng=None):
     rng = np.random if rng is None else rng
     if os.path.exists(reference_model):
         params = datafiles.load_yaml(reference_model)
-    else:
+    elif reference_model in datafiles.builtin_models():
         params = datafiles.load_model_yaml(reference_model)
+    else:
+        raise ValueError("Invalid initialisation method, please choose either 'median' or 'sample', or choose "
+                         "either one of the built-in models or a custom model to base the hyperparmeter "
+                         "initialisation on")
     W0, W1 = np.array(params['W0'], dtype=float), np.array(params['W1'], dtype=float)
     lk, tk = np.array(params['L_KNOTS'], dtype=float), np.array(params['TAU_KNOTS'], dtype=float)
     tauA_init = float(params['TAUA'])
@@ -65,11 +69,27 @@ def initial_values(model, obs, reference_model='M20_model', rng=None):
     while tauA_ < 0:
         tauA_ = tauA_init + rng.normal(0, 0.01)
     sigma0_ = 0.1 + rng.normal(0, 0.01)
-    init = {'W0': W0 + rng.normal(0, 0.01, W0.shape[0]), 'W1': W1 + rng.normal(0, 0.01, W1.shape[0]), 'RV': 3.0,
-            'tauA_tform': math.atan(tauA_ / 1.0), 'sigma0_tform': math.atan(sigma0_ / 0.1),
-            'theta': rng.normal(0, 1, n_sne), 'AV': rng.exponential(tauA_, n_sne),
-            'sigmaepsilon_tform': np.arctan(0.1 * np.ones(ne) + rng.normal(0, 0.01, ne) / 1.0),
-            'L_Omega': np.eye(ne), 'Ds': rng.normal(obs[-3, 0, :], sigma0_)}
+    sigmaepsilon_init = 0.1 * np.ones(ne)
+    # same keys, same order of random draws as the reference (:1626-1652), so that a seeded numpy RNG gives the
+    # same dictionary; the sampler takes the entries that name sample sites of train_model_globalRV
+    init = {'W0': W0 + rng.normal(0, 0.01, W0.shape[0]), 'W1': W1 + rng.normal(0, 0.01, W1.shape[0])}
+    if 'poprv' in mode.lower():
+        init['mu_R'], init['sigma_R'] = 3.0, 0.5
+        init['RV_tform'] = rng.uniform(0, 1, n_sne)
+    else:
+        init['RV'] = 3.0
+    init['tauA_tform'] = math.atan(tauA_ / 1.0)
+    init['sigma0_tform'] = math.atan(sigma0_ / 0.1)
+    init['sigma0'] = sigma0_
+    init['theta'] = rng.normal(0, 1, n_sne)
+    init['AV'] = rng.exponential(tauA_, n_sne)
+    L_Sigma = np.diag(sigmaepsilon_init) @ np.eye(ne)
+    init['epsilon_tform'] = np.linalg.inv(L_Sigma) @ rng.normal(0, 1, (ne, n_sne))
+    init['epsilon'] = rng.normal(0, 1, (n_sne, ne))
+    init['sigmaepsilon_tform'] = np.arctan(sigmaepsilon_init + rng.normal(0, 0.01, ne) / 1.0)
+    init['sigmaepsilon'] = sigmaepsilon_init + rng.normal(0, 0.01, ne)
+    init['L_Omega'] = np.eye(ne)
+    init['Ds'] = rng.normal(obs[-3, 0, :], sigma0_)
     return init
 
 

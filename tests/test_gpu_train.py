@@ -261,3 +261,35 @@ def test_run_training_from_snana_text_directory(tmp_path, init):
     ch = pickle.load(open(out / 'chains.pkl', 'rb'))
     assert ch['W1'].shape == (2, S, L * T)
     assert (out / 'initial_chains.pkl').exists() and (out / 'input.yaml').exists() and (out / 'fit_summary.csv').exists()
+
+
+@pytest.mark.gpu
+def test_run_training_on_new_knots(tmp_path):
+    """A training run that defines its model on its own knots (``l_knots`` / ``tau_knots`` of the input, reference
+    :1721-1727): seven wavelength knots instead of T21's six - another kernel instantiation (L <= 9) - started from
+    T21 interpolated onto them; bayesn.yaml comes back on the new knots and loads as a model."""
+    import yaml
+    from bayesn_b200 import SEDmodel
+    m = SEDmodel(load_model='T21_model')
+    np.random.seed(6)
+    N = 10
+    z = np.random.uniform(0.02, 0.06, N)
+    d = tmp_path / 'SIMTRAIN'
+    m.simulate_light_curve(np.arange(-8, 36, 4.0), N, PS1, yerr=0.02, err_type='mag', z=z, mu='z', ebv_mw=0.01, mag=True,
+                           write_to_files=True, output_dir=str(d))
+    (d / 'SIMTRAIN.LIST').write_text('\n'.join(sorted(os.listdir(d))) + '\n')
+    lk = [3500.0, 4500.0, 5500.0, 6500.0, 7700.0, 8700.0, 9500.0]
+    out = tmp_path / 'out'
+    W, S = 30, 15
+    samples = m.run(dict(mode='training_globalRV', version_photometry=str(d), outputdir=str(out), num_warmup=W, num_samples=S,
+                         num_chains=2, initialisation='T21_model', l_knots=lk))
+    assert list(m.l_knots) == lk and samples['W0'].shape == (2, S, 42) and samples['sigmaepsilon'].shape == (2, S, 30)
+    assert np.all(np.isfinite(samples['W0'])) and np.all(np.isfinite(samples['theta']))
+    y = yaml.safe_load(open(out / 'bayesn.yaml'))
+    assert y['L_KNOTS'] == lk and np.array(y['W0']).shape == (7, 6) and np.array(y['L_SIGMA_EPSILON']).shape == (30, 30)
+    assert np.max(np.abs(np.array(y['W0']))) < 20 and (out / 'fit_summary.csv').exists()
+    y['RV'] = 2.6                                      # reference quirk: globalRV runs do not write RV (:2235)
+    path = tmp_path / 'trained.yaml'
+    path.write_text(yaml.safe_dump(y))
+    m2 = SEDmodel(load_model=str(path))
+    assert m2.W0.shape == (7, 6) and m2.n_eps == 30

@@ -604,3 +604,49 @@ def test_f99_ultraviolet_branch_lives_in_the_dust_table(tmp_path):
     from bayesn_b200.static import spline_matrix, inv_kd, F99_XK
     a_spline = 1 + (spline_matrix(1e4 / m.grid.model_wave, F99_XK, inv_kd(F99_XK)) @ f99_yk(np.float64(3.1))[0]) / 3.1
     assert np.max(np.abs(a_spline[:nuv] / a_prod[2, :nuv] - 1)) > 0.01
+
+
+def test_training_knots_from_input_and_mirror_methods(tmp_path):
+    """Training runs may set ``l_knots`` / ``tau_knots`` (reference :1721-1727): grids and tables are rebuilt, the
+    starting values are the reference model interpolated onto them (``initial_guess`` :1568-1654, same keys and the
+    same order of random draws); ``parse_yaml_input`` / ``spline_coeffs_irr_step`` exist on the model as in the reference."""
+    from bayesn_b200 import SEDmodel, driver
+    m = SEDmodel(load_model='T21_model')
+    d = tmp_path / 'PHOT'
+    d.mkdir()
+    _write_objects(d, m)
+    fmap = {'g': 'g_PS1', 'r': 'r_PS1', 'i': 'i_PS1', 'z': 'z_PS1'}
+    lk, tk = [3500.0, 4500.0, 5500.0, 6500.0, 7700.0, 8700.0, 9500.0], [-10.0, 0.0, 10.0, 20.0, 30.0, 40.0]
+    J_before = m.J_l_T.copy()
+    args = m.parse_yaml_input(dict(mode='training_globalRV', version_photometry=str(d), outputdir=str(tmp_path / 'o'), map=fmap,
+                                   l_knots=lk, tau_knots=tk))
+    assert list(m.l_knots) == lk and m.J_l_T.shape == (300, 7) and J_before.shape == (300, 6)
+    assert m.W0.shape == (7, 6) and m.L_Sigma.shape == (30, 30) and m.n_eps == 30
+    assert m.data.shape[0] == 10 and m.hsiao_interp.shape == (3,) + m.data.shape[1:]
+    np.random.seed(11)
+    init = m.initial_guess(args, reference_model='T21_model')
+    assert list(init.keys()) == ['W0', 'W1', 'RV', 'tauA_tform', 'sigma0_tform', 'sigma0', 'theta', 'AV', 'epsilon_tform',
+                                 'epsilon', 'sigmaepsilon_tform', 'sigmaepsilon', 'L_Omega', 'Ds']
+    N = m.data.shape[-1]
+    assert init['W0'].shape == (42,) and init['epsilon_tform'].shape == (30, N) and init['epsilon'].shape == (N, 30)
+    # the same seed replayed by hand in the reference's order reproduces the dictionary
+    from bayesn_b200 import datafiles
+    p = datafiles.load_model_yaml('T21_model')
+    np.random.seed(11)
+    tauA_ = float(p['TAUA']) + np.random.normal(0, 0.01)
+    sigma0_ = 0.1 + np.random.normal(0, 0.01)
+    j0, j1 = np.random.normal(0, 0.01, 42), np.random.normal(0, 0.01, 42)
+    theta = np.random.normal(0, 1, N)
+    AV = np.random.exponential(tauA_, N)
+    assert np.isclose(init['sigma0'], sigma0_) and np.array_equal(init['theta'], theta) and np.array_equal(init['AV'], AV)
+    W0 = np.array(p['W0'])
+    # interpolation onto the new wavelength knots keeps the values at knots shared with the reference model
+    assert np.allclose((init['W0'] - j0).reshape((7, 6), order='F')[[0, 6]], W0[[0, 5]])
+    with pytest.raises(ValueError, match='Invalid initialisation method'):
+        m.initial_guess(args, reference_model='no_such_model')
+    # unchanged knots: nothing is rebuilt
+    m2 = SEDmodel(load_model='T21_model')
+    a2 = driver.parse_yaml_input(m2, dict(mode='training_globalRV', version_photometry=str(d), outputdir=str(tmp_path / 'o')))
+    assert driver.apply_training_knots(m2, a2) is False
+    row = SEDmodel.spline_coeffs_irr_step(3.0, m2.tau_knots, m2.KD_t)
+    assert row.shape == (6,) and np.isclose(row.sum(), 1.0)
