@@ -304,3 +304,21 @@ def test_corr_cholesky_is_a_correlation_factor_with_numpyro_logdet():
     ii, jj = torch.tril_indices(n, n, -1)
     J = torch.autograd.functional.jacobian(lambda v: RefSED.corr_cholesky(v, n)[0][ii, jj], y)
     assert abs(float(torch.linalg.slogdet(J)[1]) - float(ld)) < 1e-10
+
+
+def test_reference_module_names_are_importable():
+    """``bayesn.spline_utils`` / ``bayesn.bayesn_io`` names of the reference (spline_utils.py:9-180, bayesn_io.py:13)
+    exist under ``bayesn_b200`` and agree with the oracle's restatement."""
+    from bayesn_b200.spline_utils import invKD_irr, spline_coeffs_irr, cartesian_prod, spline_coeffs_irr_step
+    from bayesn_b200.bayesn_io import write_snana_lcfile
+    from oracle.ref_model import invKD_irr as o_inv, spline_coeffs_irr as o_sp
+    x = np.array([0.0, 1.0, 2.5, 4.0, 7.0])
+    xi = np.linspace(-1, 8, 41)
+    assert np.allclose(invKD_irr(x), o_inv(x), atol=1e-14)
+    J = spline_coeffs_irr(xi, x, invKD_irr(x))
+    assert np.allclose(J, o_sp(xi, x, o_inv(x)), atol=1e-13)
+    assert np.allclose(spline_coeffs_irr_step(xi[7], x, invKD_irr(x)), J[7])
+    assert cartesian_prod([1, 2], [3, 4, 5]).tolist() == [[1, 3], [1, 4], [1, 5], [2, 3], [2, 4], [2, 5]]
+    with pytest.raises(ValueError, match='out of bounds'):
+        spline_coeffs_irr(xi, x, invKD_irr(x), allow_extrap=False)
+    assert callable(write_snana_lcfile)
