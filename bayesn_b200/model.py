@@ -238,8 +238,7 @@ class SEDmodel(object):
             sl = gather_rows(sl, N, group)           # device tensors: NCCL on GPUs
         samples = btrain.constrain(self, out['samples_g'].cpu().numpy(), sl.cpu().numpy())
         stats = out['stats'].cpu().numpy()
-        samples['potential_energy'] = stats[:, num_warmup:, 3]
-        extras = {'stats': stats, 'info': out['info'], 'passes': out['passes'], 'launches': ctx.launches()}
+        extras = {'potential_energy': stats[:, num_warmup:, 3], 'stats': stats, 'info': out['info'], 'passes': out['passes'], 'launches': ctx.launches()}
         if outputdir is not None and rank == 0:
             extras['yaml'], _ = btrain.postprocess_training(self, samples, outputdir, mode)
         return samples, extras
@@ -551,9 +550,12 @@ class SEDmodel(object):
         # the plate of a single-object fit keeps eps_tform as (chains, draws, 1, n_eps) (example_fits.ipynb:166-197);
         # the vmapped batch layout is (chains, draws, n_eps, N)
         samples['eps_tform'] = samples['eps_tform'].transpose(0, 1, 3, 2)
-        samples['potential_energy'] = extras['potential_energy'][..., 0]
+        # numpyro keeps extra fields out of get_samples(): like mcmc.get_extra_fields() they stay on the side
+        self.extra_fields = {'potential_energy': extras['potential_energy'][..., 0]}
         if print_summary:
-            summary.print_summary({k: v for k, v in samples.items() if k not in ('potential_energy', 'eps')},
+            # mcmc.print_summary() leaves deterministic sites out: eps, and R_V where it is a transform of RV_tform
+            det = {'eps'} | ({'RV'} if 'RV_tform' in samples else set())
+            summary.print_summary({k: v for k, v in samples.items() if k not in det},
                                   n_div=int((extras['chain_info'][..., 3]).sum()))
         if peak_mjd is not None:
             samples['peak_MJD'] = peak_mjd + samples['tmax'] * (1 + z)
