@@ -341,7 +341,12 @@ def summary_columns_t(x, hdi_prob=0.94):
         sp = _split_t(xd)
         e_mean = _ess_t(sp)
         e_sd = torch.minimum(e_mean, _ess_t(sp ** 2))
-        q = torch.quantile(flat, torch.tensor([0.05, 0.95], dtype=flat.dtype, device=flat.device), dim=1)     # (2, B)
+        def quant(p):                                              # numpy's default (linear) quantile, from the sorted rows
+            pos = p * (M - 1)
+            i0 = int(math.floor(pos))
+            i1 = min(i0 + 1, M - 1)
+            return srt[:, i0] + (pos - i0) * (srt[:, i1] - srt[:, i0])
+        q = [quant(0.05), quant(0.95)]
         e_tail = torch.minimum(*[_ess_t(_split_t((xd <= q[j][:, None, None]).double())) for j in range(2)])
         med = (srt[:, (M - 1) // 2] + srt[:, M // 2]) / 2
         rhat = torch.maximum(_rhat_t(_z_scale_t(sp)), _rhat_t(_z_scale_t((sp - med[:, None, None]).abs())))
