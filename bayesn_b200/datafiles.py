@@ -12,7 +12,6 @@ this image.  The layouts are fixed, so they are parsed directly:
 * model ``BAYESN.YAML`` and ``filters.yaml`` (reference ``:223-228``, ``:319-320``): PyYAML.
 """
 import os
-import struct
 
 import numpy as np
 import yaml

@@ -18,7 +18,7 @@ import time
 import numpy as np
 
 from . import datafiles, native, packing
-from .static import FilterSet, FlatLambdaCDM, ModelGrid, spline_row, HSIAO_PHASE0_INDEX, f99_yk
+from .static import FilterSet, FlatLambdaCDM, ModelGrid, spline_row, HSIAO_PHASE0_INDEX
 from . import snana, summary
 
 

@@ -1,9 +1,9 @@
 """Warm, back-to-back timing (CUDA events) of the stages of a training pass (fused reduction: SN kernel + first
 reduction stage | control kernel incl. the second stage).  usage: python scripts/train_kernel_times.py [N_sne ...]
 (N = 500: one GPU's C4; N = 63: a rank's shard of C4 on 8 GPUs, where the SN kernel runs in latency mode)"""
-import sys, numpy as np, torch, ctypes as C
+import sys, torch
 sys.path.insert(0, '.')
-from bayesn_b200 import SEDmodel, native, train as btrain
+from bayesn_b200 import SEDmodel, train as btrain
 m = SEDmodel(load_model='M20_model')
 for N in ([int(a) for a in sys.argv[1:]] or [500]):
   obs, weights, band_inds = btrain.simulate_training_set(m, N, seed=20241019)
