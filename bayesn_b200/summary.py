@@ -112,6 +112,8 @@ def _ess_chains(x):
     c, n = x.shape
     if n < 4 or not np.isfinite(x).all():
         return np.nan
+    if x.max() - x.min() < np.finfo(float).resolution:          # a constant site: every draw counts (as arviz does)
+        return float(c * n)
     acov = _autocov(x)
     mean_var = acov[:, 0].mean() * n / (n - 1.0)
     var_plus = mean_var * (n - 1.0) / n
@@ -277,6 +279,8 @@ def _ess_t(x):
     over the lags run for all rows at once."""
     import torch
     B, c, n = x.shape
+    if n < 4:
+        return torch.full((B,), float('nan'), dtype=x.dtype, device=x.device)
     m = 1 << int(math.ceil(math.log2(2 * n)))
     xc = x - x.mean(dim=-1, keepdim=True)
     f = torch.fft.rfft(xc, n=m, dim=-1)
@@ -317,8 +321,11 @@ def _ess_t(x):
     head = cs.gather(1, (max_t + 1).clamp(min=0)[:, None])[:, 0]                   # sum(rho[:max_t + 1])
     tau = -1.0 + 2.0 * head + rho.gather(1, idx)[:, 0]
     total = float(c * n)
-    tau = torch.clamp(tau, min=1.0 / math.log10(total))
-    return total / tau
+    ess = total / torch.clamp(tau, min=1.0 / math.log10(total))
+    flat = x.reshape(B, -1)
+    ess = torch.where(torch.isfinite(tau), ess, torch.full_like(ess, float('nan')))
+    const = flat.max(dim=1).values - flat.min(dim=1).values < torch.finfo(torch.float64).resolution
+    return torch.where(const, torch.full_like(ess, total), ess)
 
 
 def summary_columns_t(x, hdi_prob=0.94):
