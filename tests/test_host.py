@@ -650,3 +650,33 @@ def test_training_knots_from_input_and_mirror_methods(tmp_path):
     assert driver.apply_training_knots(m2, a2) is False
     row = SEDmodel.spline_coeffs_irr_step(3.0, m2.tau_knots, m2.KD_t)
     assert row.shape == (6,) and np.isclose(row.sum(), 1.0)
+
+
+def test_module_entry_point_mirrors_run_bayesn(tmp_path, monkeypatch):
+    """``python -m bayesn_b200 input.yaml --overrides``: the reference's ``run_bayesn`` script - default model T21,
+    command-line values override the YAML through ``parse_yaml_input`` (:1670-1679), a missing input file or data set
+    raises the reference's errors."""
+    import yaml
+    from bayesn_b200 import __main__ as cli, SEDmodel, driver
+    with pytest.raises(FileNotFoundError, match='Specified input file'):
+        cli.main([str(tmp_path / 'none.yaml')])
+    inp = tmp_path / 'input.yaml'
+    inp.write_text(yaml.safe_dump(dict(mode='fitting', num_chains=4, outputdir=str(tmp_path / 'out'))))
+    with pytest.raises(ValueError, match='Please pass either data_dir'):
+        cli.main([str(inp)])
+    seen = {}
+
+    def fake_run(self, args, cmd_args=None):
+        seen['model'] = self
+        seen['args'] = driver.parse_yaml_input(self, args, cmd_args)
+        return 'ran'
+    monkeypatch.setattr(SEDmodel, 'run', fake_run)
+    mapf = tmp_path / 'map.txt'
+    mapf.write_text('g g_PS1\nr r_PS1\n')
+    out = cli.main([str(inp), '--num_chains', '2', '--num_warmup', '10', '--jobsplit', '2', '5', '--map', str(mapf),
+                    '--drop_bands', 'z', 'y', '--load_model', 'M20_model', '--version_photometry', 'X'])
+    a = seen['args']
+    assert out == 'ran' and len(seen['model'].l_knots) == 9                  # M20 from the command line
+    assert a['num_chains'] == 2 and a['num_warmup'] == 10 and a['num_samples'] == 500 and a['jobsplit'] == [2, 5]
+    assert a['snana'] is True and a['jobid'] == 2 and a['njobtot'] == 5 and a['map'] == {'g': 'g_PS1', 'r': 'r_PS1'}
+    assert a['drop_bands'] == ['z', 'y'] and a['version_photometry'] == 'X' and a['outfile_prefix'] == 'output'
