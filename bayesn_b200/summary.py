@@ -328,12 +328,14 @@ def _ess_t(x):
     return torch.where(const, torch.full_like(ess, total), ess)
 
 
-def summary_columns_t(x, hdi_prob=0.94):
-    """x (B, chains, draws) torch tensor -> dict of (B,) float64 tensors with arviz.summary's nine columns."""
+def summary_columns_t(x, hdi_prob=0.94, device=None):
+    """x (B, chains, draws) torch tensor -> dict of (B,) float64 tensors with arviz.summary's nine columns.  Rows are
+    processed ``ROW_CHUNK`` at a time and only a chunk is moved to ``device`` (default: where ``x`` lives), so the
+    draws of a large run can stay in host memory."""
     import torch
     cols = {}
     for r0 in range(0, x.shape[0], ROW_CHUNK):
-        xd = x[r0:r0 + ROW_CHUNK].double()
+        xd = x[r0:r0 + ROW_CHUNK].to(device if device is not None else x.device).double()
         B = xd.shape[0]
         flat = xd.reshape(B, -1)
         M = flat.shape[1]
@@ -385,7 +387,7 @@ def summary_table(samples, hdi_prob=0.94, device=None):
     names = ['mean', 'sd', lo, hi, 'mcse_mean', 'mcse_sd', 'ess_bulk', 'ess_tail', 'r_hat']
     if not blocks:
         return pd.DataFrame(columns=names)
-    cols = summary_columns_t(torch.from_numpy(np.concatenate(blocks, axis=0)).to(device), hdi_prob)
+    cols = summary_columns_t(torch.from_numpy(np.concatenate(blocks, axis=0)), hdi_prob, device=device)
     keys = ['mean', 'sd', 'hdi_lo', 'hdi_hi', 'mcse_mean', 'mcse_sd', 'ess_bulk', 'ess_tail', 'r_hat']
     return pd.DataFrame({n: cols[k].cpu().numpy() for n, k in zip(names, keys)}, index=labels)
 
